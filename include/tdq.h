@@ -1,0 +1,231 @@
+/*
+ * tdq.h -- C ABI of libtdq (torchdiffeq_b200/csrc), the sm_100a implementation of the
+ * explicit Runge-Kutta hot path of rtqichen/torchdiffeq.
+ *
+ * Boundary rules:
+ *   - plain pointers and sizes only; no torch types.  Every `void *stream` is a cudaStream_t.
+ *   - the CALLER allocates every device buffer (state vectors, stage slots, partials, the control
+ *     block).  The library owns nothing but the mapped-host mailbox it hands out on request.
+ *   - every launcher is asynchronous and stream ordered, hence capturable into a CUDA graph.
+ *   - every entry point returns a tdq_status; tdq_last_error() gives the text for the calling thread.
+ *
+ * Each entry point names the reference code (file:line under torchdiffeq/_impl/) it replaces.
+ * The Python host (torchdiffeq_b200/) binds these with ctypes; INTEGRATION.md shows the binding a
+ * reference maintainer would add.
+ */
+#ifndef TDQ_H_
+#define TDQ_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TDQ_ABI_VERSION 1
+
+#define TDQ_MAX_STAGES 16            /* func evaluations per attempt, excluding f0 (dopri8: 13)   */
+#define TDQ_MAX_K      (TDQ_MAX_STAGES + 1) /* stage slots k_0 .. k_S                              */
+#define TDQ_MAX_SEGS   64            /* segments of a mixed (max-of-rms) norm                      */
+
+typedef enum {
+    TDQ_OK = 0,
+    TDQ_ERR_INVALID = 1,   /* bad argument (null pointer, unsupported dtype, too many stages ...)   */
+    TDQ_ERR_CUDA = 2,      /* a CUDA runtime call failed; see tdq_last_error()                     */
+    TDQ_ERR_UNSUPPORTED = 3
+} tdq_status;
+
+typedef enum { TDQ_F32 = 0, TDQ_F64 = 1 } tdq_dtype;
+
+/* Solver status word kept in the control block (device) and mirrored into the mailbox.
+ * Mirrors the three assertions of the reference's adaptive loop. */
+typedef enum {
+    TDQ_RUN_OK = 0,
+    TDQ_RUN_DT_UNDERFLOW = 1,   /* rk_common.py:286  assert t0 + dt > t0                          */
+    TDQ_RUN_NONFINITE = 2,      /* rk_common.py:287  assert isfinite(y0).all()                     */
+    TDQ_RUN_MAX_STEPS = 3       /* rk_common.py:247  assert n_steps < max_num_steps                */
+} tdq_run_status;
+
+/* Butcher tableau of an explicit embedded RK method, float64 as in the reference
+ * (rk_common.py:15 _ButcherTableau; dopri5.py:5-30; dopri8.py:5-70; tsit5.py, bosh3.py,
+ * fehlberg2.py, adaptive_heun.py).  beta is lower triangular: row i has i+1 entries. */
+typedef struct {
+    int32_t n_stages;                 /* S                                                          */
+    int32_t order;                    /* controller order (dopri5 5, dopri8 8)                      */
+    int32_t fsal;                     /* 1: y1 is the last stage value (rk_common.py:83 shortcut)   */
+    int32_t reserved;
+    double alpha[TDQ_MAX_STAGES];
+    double beta[TDQ_MAX_STAGES][TDQ_MAX_K];
+    double c_sol[TDQ_MAX_K];
+    double c_err[TDQ_MAX_K];
+    double c_mid[TDQ_MAX_K];
+} tdq_tableau;
+
+/* Adaptive-solver options; names and defaults follow RKAdaptiveStepsizeODESolver.__init__
+ * (rk_common.py:166-177). */
+typedef struct {
+    int32_t dtype;                    /* tdq_dtype of the state                                     */
+    int32_t ratio_f64;                /* 1: error ratio kept in float64 (vector tolerances)         */
+    double rtol, atol;                /* scalar tolerances (ignored by the vector-tol norm kernel)  */
+    double min_step, max_step;
+    double safety, ifactor, dfactor;
+    double t_sign;                    /* +1, or -1 when the caller integrates -t (misc.py:273-279): */
+                                      /* func sees t_sign*t and stage slots hold RAW func outputs;  */
+                                      /* the -1 of _ReverseFunc (misc.py:158-165) is folded into    */
+                                      /* every coefficient instead of a pass over f.                */
+    int64_t max_num_steps;            /* per output interval (rk_common.py:247)                     */
+    int64_t n_global;                 /* element count the RMS mean divides by (all ranks)          */
+} tdq_options;
+
+/* Mapped-host mailbox the controller kernel writes after every attempt; the host polls `seq`
+ * instead of synchronising the stream. */
+typedef struct {
+    volatile uint64_t seq;            /* attempts finished so far (written last)                    */
+    volatile int32_t status;          /* tdq_run_status                                             */
+    volatile int32_t accept;          /* last attempt accepted?                                     */
+    volatile int32_t done;            /* all requested output times emitted                         */
+    volatile int32_t out_cursor;      /* next output index to emit                                  */
+    volatile int64_t n_accept, n_reject;
+    volatile double t0, t1, dt;       /* last accepted interval and the next step size              */
+    volatile double ratio;            /* error ratio of the last attempt                            */
+    volatile double att_t0, att_dt;   /* start time and step size the last attempt used             */
+    volatile double next_t0, next_dt; /* the same for the attempt prepared next (callback_step)     */
+} tdq_mailbox;
+
+/* ---- library ------------------------------------------------------------------------------ */
+int tdq_abi_version(void);
+const char *tdq_last_error(void);
+/* Number of SMs of the current device (grid sizing). */
+int tdq_device_sm_count(int *out);
+
+/* Named tableaus: "dopri5", "dopri8", "tsit5", "bosh3", "fehlberg2", "adaptive_heun". */
+int tdq_tableau_get(const char *name, tdq_tableau *out);
+
+/* Mapped, pinned host memory for a mailbox (cudaHostAlloc mapped); dev_ptr is what kernels get. */
+int tdq_mailbox_create(tdq_mailbox **host_ptr, void **dev_ptr);
+int tdq_mailbox_destroy(tdq_mailbox *host_ptr);
+
+/* ---- control block ------------------------------------------------------------------------ */
+/* Size in bytes of the device control block, and offsets of the state-dtype scalars torch views
+ * alias as func's time argument: tstage[i] = time func sees at stage i (already perturbed and
+ * sign-corrected); taux[0] = time of f0, taux[1] = probe time of the initial-step heuristic. */
+size_t tdq_ctrl_size(void);
+size_t tdq_ctrl_tstage_offset(void);
+size_t tdq_ctrl_taux_offset(void);
+
+/* Fill the control block: tableau cast to the state dtype (rk_common.py:201-205), options, start
+ * time t_start = t[0], output times (device float64 array of n_out ascending values; misc.py:273-279
+ * negates for the caller; must stay alive for the solve).  Replaces
+ * RKAdaptiveStepsizeODESolver.__init__ (rk_common.py:166-205) and the scalar part of
+ * _before_integrate (:213-221).  Not capturable (host-to-device copy of the block). */
+int tdq_ctrl_init(void *ctrl_dev, const tdq_tableau *tab, const tdq_options *opt, const double *t_out_dev,
+                  double t_start, int32_t n_out, void *mailbox_dev, void *stream);
+
+/* Optional sorted step_t grid (device float64, values >= t[0]); rk_common.py:223-241, :293-300. */
+int tdq_ctrl_set_step_t(void *ctrl_dev, const double *step_t_dev, int32_t n, void *stream);
+
+/* ---- norms: deterministic segmented sum of squares ---------------------------------------- */
+/* Doubles the caller must provide (zero-initialised ONCE) as `partials` for the two reductions
+ * below, given the longest segment length and the segment count. */
+size_t tdq_norm_partials_len(size_t n_max_seg_len, int32_t n_seg);
+
+/* ---- initial step (misc.py:36-77 _select_initial_step) ------------------------------------ */
+/* out[s] = sum over segment s of (x/scale)^2 (or ((x - x2)/scale)^2 when x2 != NULL),
+ * scale = atol + |y0|*rtol (misc.py:55-58, :69); out[n_seg] unused (0).  seg_offsets/seg_lens are
+ * HOST arrays (NULL: one segment [0,n)).  rtol_vec/atol_vec: optional per-element float64. */
+int tdq_scaled_sumsq(void *ctrl_dev, int32_t dtype, const void *x, const void *x2, const void *y0,
+                     const double *rtol_vec, const double *atol_vec, const int64_t *seg_offsets,
+                     const int64_t *seg_lens, int32_t n_seg, size_t n, double *partials, double *out,
+                     void *stream);
+/* h0 from d0 = norm(y0/scale), d1 = norm(f0/scale) given as (all-reduced) segment sums; also sets
+ * taux[1] = probe time t0 + h0 (misc.py:60-67).  seg_counts_dev: GLOBAL element count per segment
+ * (device int64) or NULL for a single segment of options.n_global elements. */
+int tdq_initial_step_h0(void *ctrl_dev, int32_t dtype, const double *d0_sumsq, const double *d1_sumsq,
+                        const int64_t *seg_counts_dev, int32_t n_seg, void *stream);
+/* y_probe = y0 + h0*f0 (misc.py:66); f0 is the RAW func output (t_sign applied inside). */
+int tdq_initial_step_probe(void *ctrl_dev, int32_t dtype, void *y_probe, const void *y0, const void *f0,
+                           size_t n, void *stream);
+/* dt = min(100*h0, h1) from d2 = norm((f1 - f0)/scale)/h0 (misc.py:69-77). */
+int tdq_initial_step_finish(void *ctrl_dev, int32_t dtype, const double *d2_sumsq,
+                            const int64_t *seg_counts_dev, int32_t n_seg, void *stream);
+/* options['first_step'] (rk_common.py:218-219). */
+int tdq_set_first_step(void *ctrl_dev, double first_step, void *stream);
+
+/* ---- one adaptive attempt (rk_common.py:266-361 _adaptive_step) --------------------------- */
+/* Start-of-attempt scalar work: clamp dt, t1 = t0 + dt, step_t clipping, the dt-underflow and
+ * max_num_steps assertions, stage times t_i = T(t0) + alpha_i*T(dt) (or prev(T(t1)) when
+ * alpha_i == 1) and coefficients fl_T(beta_ij*T(dt)); rk_common.py:246-247, :269-308, :61-79, :89.
+ * tdq_controller already does this for attempt n+1, so the host calls it once per solve. */
+int tdq_prepare_attempt(void *ctrl_dev, int32_t dtype, void *stream);
+
+/* y_out = y0 + sum_j k_j * coef[row][j] over the non-zero tableau entries (rk_common.py:79, :85).
+ * row in [0, S): stage rows; row == S: the c_sol row of a non-FSAL tableau.  k[j] is stage slot j
+ * (RAW func output), NULL allowed where the tableau entry is zero.  `tab` only selects the
+ * sparsity pattern; coefficients come from the control block.  No-op once the solve has halted. */
+int tdq_stage_combine(void *ctrl_dev, const tdq_tableau *tab, int32_t dtype, int32_t row, void *y_out,
+                      const void *y0, const void *const *k, size_t n, void *stream);
+
+/* Embedded error + scaled squared norm (rk_common.py:89 + misc.py:80-82 + misc.py:22-23), fused:
+ * err = sum_j k_j*fl_T(dt*e_j); tol = atol + rtol*max(|y0|,|y1|); out[s] = sum over segment s of
+ * (err/tol)^2, out[n_seg] = number of non-finite y1 elements.  Segments (HOST arrays; NULL = one
+ * segment [0,n)) express the max-of-RMS norms of misc.py:30-33 and adjoint.py:247-271.
+ * err_over_tol_out, if non-NULL, receives err/tol (state dtype; float64 with vector tolerances)
+ * for callers with a custom norm callable. */
+int tdq_error_norm(void *ctrl_dev, const tdq_tableau *tab, int32_t dtype, const void *y0, const void *y1,
+                   const void *const *k, const double *rtol_vec, const double *atol_vec,
+                   const int64_t *seg_offsets, const int64_t *seg_lens, int32_t n_seg, size_t n,
+                   double *partials, double *out, void *err_over_tol_out, void *stream);
+
+/* Accept/reject, I-controller, bookkeeping, output cursor, the NEXT attempt's constants, mailbox
+ * (rk_common.py:323-361, misc.py:85-95, solvers.py:33-34, then :269-308 for the next attempt).
+ * norm_in: the (all-reduced) output of tdq_error_norm.  If ratio_dev != NULL (state dtype scalar,
+ * float64 when options.ratio_f64) the ratio is read from there instead (custom norm callable). */
+int tdq_controller(void *ctrl_dev, int32_t dtype, const double *norm_in, const int64_t *seg_counts_dev,
+                   int32_t n_seg, const void *ratio_dev, void *stream);
+
+/* On accept: y_mid and the quartic coefficients (rk_common.py:363-369, interp.py:1-22) and the
+ * state commit y0 <- y1, k[0] <- k[S] (rk_common.py:338-352), one pass.  No-op on reject.
+ * coeff[0..4] = e,d,c,b,a (state dtype). */
+int tdq_interp_fit_commit(void *ctrl_dev, const tdq_tableau *tab, int32_t dtype, void *y0, const void *y1,
+                          void *const *k, void *const *coeff, size_t n, void *stream);
+
+/* On accept: solution[j] for every requested t_j in (t0, t1] not yet emitted (interp.py:25-48 via
+ * rk_common.py:243-250 / solvers.py:28-35).  solution is [n_out, n] in the state dtype. */
+int tdq_interp_eval(void *ctrl_dev, int32_t dtype, const void *const *coeff, void *solution, size_t n,
+                    void *stream);
+/* Evaluate the current interpolant at one time (device float64 scalar) into out[n] (interp.py:25-48). */
+int tdq_interp_eval_at(void *ctrl_dev, int32_t dtype, const void *const *coeff, const double *t_dev, void *out,
+                       size_t n, void *stream);
+/* Reset the per-output-interval attempt counter (rk_common.py:245). */
+int tdq_ctrl_reset_interval(void *ctrl_dev, void *stream);
+
+/* ---- fixed grid RK4, 3/8 rule (fixed_grid.py:24-29, rk_common.py:110-118) ----------------- */
+/* which = 1: y0 + (dt*k1)*(1/3);  2: y0 + dt*(k2 - k1*(1/3));  3: y0 + dt*((k1 - k2) + k3);
+ * 4: y1 = y0 + ((k1 + 3*(k2 + k3)) + k4)*dt*0.125 (solvers.py:115).
+ * dt is dt_dev[step_dev[0]] (state dtype array, int64 device step counter; step_dev may be NULL for
+ * index 0) so that one captured graph serves every step of the grid. */
+int tdq_rk4_stage(int32_t dtype, int32_t which, void *y_out, const void *y0, const void *k1,
+                  const void *k2, const void *k3, const void *k4, const void *dt_dev,
+                  const int64_t *step_dev, size_t n, void *stream);
+/* End of one fixed-grid step (solvers.py:117-126, :175-181, linear interpolation): for every record r
+ * in [rec_begin[step], rec_begin[step+1]): solution[out_idx[r]] = y0 | y1 | y0 + slope[r]*(y1 - y0)
+ * for mode[r] = 0|1|2; then y0 <- y1, the step counter is incremented and the next step's four func
+ * times are copied from tstage_all[step+1][0..4) to tstage_cur[0..4) (state dtype; what func's time
+ * argument aliases). */
+int tdq_fixed_emit(int32_t dtype, void *y0, const void *y1, void *solution,
+                   const int32_t *rec_begin_dev, const int32_t *out_idx_dev, const int32_t *mode_dev,
+                   const void *slope_dev, int64_t *step_dev, const void *tstage_all_dev,
+                   void *tstage_cur_dev, int64_t n_steps, size_t n, void *stream);
+
+/* ---- adjoint augmented state (adjoint.py:72-105, misc.py:137-165) ------------------------- */
+/* dst[offset_i .. offset_i + len_i) = scale_i * src_i for i < n_src, one launch
+ * (the torch.cat of _TupleFunc, the unary minus on adj_y and the *(-1) of _ReverseFunc).
+ * src_i == NULL writes zeros (adjoint.py:100-103).  All arrays are HOST arrays. */
+int tdq_pack_segments(int32_t dtype, void *dst, const void *const *src, const int64_t *offsets,
+                      const int64_t *lens, const double *scales, int32_t n_src, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TDQ_H_ */

@@ -1,0 +1,382 @@
+"""CPU oracle for the explicit Runge-Kutta hot path of rtqichen/torchdiffeq.
+
+TEST INFRASTRUCTURE ONLY.  Nothing under torchdiffeq_b200/ imports this file; only tests/,
+__graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs do, and only as the
+checker or the CPU baseline, never as the thing measured or shipped.
+
+It is a plain restatement, on CPU torch tensors, of what the reference computes for this path
+(each function cites the reference lines it follows, relative to torchdiffeq/_impl/):
+
+    adaptive explicit RK step     rk_common.py:43-90, :266-361
+    error ratio / step controller misc.py:80-95
+    initial step                  misc.py:36-77
+    dense output                  interp.py:1-48, rk_common.py:363-369
+    fixed-grid RK4 (3/8 rule)     rk_common.py:110-118, fixed_grid.py:24-29, solvers.py:102-128, :175-181
+    adjoint backward              adjoint.py:36-153, :243-271
+
+Layout differs on purpose from the reference (stage derivatives are a list of separate arrays, not one
+[..., S+1] tensor; sums over stages run j = 0, 1, ... in order), which is also the order the CUDA
+kernels use.  Dtype rules are the reference's: times / dt / tolerances float64 scalars, everything
+elementwise in the state dtype T, coefficients rounded to T before use.
+
+PINNING: tests/test_oracle_golden.py checks this oracle against vectors produced by the unmodified
+reference (tests/golden/make_golden.py, run in the build container where /root/reference exists):
+solutions, accepted/rejected step counts, NFE and dt sequences.  Tableau coefficients are not restated
+here at all: they are read from tests/golden/tableaus.json, which that script dumped from the
+reference's own float64 tensors.
+"""
+import json
+import math
+import os
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_TABLEAUS = os.path.join(os.path.dirname(_HERE), "tests", "golden", "tableaus.json")
+_tab_cache = None
+
+
+def tableau(name):
+    """Float64 coefficients dumped from the reference (dopri5.py:5-36, dopri8.py:5-76, ...)."""
+    global _tab_cache
+    if _tab_cache is None:
+        with open(_TABLEAUS) as f:
+            _tab_cache = json.load(f)
+    return _tab_cache[name]
+
+
+def _real_dtype(y):
+    return y.abs().dtype                      # rk_common.py:61
+
+
+def rms(x):
+    """misc.py:22-23."""
+    return x.abs().pow(2).mean().sqrt()
+
+
+def mixed(parts):
+    """misc.py:30-33."""
+    if len(parts) == 0:
+        return 0.
+    return max([rms(p) for p in parts])
+
+
+class Counter:
+    """Wraps func to count evaluations (the reference's tests do this inside func, problems.py:41-44)."""
+
+    def __init__(self, func):
+        self.func, self.nfe = func, 0
+
+    def __call__(self, t, y):
+        self.nfe += 1
+        return self.func(t, y)
+
+
+# ------------------------------------------------------------------------------------------------
+# one adaptive attempt
+# ------------------------------------------------------------------------------------------------
+def _cast_tableau(tab, T):
+    """rk_common.py:201-205: coefficients are cast to the state dtype once."""
+    c = lambda v: torch.tensor(v, dtype=torch.float64).to(T)
+    return {
+        "alpha": c(tab["alpha"]), "beta": [c(b) for b in tab["beta"]], "c_sol": c(tab["c_sol"]),
+        "c_err": c(tab["c_err"]), "c_mid": c(tab["c_mid"]), "fsal": tab["fsal"], "order": tab["order"],
+    }
+
+
+def _prev(t):
+    return torch.nextafter(t, t - 1)          # misc.py:191-193 Perturb.PREV
+
+
+def _next(t):
+    return torch.nextafter(t, t + 1)          # misc.py:188-190 Perturb.NEXT
+
+
+def _weighted(ks, coefs):
+    """sum_j ks[j]*coefs[j] with a rounding after every product and every sum, j ascending, zero
+    weights skipped (they contribute exact zeros in the reference, rk_common.py:79)."""
+    acc = None
+    for kj, cj in zip(ks, coefs):
+        if float(cj) == 0.0:
+            continue
+        term = kj * cj
+        acc = term if acc is None else acc + term
+    return acc
+
+
+def rk_attempt(func, y0, f0, t0, dt, t1, ct):
+    """rk_common.py:43-90.  func(t, y) takes t in the state's real dtype.  Returns y1, f1, err, ks."""
+    T = _real_dtype(y0)
+    t0T, dtT, t1T = t0.to(T), dt.to(T), t1.to(T)                  # :61-65
+    ks = [f0]
+    yi = None
+    for a_i, b_i in zip(ct["alpha"], ct["beta"]):                 # :71-81
+        if a_i == 1.:
+            ti = _prev(t1T)
+        else:
+            ti = t0T + a_i * dtT
+        yi = y0 + _weighted(ks, b_i * dtT)                        # :79
+        ks.append(func(ti, yi))
+    if not ct["fsal"]:                                            # :83-85
+        yi = y0 + _weighted(ks, dtT * ct["c_sol"])
+    err = _weighted(ks, dtT * ct["c_err"])                        # :89
+    return yi, ks[-1], err, ks
+
+
+def error_ratio(err, rtol, atol, y0, y1, norm):
+    """misc.py:80-82."""
+    tol = atol + rtol * torch.max(y0.abs(), y1.abs())
+    return norm(err / tol).abs()
+
+
+def optimal_step(last, ratio, safety, ifactor, dfactor, order):
+    """misc.py:85-95 (float64)."""
+    if ratio == 0:
+        return last * ifactor
+    if ratio < 1:
+        dfactor = torch.ones((), dtype=last.dtype)
+    ratio = ratio.type_as(last)
+    expo = torch.tensor(order, dtype=last.dtype).reciprocal()
+    factor = torch.min(ifactor, torch.max(safety / ratio ** expo, dfactor))
+    return last * factor
+
+
+def initial_step(func, t0, y0, order, rtol, atol, norm, f0):
+    """misc.py:36-77; `order` is solver.order - 1 (rk_common.py:217).  One more func evaluation."""
+    T = y0.dtype
+    scale = atol + torch.abs(y0) * rtol
+    d0 = norm(y0 / scale).abs()
+    d1 = norm(f0 / scale).abs()
+    if d0 < 1e-5 or d1 < 1e-5:
+        h0 = torch.tensor(1e-6, dtype=T)
+    else:
+        h0 = 0.01 * d0 / d1
+    h0 = h0.abs()
+    y1 = y0 + h0 * f0
+    f1 = func((t0 + h0).to(_real_dtype(y0)), y1)
+    d2 = torch.abs(norm((f1 - f0) / scale) / h0)
+    if d1 <= 1e-15 and d2 <= 1e-15:
+        h1 = torch.max(torch.tensor(1e-6, dtype=T), h0 * 1e-3)
+    else:
+        h1 = (0.01 / max(d1, d2)) ** (1. / float(order + 1))
+    h1 = h1.abs()
+    return torch.min(100 * h0, h1).to(t0.dtype)
+
+
+def interp_fit(y0, y1, ks, dt, ct):
+    """rk_common.py:363-369 + interp.py:1-22: [e, d, c, b, a]."""
+    dt = dt.type_as(y0)
+    y_mid = y0 + _weighted(ks, dt * ct["c_mid"])
+    f0, f1 = ks[0], ks[-1]
+    a = 2 * dt * (f1 - f0) - 8 * (y1 + y0) + 16 * y_mid
+    b = dt * (5 * f0 - 3 * f1) + 18 * y0 + 14 * y1 - 32 * y_mid
+    c = dt * (f1 - 4 * f0) - 11 * y0 - 5 * y1 + 16 * y_mid
+    d = dt * f0
+    return [y0, d, c, b, a]
+
+
+def interp_eval(coeffs, t0, t1, t):
+    """interp.py:25-48."""
+    assert (t0 <= t) & (t <= t1)
+    x = ((t - t0) / (t1 - t0)).to(coeffs[0].dtype)
+    total = coeffs[0] + x * coeffs[1]
+    xp = x
+    for c in coeffs[2:]:
+        xp = xp * x
+        total = total + xp * c
+    return total
+
+
+# ------------------------------------------------------------------------------------------------
+# adaptive driver
+# ------------------------------------------------------------------------------------------------
+def odeint_adaptive(func, y0, t, method="dopri5", rtol=1e-7, atol=1e-9, norm=rms, min_step=0.,
+                    max_step=float("inf"), first_step=None, step_t=None, safety=0.9, ifactor=10.0,
+                    dfactor=0.2, max_num_steps=2 ** 31 - 1, record=None):
+    """solvers.py:28-35 + rk_common.py:213-361 for a flat or shaped tensor state and ascending or
+    descending t.  Returns solution [len(t), *y0.shape].  `record`, if a dict, receives
+    n_accept, n_reject, dts (attempted step sizes), accepted (flags)."""
+    f64 = torch.float64
+    tab = tableau(method)
+    ct = _cast_tableau(tab, y0.dtype)
+    sign = 1.0
+    if len(t) > 1 and t[0] > t[1]:                                  # misc.py:270-279
+        sign = -1.0
+        t = -t
+        if step_t is not None:
+            step_t = -step_t
+    user = func
+    if sign < 0:
+        func = lambda tt, yy: -1.0 * user(-tt, yy)                  # misc.py:158-165
+    t = t.to(f64)
+    as64 = lambda v: torch.as_tensor(v, dtype=f64)
+    rtol, atol = as64(rtol), as64(atol)                             # rk_common.py:186-187
+    min_step, max_step, safety, ifactor, dfactor = map(as64, (min_step, max_step, safety, ifactor, dfactor))
+    solution = torch.empty(len(t), *y0.shape, dtype=y0.dtype)
+    solution[0] = y0
+    T = _real_dtype(y0)
+
+    f0 = func(t[0].to(T), y0)                                       # rk_common.py:215
+    if first_step is None:
+        dt = initial_step(func, t[0], y0, tab["order"] - 1, rtol, atol, norm, f0)
+    else:
+        dt = as64(first_step)
+    if step_t is None:
+        step_t = torch.tensor([], dtype=f64)
+    else:
+        step_t = torch.sort(as64(step_t)[as64(step_t) >= t[0]]).values   # rk_common.py:372-375
+    import bisect
+    next_step = min(bisect.bisect(step_t.tolist(), t[0]), len(step_t) - 1)   # :240
+    y, f, t_lo, t_hi = y0, f0, t[0], t[0]
+    coeffs = [y0] * 5
+    stats = {"n_accept": 0, "n_reject": 0, "dts": [], "accepted": []}
+    for i in range(1, len(t)):
+        n_steps = 0
+        while t[i] > t_hi:                                          # rk_common.py:246
+            assert n_steps < max_num_steps, 'max_num_steps exceeded ({}>={})'.format(n_steps, max_num_steps)
+            # ---- rk_common.py:266-361 ----
+            if not torch.isfinite(dt):
+                dt = min_step
+            dt = dt.clamp(min_step, max_step)
+            a0 = t_hi
+            a1 = a0 + dt
+            assert a0 + dt > a0, 'underflow in dt {}'.format(dt.item())
+            assert torch.isfinite(y).all(), 'non-finite values in state `y`: {}'.format(y)
+            on_step_t = False
+            if len(step_t):
+                nxt = step_t[next_step]
+                on_step_t = bool(a0 < nxt < a0 + dt)
+                if on_step_t:
+                    a1 = nxt
+                    dt = a1 - a0
+            y1, f1, err, ks = rk_attempt(func, y, f, a0, dt, a1, ct)
+            ratio = error_ratio(err, rtol, atol, y, y1, norm)
+            accept = bool(ratio <= 1)
+            if dt > max_step:
+                accept = False
+            if dt <= min_step:
+                accept = True
+            stats["dts"].append(float(dt))
+            stats["accepted"].append(accept)
+            if accept:
+                coeffs = interp_fit(y, y1, ks, dt, ct)
+                if on_step_t and next_step != len(step_t) - 1:
+                    next_step += 1
+                y, f, t_lo, t_hi = y1, f1, a0, a1
+                stats["n_accept"] += 1
+            else:
+                t_lo, t_hi = a0, a0
+                stats["n_reject"] += 1
+            dt = optimal_step(dt, ratio, safety, ifactor, dfactor, tab["order"]).clamp(min_step, max_step)
+            n_steps += 1
+        solution[i] = interp_eval(coeffs, t_lo, t_hi, t[i])         # rk_common.py:250
+    if record is not None:
+        record.update(stats)
+    return solution
+
+
+# ------------------------------------------------------------------------------------------------
+# fixed-grid RK4, 3/8 rule
+# ------------------------------------------------------------------------------------------------
+_ONE_THIRD, _TWO_THIRDS = 1 / 3, 2 / 3
+
+
+def rk4_increment(func, t0, dt, t1, y0, perturb=False):
+    """fixed_grid.py:27-29 + rk_common.py:110-118.  Returns dy."""
+    T = _real_dtype(y0)
+    cast = lambda tt: tt.to(T)
+    k1 = func(_next(cast(t0)) if perturb else cast(t0), y0)
+    k2 = func(cast(t0 + dt * _ONE_THIRD), y0 + dt * k1 * _ONE_THIRD)
+    k3 = func(cast(t0 + dt * _TWO_THIRDS), y0 + dt * (k2 - k1 * _ONE_THIRD))
+    k4 = func(_prev(cast(t1)) if perturb else cast(t1), y0 + dt * (k1 - k2 + k3))
+    return (k1 + 3 * (k2 + k3) + k4) * dt * 0.125
+
+
+def odeint_rk4(func, y0, t, grid=None, perturb=False):
+    """solvers.py:102-128 with linear interpolation (:175-181).  t keeps its own dtype (no float64 cast)."""
+    sign = 1.0
+    if len(t) > 1 and t[0] > t[1]:
+        sign = -1.0
+        t = -t
+        if grid is not None:
+            grid = -grid
+    user = func
+    if sign < 0:
+        func = lambda tt, yy: -1.0 * user(-tt, yy)
+    grid = t if grid is None else grid
+    assert grid[0] == t[0] and grid[-1] == t[-1]
+    solution = torch.empty(len(t), *y0.shape, dtype=y0.dtype)
+    solution[0] = y0
+    j, y = 1, y0
+    for t0, t1 in zip(grid[:-1], grid[1:]):
+        dt = t1 - t0
+        y1 = y + rk4_increment(func, t0, dt, t1, y, perturb)
+        while j < len(t) and t1 >= t[j]:
+            if t[j] == t0:
+                solution[j] = y
+            elif t[j] == t1:
+                solution[j] = y1
+            else:
+                solution[j] = y + ((t[j] - t0) / (t1 - t0)) * (y1 - y)
+            j += 1
+        y = y1
+    return solution
+
+
+# ------------------------------------------------------------------------------------------------
+# adjoint backward (adjoint.py:36-153) for a tensor state
+# ------------------------------------------------------------------------------------------------
+def adjoint_gradients(func, params, y0, t, grad_y, method="dopri5", rtol=1e-7, atol=1e-9,
+                      adjoint_rtol=None, adjoint_atol=None, seminorm=False, record=None):
+    """Solve forward with odeint_adaptive, then the augmented system backwards interval by interval.
+    grad_y: dL/dy at every output time, [len(t), *y0.shape].  Returns (solution, dL/dy0, [dL/dparam])."""
+    adjoint_rtol = rtol if adjoint_rtol is None else adjoint_rtol
+    adjoint_atol = atol if adjoint_atol is None else adjoint_atol
+    params = tuple(params)
+    with torch.no_grad():
+        ys = odeint_adaptive(func, y0, t, method, rtol, atol)
+    shape, n = y0.shape, y0.numel()
+    sizes = [1, n, n] + [p.numel() for p in params]
+    bounds = [0]
+    for s in sizes:
+        bounds.append(bounds[-1] + s)
+
+    def split(v):
+        return [v[bounds[i]:bounds[i + 1]] for i in range(len(sizes))]
+
+    def aug_dynamics(tt, v):                                        # adjoint.py:72-105 (flat in/out, misc.py:137-145)
+        parts = split(v)
+        yv, adj = parts[1].view(shape), parts[2].view(shape)
+        with torch.enable_grad():
+            yv = yv.detach().requires_grad_(True)
+            fe = func(tt.detach(), yv)
+            grads = torch.autograd.grad(fe, (yv,) + params, -adj, allow_unused=True)
+        vjp_y = torch.zeros_like(yv) if grads[0] is None else grads[0]
+        vjp_p = [torch.zeros_like(p) if g is None else g for p, g in zip(params, grads[1:])]
+        return torch.cat([torch.zeros(1, dtype=v.dtype), fe.detach().reshape(-1), vjp_y.reshape(-1)] +
+                         [g.reshape(-1) for g in vjp_p])
+
+    def aug_norm(q):                                                # adjoint.py:247-250, :267-271
+        parts = split(q)
+        vals = [parts[0].abs().max(), rms(parts[1]), rms(parts[2])]
+        if not seminorm and len(parts) > 3:
+            vals.append(mixed(parts[3:]))
+        return max(vals)
+
+    with torch.no_grad():
+        aug = torch.cat([torch.zeros(1, dtype=y0.dtype), ys[-1].reshape(-1), grad_y[-1].reshape(-1)] +
+                        [torch.zeros(p.numel(), dtype=y0.dtype) for p in params])
+        nfe = 0
+        for i in range(len(t) - 1, 0, -1):                          # adjoint.py:124-141
+            cf = Counter(aug_dynamics)
+            rec = {}
+            out = odeint_adaptive(cf, aug, t[i - 1:i + 1].flip(0), method, adjoint_rtol, adjoint_atol,
+                                  norm=aug_norm, record=rec)
+            nfe += cf.nfe
+            aug = out[1].clone()
+            aug[bounds[1]:bounds[2]] = ys[i - 1].reshape(-1)
+            aug[bounds[2]:bounds[3]] += grad_y[i - 1].reshape(-1)
+        parts = split(aug)
+    if record is not None:
+        record["backward_nfe"] = nfe
+    return ys, parts[2].view(shape), [g.view(p.shape) for g, p in zip(parts[3:], params)]

@@ -1,0 +1,195 @@
+"""Generate the golden vectors under tests/golden/ from the UNMODIFIED reference.
+
+Run in the build container, where the reference lives at /root/reference (it does not exist on the GPU
+box, so nothing else may import it):
+
+    python tests/golden/make_golden.py
+
+Outputs (committed):
+    tableaus.json         float64 coefficients of the reference's own tableau tensors
+    zoo.pt                reference solutions + NFE for the analytic problem zoo (tests/problems.py)
+    linear_batch.pt       C2-shaped batched linear ODE at a small batch: solution, dt sequence, accept flags
+    spiral_rk4.pt         C1: rk4 on the cubic spiral, B=1024, selected output rows
+    adjoint_mlp.pt        odeint_adjoint gradients for a small MLP field
+    detest.pt             DETEST classes A/B: NFE and end states at rtol=atol in {1e-3, 1e-6, 1e-9}
+    options.pt            step_t / min_step / max_step / first_step / tuple-state / vector-tol cases
+"""
+import json
+import os
+import sys
+
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, "/root/reference")
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+import torchdiffeq                                   # noqa: E402  (the reference)
+from torchdiffeq._impl import adaptive_heun, bosh3, dopri5, dopri8, fehlberg2   # noqa: E402
+import problems as P                                 # noqa: E402
+
+assert torchdiffeq.__file__.startswith("/root/reference"), torchdiffeq.__file__
+torch.set_num_threads(8)
+
+
+class Rec(torch.nn.Module):
+    """Counts NFE and records the accepted/rejected dt sequence through the reference's callbacks."""
+
+    def __init__(self, f):
+        super().__init__()
+        self.f, self.nfe, self.dts, self.acc = f, 0, [], []
+
+    def forward(self, t, y):
+        self.nfe += 1
+        return self.f(t, y)
+
+    def callback_accept_step(self, t0, y0, dt):
+        self.dts.append(float(dt)); self.acc.append(True)
+
+    def callback_reject_step(self, t0, y0, dt):
+        self.dts.append(float(dt)); self.acc.append(False)
+
+
+def dump_tableaus():
+    out = {}
+    for name, cls in [("dopri5", dopri5.Dopri5Solver), ("dopri8", dopri8.Dopri8Solver), ("bosh3", bosh3.Bosh3Solver),
+                      ("fehlberg2", fehlberg2.Fehlberg2), ("adaptive_heun", adaptive_heun.AdaptiveHeunSolver)]:
+        tab = cls.tableau
+        fsal = bool(tab.c_sol[-1] == 0 and (tab.c_sol[:-1] == tab.beta[-1]).all())     # rk_common.py:83
+        out[name] = {"alpha": tab.alpha.tolist(), "beta": [b.tolist() for b in tab.beta], "c_sol": tab.c_sol.tolist(),
+                     "c_err": tab.c_error.tolist(), "c_mid": cls.mid.tolist(), "order": cls.order, "fsal": fsal,
+                     "n_stages": len(tab.alpha)}
+    with open(os.path.join(HERE, "tableaus.json"), "w") as f:
+        json.dump(out, f, indent=1)
+
+
+def zoo():
+    # the matrix construction must agree with the reference's LinearODE (problems.py:35-38)
+    sys.path.insert(0, "/root/reference/tests")
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("ref_problems", "/root/reference/tests/problems.py")
+    refp = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(refp)
+    assert torch.equal(refp.LinearODE().A.detach(), P.LinearODE().A.detach())
+    cases = {}
+    for ode in ("constant", "sine", "linear", "exp"):
+        for method in ("dopri5", "dopri8", "bosh3", "fehlberg2", "adaptive_heun", "rk4"):
+            for dtype in (torch.float32, torch.float64):
+                for reverse in (False, True):
+                    if method == "rk4" and ode != "constant":
+                        continue
+                    f, y0, t, sol = P.construct_problem("cpu", ode=ode, reverse=reverse, dtype=dtype)
+                    if method == "dopri8":                         # odeint_tests.py:29-32
+                        kw = dict(rtol=1e-12, atol=1e-14) if dtype == torch.float64 else dict(rtol=1e-7, atol=1e-7)
+                    else:
+                        kw = {}
+                    rec = Rec(f)
+                    with torch.no_grad():
+                        y = torchdiffeq.odeint(rec, y0, t, method=method, **kw)
+                    key = "%s/%s/%s/%s" % (ode, method, str(dtype).split(".")[1], "rev" if reverse else "fwd")
+                    cases[key] = {"y": y, "nfe": rec.nfe, "dts": rec.dts, "acc": rec.acc, "kw": kw, "exact": sol}
+    torch.save(cases, os.path.join(HERE, "zoo.pt"))
+
+
+def linear_batch():
+    out = {}
+    for dtype in (torch.float32, torch.float64):
+        f = P.BatchedLinear(128, dtype)
+        g = torch.Generator().manual_seed(1)
+        y0 = torch.randn(64, 128, generator=g).to(dtype)
+        for name, t in (("span", torch.tensor([0., 2.])), ("dense", torch.linspace(0, 2, 9))):
+            rec = Rec(f)
+            with torch.no_grad():
+                y = torchdiffeq.odeint(rec, y0, t, method="dopri5", rtol=1e-5, atol=1e-7)
+            out["%s/%s" % (name, str(dtype).split(".")[1])] = {"y": y, "nfe": rec.nfe, "dts": rec.dts, "acc": rec.acc,
+                                                              "t": t}
+    torch.save(out, os.path.join(HERE, "linear_batch.pt"))
+
+
+def spiral_rk4():
+    f = P.Spiral()
+    g = torch.Generator().manual_seed(0)
+    y0 = torch.tensor([[2., 0.]]) * (1 + 0.1 * torch.rand(1024, 1, generator=g))
+    t = torch.linspace(0., 25., 1000)
+    with torch.no_grad():
+        y = torchdiffeq.odeint(f, y0, t, method="rk4")
+        # a coarser output grid on a fine step_size grid exercises the linear interpolation
+        t2 = torch.linspace(0., 5., 7)
+        y2 = torchdiffeq.odeint(f, y0[:16], t2, method="rk4", options={"step_size": 0.03})
+    rows = [0, 1, 2, 10, 100, 500, 998, 999]
+    torch.save({"y0": y0, "rows": rows, "y_rows": y[rows].clone(), "t2": t2, "y2": y2},
+               os.path.join(HERE, "spiral_rk4.pt"))
+
+
+def adjoint_mlp():
+    out = {}
+    for dtype in (torch.float32, torch.float64):
+        f = P.MLPField(dim=8, hidden=16, seed=0, dtype=dtype)
+        g = torch.Generator().manual_seed(1)
+        y0 = torch.randn(32, 8, generator=g).to(dtype).requires_grad_(True)
+        for name, t in (("span", torch.tensor([0., 1.])), ("multi", torch.tensor([0., 0.4, 1.0]))):
+            for norm in ("default", "seminorm"):
+                f.zero_grad()
+                y0.grad = None
+                ao = {"norm": "seminorm"} if norm == "seminorm" else None
+                y = torchdiffeq.odeint_adjoint(f, y0, t, method="dopri5", rtol=1e-6, atol=1e-8, adjoint_options=ao)
+                loss = y[-1].pow(2).mean() + (y[1].sum() * 0.01 if len(t) > 2 else 0)
+                loss.backward()
+                out["%s/%s/%s" % (name, norm, str(dtype).split(".")[1])] = {
+                    "y": y.detach().clone(), "gy0": y0.grad.clone(), "gp": [q.grad.clone() for q in f.parameters()],
+                    "t": t}
+    torch.save(out, os.path.join(HERE, "adjoint_mlp.pt"))
+
+
+def detest():
+    out = {}
+    for name in P.DETEST_NAMES:
+        f, y0, t0 = P.detest(name)
+        y0 = torch.tensor(y0, dtype=torch.float64)
+        if name.startswith("A"):
+            y0 = y0[0]
+        t = torch.tensor([t0, 20.0], dtype=torch.float64)
+        for method in ("dopri5", "dopri8"):
+            for tol in (1e-3, 1e-6, 1e-9):
+                rec = Rec(f)
+                with torch.no_grad():
+                    y = torchdiffeq.odeint(rec, y0, t, method=method, rtol=tol, atol=tol)
+                out["%s/%s/%g" % (name, method, tol)] = {"y": y[-1].clone(), "nfe": rec.nfe}
+    torch.save(out, os.path.join(HERE, "detest.pt"))
+
+
+def options_cases():
+    out = {}
+    f, y0, t, _ = P.construct_problem("cpu", ode="linear", dtype=torch.float64)
+    for key, opts in (("min_step", {"min_step": 2}), ("max_step", {"max_step": 0.05}), ("first_step", {"first_step": 0.01}),
+                      ("step_t", {"step_t": torch.tensor([1.5, 2.25, 6.0])}), ("factors", {"safety": 0.8, "ifactor": 5.0, "dfactor": 0.3})):
+        rec = Rec(f)
+        with torch.no_grad():
+            y = torchdiffeq.odeint(rec, y0, t, method="dopri5", options=dict(opts))
+        out[key] = {"y": y, "nfe": rec.nfe, "dts": rec.dts, "acc": rec.acc, "opts": opts}
+    # tuple state with per-piece tolerances (misc.py:115-123) and the mixed norm (misc.py:30-33)
+    A = P.skew_matrix(6, torch.float64)
+    def tf(t_, state):
+        a, b = state
+        return (a @ A.t(), -0.5 * b + a[:, :2].sum())
+    g = torch.Generator().manual_seed(3)
+    ya, yb = torch.randn(5, 6, generator=g, dtype=torch.float64), torch.randn(3, generator=g, dtype=torch.float64)
+    tt = torch.linspace(0, 2, 5, dtype=torch.float64)
+    with torch.no_grad():
+        sol = torchdiffeq.odeint(tf, (ya, yb), tt, method="dopri5", rtol=1e-6, atol=1e-8)
+        sol_v = torchdiffeq.odeint(tf, (ya, yb), tt, method="dopri5", rtol=(1e-6, 1e-4), atol=(1e-8, 1e-7))
+    out["tuple"] = {"ya": ya, "yb": yb, "t": tt, "sol": [s.clone() for s in sol], "sol_vtol": [s.clone() for s in sol_v]}
+    torch.save(out, os.path.join(HERE, "options.pt"))
+
+
+if __name__ == "__main__":
+    dump_tableaus()
+    zoo()
+    linear_batch()
+    spiral_rk4()
+    adjoint_mlp()
+    detest()
+    options_cases()
+    for fn in sorted(os.listdir(HERE)):
+        print(fn, os.path.getsize(os.path.join(HERE, fn)))

@@ -1,0 +1,12 @@
+"""torchdiffeq_b200 -- a B200-native (sm_100a) implementation of torchdiffeq's explicit Runge-Kutta
+hot path behind the reference's own API: odeint / odeint_adjoint(func, y0, t, method=, rtol=, atol=).
+
+Importing the package does not need a GPU; calling a solver does, and fails loudly when libtdq.so is
+missing -- there is no CPU or PyTorch fallback."""
+from .odeint import odeint
+from .adjoint import odeint_adjoint, find_parameters
+from ._engine import SolverFailure
+from ._lib import TdqError
+
+__version__ = "0.1.0"
+__all__ = ["odeint", "odeint_adjoint", "find_parameters", "SolverFailure", "TdqError"]

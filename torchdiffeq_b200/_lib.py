@@ -1,0 +1,158 @@
+"""ctypes binding of libtdq.so (include/tdq.h).  The library is the product: if it is missing or does
+not load, every solver entry point raises -- there is no CPU or PyTorch fallback."""
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "csrc", "libtdq.so")
+
+TDQ_MAX_STAGES = 16
+TDQ_MAX_K = TDQ_MAX_STAGES + 1
+TDQ_MAX_SEGS = 64
+TDQ_F32, TDQ_F64 = 0, 1
+RUN_OK, RUN_DT_UNDERFLOW, RUN_NONFINITE, RUN_MAX_STEPS = 0, 1, 2, 3
+
+
+class Tableau(C.Structure):
+    _fields_ = [
+        ("n_stages", C.c_int32), ("order", C.c_int32), ("fsal", C.c_int32), ("reserved", C.c_int32),
+        ("alpha", C.c_double * TDQ_MAX_STAGES),
+        ("beta", (C.c_double * TDQ_MAX_K) * TDQ_MAX_STAGES),
+        ("c_sol", C.c_double * TDQ_MAX_K),
+        ("c_err", C.c_double * TDQ_MAX_K),
+        ("c_mid", C.c_double * TDQ_MAX_K),
+    ]
+
+
+class Options(C.Structure):
+    _fields_ = [
+        ("dtype", C.c_int32), ("ratio_f64", C.c_int32),
+        ("rtol", C.c_double), ("atol", C.c_double),
+        ("min_step", C.c_double), ("max_step", C.c_double),
+        ("safety", C.c_double), ("ifactor", C.c_double), ("dfactor", C.c_double),
+        ("t_sign", C.c_double),
+        ("max_num_steps", C.c_int64), ("n_global", C.c_int64),
+    ]
+
+
+class Mailbox(C.Structure):
+    _fields_ = [
+        ("seq", C.c_uint64),
+        ("status", C.c_int32), ("accept", C.c_int32), ("done", C.c_int32), ("out_cursor", C.c_int32),
+        ("n_accept", C.c_int64), ("n_reject", C.c_int64),
+        ("t0", C.c_double), ("t1", C.c_double), ("dt", C.c_double),
+        ("ratio", C.c_double), ("att_t0", C.c_double), ("att_dt", C.c_double),
+        ("next_t0", C.c_double), ("next_dt", C.c_double),
+    ]
+
+
+class TdqError(RuntimeError):
+    pass
+
+
+_vp, _i32, _i64, _sz, _dbl = C.c_void_p, C.c_int32, C.c_int64, C.c_size_t, C.c_double
+_pp = C.POINTER(C.c_void_p)
+_pi64 = C.POINTER(C.c_int64)
+_pdbl = C.POINTER(C.c_double)
+_ptab = C.POINTER(Tableau)
+
+# name -> (restype, argtypes); mirrors include/tdq.h one to one
+_SIGNATURES = {
+    "tdq_abi_version": (C.c_int, []),
+    "tdq_last_error": (C.c_char_p, []),
+    "tdq_device_sm_count": (C.c_int, [C.POINTER(C.c_int)]),
+    "tdq_tableau_get": (C.c_int, [C.c_char_p, _ptab]),
+    "tdq_mailbox_create": (C.c_int, [C.POINTER(C.POINTER(Mailbox)), _pp]),
+    "tdq_mailbox_destroy": (C.c_int, [C.POINTER(Mailbox)]),
+    "tdq_ctrl_size": (_sz, []),
+    "tdq_ctrl_tstage_offset": (_sz, []),
+    "tdq_ctrl_taux_offset": (_sz, []),
+    "tdq_ctrl_init": (C.c_int, [_vp, _ptab, C.POINTER(Options), _vp, _dbl, _i32, _vp, _vp]),
+    "tdq_ctrl_set_step_t": (C.c_int, [_vp, _vp, _i32, _vp]),
+    "tdq_norm_partials_len": (_sz, [_sz, _i32]),
+    "tdq_scaled_sumsq": (C.c_int, [_vp, _i32, _vp, _vp, _vp, _vp, _vp, _pi64, _pi64, _i32, _sz, _vp, _vp, _vp]),
+    "tdq_initial_step_h0": (C.c_int, [_vp, _i32, _vp, _vp, _vp, _i32, _vp]),
+    "tdq_initial_step_probe": (C.c_int, [_vp, _i32, _vp, _vp, _vp, _sz, _vp]),
+    "tdq_initial_step_finish": (C.c_int, [_vp, _i32, _vp, _vp, _i32, _vp]),
+    "tdq_set_first_step": (C.c_int, [_vp, _dbl, _vp]),
+    "tdq_prepare_attempt": (C.c_int, [_vp, _i32, _vp]),
+    "tdq_stage_combine": (C.c_int, [_vp, _ptab, _i32, _i32, _vp, _vp, _pp, _sz, _vp]),
+    "tdq_error_norm": (C.c_int, [_vp, _ptab, _i32, _vp, _vp, _pp, _vp, _vp, _pi64, _pi64, _i32, _sz, _vp, _vp, _vp, _vp]),
+    "tdq_controller": (C.c_int, [_vp, _i32, _vp, _vp, _i32, _vp, _vp]),
+    "tdq_interp_fit_commit": (C.c_int, [_vp, _ptab, _i32, _vp, _vp, _pp, _pp, _sz, _vp]),
+    "tdq_interp_eval": (C.c_int, [_vp, _i32, _pp, _vp, _sz, _vp]),
+    "tdq_interp_eval_at": (C.c_int, [_vp, _i32, _pp, _vp, _vp, _sz, _vp]),
+    "tdq_ctrl_reset_interval": (C.c_int, [_vp, _vp]),
+    "tdq_rk4_stage": (C.c_int, [_i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "tdq_fixed_emit": (C.c_int, [_i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _sz, _vp]),
+    "tdq_pack_segments": (C.c_int, [_i32, _vp, _pp, _pi64, _pi64, _pdbl, _i32, _vp]),
+}
+
+EXPORTED_SYMBOLS = tuple(_SIGNATURES)
+
+_lib = None
+
+
+def load():
+    """Load libtdq.so once; raises TdqError (never falls back) when it is absent or stale."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise TdqError(
+            "libtdq.so is not built (%s). Run `python -m torchdiffeq_b200.csrc.build` "
+            "(or __graft_entry__.build()); there is no fallback path." % LIB_PATH)
+    lib = C.CDLL(LIB_PATH)
+    for name, (res, args) in _SIGNATURES.items():
+        try:
+            fn = getattr(lib, name)
+        except AttributeError as e:
+            raise TdqError("libtdq.so does not export %s; rebuild it" % name) from e
+        fn.restype = res
+        fn.argtypes = args
+    if lib.tdq_abi_version() != 1:
+        raise TdqError("libtdq.so ABI version mismatch")
+    _lib = lib
+    return lib
+
+
+def check(rc):
+    if rc != 0:
+        msg = load().tdq_last_error()
+        raise TdqError("libtdq call failed (%d): %s" % (rc, msg.decode() if msg else "?"))
+
+
+def tableau(name):
+    t = Tableau()
+    check(load().tdq_tableau_get(name.encode(), C.byref(t)))
+    return t
+
+
+def tableau_as_dict(name):
+    """Dense float64 view of a named tableau (for tests and documentation)."""
+    t = tableau(name)
+    S = t.n_stages
+    return {
+        "n_stages": S, "order": t.order, "fsal": bool(t.fsal),
+        "alpha": [t.alpha[i] for i in range(S)],
+        "beta": [[t.beta[i][j] for j in range(i + 1)] for i in range(S)],
+        "c_sol": [t.c_sol[j] for j in range(S + 1)],
+        "c_err": [t.c_err[j] for j in range(S + 1)],
+        "c_mid": [t.c_mid[j] for j in range(S + 1)],
+    }
+
+
+def ptr_array(ptrs):
+    """void*[] from a list of ints/None."""
+    arr = (C.c_void_p * len(ptrs))()
+    for i, p in enumerate(ptrs):
+        arr[i] = p
+    return arr
+
+
+def i64_array(vals):
+    return (C.c_int64 * len(vals))(*vals)
+
+
+def dbl_array(vals):
+    return (C.c_double * len(vals))(*vals)

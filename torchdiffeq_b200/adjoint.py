@@ -1,0 +1,272 @@
+"""odeint_adjoint -- the reference's adjoint sensitivity entry point
+(torchdiffeq/_impl/adjoint.py:8-223) on the B200 path.
+
+Forward: the same device-resident solve as odeint, under no_grad (adjoint.py:23-24).
+Backward: for every output interval, right to left, the augmented system
+    d/dt (vjp_t, y, adj_y, adj_theta) = (-a.df/dt, f, -a.df/dy, -a.df/dtheta)      (adjoint.py:72-105)
+is integrated backwards in time by the same adaptive engine on ONE flat, 16-byte aligned vector
+
+    [ vjp_t | y | adj_y | theta_1 | theta_2 | ... ]
+
+Unpacking is views; packing the pieces func/autograd return (the reference's torch.cat, misc.py:145),
+the minus of `-adj_y` (adjoint.py:96) and the *(-1) of reverse time (misc.py:165) are one
+tdq_pack_segments launch per evaluation.  The default adjoint norm
+max(|t|, rms(y), rms(adj_y), max_i rms(theta_i)) (adjoint.py:247-250) and 'seminorm' (:267-271) are
+segments of the fused error-norm kernel.  One engine (and one captured graph) serves all intervals.
+"""
+import warnings
+
+import torch
+import torch.nn as nn
+
+from . import _lib
+from ._engine import Layout
+from .odeint import (ADAPTIVE_METHODS, _ADJOINT_CALLBACK_NAMES, _CALLBACK_NAMES, _make_adaptive_engine,
+                     _mixed_norm, _rms_norm, _solve, _unflatten, normalise, Problem)
+
+
+def find_parameters(module):
+    """adjoint.py:226-240."""
+    assert isinstance(module, nn.Module)
+    if getattr(module, '_is_replica', False):
+        def find_tensor_attributes(module):
+            return [(k, v) for k, v in module.__dict__.items() if torch.is_tensor(v) and v.requires_grad]
+        gen = module._named_members(get_members_fn=find_tensor_attributes)
+        return [param for _, param in gen]
+    return list(module.parameters())
+
+
+class _AdjointFunction(torch.autograd.Function):
+    """adjoint.py:8-153 OdeintAdjointMethod."""
+
+    @staticmethod
+    def forward(ctx, p, adjoint_rtol, adjoint_atol, adjoint_method, adjoint_options, t_requires_grad, t, y0_flat,
+                *adjoint_params):
+        ctx.p = p
+        ctx.adjoint_rtol, ctx.adjoint_atol = adjoint_rtol, adjoint_atol
+        ctx.adjoint_method, ctx.adjoint_options = adjoint_method, adjoint_options
+        ctx.t_requires_grad = t_requires_grad
+        with torch.no_grad():
+            sol, _ = _solve(p)                                          # adjoint.py:23-24
+            sol = sol.clone() if sol._base is not None else sol
+        ctx.save_for_backward(t, sol, *adjoint_params)                   # adjoint.py:28
+        return sol
+
+    @staticmethod
+    def backward(ctx, grad_sol):
+        p = ctx.p
+        t, y, *adjoint_params = ctx.saved_tensors
+        adjoint_params = tuple(adjoint_params)
+        t_requires_grad = ctx.t_requires_grad
+        dev, T = p.device, p.dtype
+        n = p.n
+        grad_sol = grad_sol.contiguous()
+        with torch.no_grad():
+            # ---- augmented layout: [vjp_t | y | adj_y | params...]   (adjoint.py:64-65) ----------
+            lay = Layout([(1,), (n,), (n,)] + [q.shape for q in adjoint_params], T)
+            o_t, o_y, o_a = lay.offsets[0], lay.offsets[1], lay.offsets[2]
+            aug = torch.zeros(lay.n, dtype=T, device=dev)
+            aug[o_y:o_y + n] = y[-1]
+            aug[o_a:o_a + n] = grad_sol[-1]
+
+            base_fn, fwd_layout = p.fn, p.layout
+
+            # ---- augmented dynamics (adjoint.py:72-105), returning RAW pieces ------------------
+            def aug_fn(t_, aug_flat):
+                y_ = aug_flat[o_y:o_y + n]
+                adj = aug_flat[o_a:o_a + n]
+                with torch.enable_grad():
+                    tt = t_.detach()
+                    if t_requires_grad:
+                        tt = tt.clone().requires_grad_(True)
+                    yy = y_.detach().requires_grad_(True)
+                    f = base_fn(tt, yy)                                  # Tensor, or tuple of pieces (tuple state)
+                    if isinstance(f, tuple):
+                        outs = [f_.reshape(-1) for f_ in f]
+                        gouts = [adj[o:o + l] for o, l in zip(fwd_layout.offsets, fwd_layout.lens)]
+                    else:
+                        outs = [f.reshape(-1)]
+                        gouts = [adj]
+                    keep = [(o_, g_) for o_, g_ in zip(outs, gouts) if o_.requires_grad]
+                    inputs = ((tt,) if t_requires_grad else ()) + (yy,) + adjoint_params
+                    if keep:
+                        grads = torch.autograd.grad([o_ for o_, _ in keep], inputs, [g_ for _, g_ in keep],
+                                                    allow_unused=True)   # +adj: the minus sits in the pack scale
+                    else:
+                        grads = (None,) * len(inputs)
+                if t_requires_grad:
+                    vjp_t, vjp_y, *vjp_params = grads
+                else:
+                    vjp_t = None
+                    vjp_y, *vjp_params = grads
+                if isinstance(f, tuple):
+                    # tuple state: write the pieces of f at their offsets inside the y segment
+                    return (vjp_t, *[f_.detach() for f_ in f], vjp_y, *vjp_params)
+                return (vjp_t, f.detach(), vjp_y, *vjp_params)
+
+            # pieces and their scales.  Reference: k_ref = mul * (vjp_t, f, vjp_y, vjp_p) with
+            # vjp = grad(f, ., -adj) and mul = -1 (time runs backwards, misc.py:165); the engine applies
+            # t_sign = -1 to every stage slot, so the RAW slot must hold -k_ref = (-g_t, +f, -g_y, -g_p)
+            # where g = grad(f, ., +adj).
+            if p.is_tuple:
+                f_offs = [o_y + o for o in fwd_layout.offsets]
+                f_lens = list(fwd_layout.lens)
+            else:
+                f_offs, f_lens = [o_y], [n]
+            offs = [o_t] + f_offs + [o_a] + list(lay.offsets[3:])
+            lens = [1] + f_lens + [n] + list(lay.lens[3:])
+            scales = [-1.0] + [1.0] * len(f_offs) + [-1.0] + [-1.0] * len(adjoint_params)
+            pieces = (offs, lens, scales)
+
+            # ---- adjoint norm (adjoint.py:243-288) -------------------------------------------
+            opts = dict(ctx.adjoint_options)
+            y_segs = [(o_y + o, l) for o, l in zip(fwd_layout.offsets, fwd_layout.lens)] if p.is_tuple else [(o_y, n)]
+            a_segs = [(o_a + o, l) for o, l in zip(fwd_layout.offsets, fwd_layout.lens)] if p.is_tuple else [(o_a, n)]
+            p_segs = [(o, l) for o, l in zip(lay.offsets[3:], lay.lens[3:]) if l > 0]
+            norm_fn, q_view, segs = None, None, None
+            adj_norm = opts.pop("norm", None)
+            fwd_norm_fused = p.norm_fn is None
+            def views_of(q):
+                yq, aq = q[o_y:o_y + n], q[o_a:o_a + n]
+                if p.is_tuple:
+                    yq, aq = fwd_layout.views(yq), fwd_layout.views(aq)
+                else:
+                    yq, aq = yq.view(p.shape), aq.view(p.shape)
+                return q[o_t:o_t + 1].view(()), yq, aq, [q[o:o + l].view(s) for o, l, s in
+                                                         zip(lay.offsets[3:], lay.lens[3:], lay.shapes[3:])]
+            if adj_norm is None or adj_norm == "seminorm":
+                segs = [(o_t, 1)] + y_segs + a_segs + ([] if adj_norm == "seminorm" else p_segs)
+                if not fwd_norm_fused or len(segs) > _lib.TDQ_MAX_SEGS:
+                    state_norm = p.norm_fn if p.norm_fn is not None else (_mixed_norm if p.is_tuple else _rms_norm)
+                    semi = adj_norm == "seminorm"
+                    def norm_fn(parts):                                  # adjoint.py:247-250 / :267-271
+                        tq, yq, aq, pq = parts
+                        vals = [tq.abs(), state_norm(yq), state_norm(aq)]
+                        if not semi:
+                            vals.append(_mixed_norm(pq))
+                        return max(vals)
+                    q_view, segs = views_of, None
+            else:
+                # user callable: gets (t, y, adj_y, *adj_params), y/adj_y expanded for tuple states (:273-288)
+                def norm_fn(parts):
+                    tq, yq, aq, pq = parts
+                    if p.is_tuple:
+                        return adj_norm((tq, *yq, *aq, *pq))
+                    return adj_norm((tq, yq, aq, *pq))
+                q_view = views_of
+
+            # adjoint callbacks (adjoint.py:107-114)
+            callbacks = {}
+            for name, adj_name in zip(_CALLBACK_NAMES, _ADJOINT_CALLBACK_NAMES):
+                cb = getattr(p.original_func, adj_name, None)
+                if cb is not None:
+                    def _cb(t0, y_flat, dt, _cb_=cb):
+                        tq, yq, aq, pq = views_of(y_flat)
+                        state = (tq, *yq, *aq, *pq) if p.is_tuple else (tq, yq, aq, *pq)
+                        return _cb_(-t0, state, dt)                       # time runs backwards (misc.py:330-331)
+                    callbacks[name] = _cb
+
+            # The backward solve always runs against the forward time direction (adjoint.py:136
+            # t[i-1:i+1].flip(0)).  The engine integrates ascending s = t_sign_b * t, t_sign_b = -fwd_sign.
+            fwd_sign = -1.0 if p.t_reversed else 1.0
+            bp = Problem()                       # the backward problem as the engine factory sees it
+            bp.t_sign, bp.device, bp.dtype, bp.n, bp.fn = -fwd_sign, dev, T, lay.n, aug_fn
+            bp.t_cpu = (t.detach().to("cpu").to(torch.float64) * (-fwd_sign)).flip(0)
+            a_rtol, a_atol = ctx.adjoint_rtol, ctx.adjoint_atol
+            # tolerances: scalars, or per-piece tuples expanded like misc.py:115-123 over the aug tuple
+            rtol_s, rtol_v = _adj_tol(a_rtol, lay, dev)
+            atol_s, atol_v = _adj_tol(a_atol, lay, dev)
+            if (rtol_v is None) != (atol_v is None):
+                if rtol_v is None:
+                    rtol_v = torch.full_like(atol_v, rtol_s)
+                else:
+                    atol_v = torch.full_like(rtol_v, atol_s)
+            eng = _make_adaptive_engine(bp, ctx.adjoint_method, rtol_s, atol_s, rtol_v, atol_v, opts, fn=aug_fn,
+                                        n=lay.n, segs=segs, pieces=pieces, norm_fn=norm_fn, q_view=q_view,
+                                        callbacks=callbacks, solver_name=ctx.adjoint_method)
+            t64 = t.detach().to(device=dev, dtype=torch.float64)
+
+            time_vjps = torch.empty(len(t), dtype=t.dtype, device=t.device) if t_requires_grad else None
+            for i in range(len(t) - 1, 0, -1):                            # adjoint.py:124-141
+                if t_requires_grad:
+                    fe = base_fn(t[i].to(T), y[i])
+                    if isinstance(fe, tuple):
+                        fe = fwd_layout.flatten([f_.detach() for f_ in fe])
+                    dLd_cur_t = fe.reshape(-1).dot(grad_sol[i].reshape(-1))
+                    aug[o_t] -= dLd_cur_t
+                    time_vjps[i] = dLd_cur_t
+                # ascending time for the engine: integrate s = -fwd_sign * t from s_i to s_{i-1}
+                pair = torch.stack([t64[i], t64[i - 1]]) * (-fwd_sign)
+                sol = eng.solve(aug, pair)
+                aug.copy_(sol[1])
+                aug[o_y:o_y + n] = y[i - 1]                               # adjoint.py:140
+                aug[o_a:o_a + n] += grad_sol[i - 1]                       # adjoint.py:141
+            if t_requires_grad:
+                time_vjps[0] = aug[o_t]
+            adj_y = aug[o_a:o_a + n].clone()
+            adj_params = [aug[o:o + l].view(s).clone() for o, l, s in zip(lay.offsets[3:], lay.lens[3:], lay.shapes[3:])]
+        ctx.backward_nfe = eng.nfe
+        return (None, None, None, None, None, None, time_vjps, adj_y, *adj_params)
+
+
+def _adj_tol(tol, lay, device):
+    if isinstance(tol, torch.Tensor) and tol.ndim == 0:
+        return float(tol), None
+    try:
+        iter(tol)
+    except TypeError:
+        return float(tol), None
+    tol = tuple(tol)
+    assert len(tol) == len(lay.shapes), "If using tupled adjoint tolerances they must match (t, y, adj_y, *params)"
+    vec = torch.ones(lay.n, dtype=torch.float64, device=device)
+    for tol_, o, l in zip(tol, lay.offsets, lay.lens):
+        vec[o:o + l] = float(torch.as_tensor(tol_).to(torch.float32)) if not torch.is_tensor(tol_) or tol_.ndim == 0 \
+            else torch.as_tensor(tol_).to(device).reshape(-1).to(torch.float64)
+    return None, vec
+
+
+def odeint_adjoint(func, y0, t, *, rtol=1e-7, atol=1e-9, method=None, options=None, event_fn=None,
+                   adjoint_rtol=None, adjoint_atol=None, adjoint_method=None, adjoint_options=None,
+                   adjoint_params=None):
+    """adjoint.py:156-223, same signature and defaults."""
+    if adjoint_params is None and not isinstance(func, nn.Module):                     # adjoint.py:161-164
+        raise ValueError('func must be an instance of nn.Module to specify the adjoint parameters; alternatively they '
+                         'can be specified explicitly via the `adjoint_params` argument. If there are no parameters '
+                         'then it is allowable to set `adjoint_params=()`.')
+    if adjoint_rtol is None:                                                           # adjoint.py:167-172
+        adjoint_rtol = rtol
+    if adjoint_atol is None:
+        adjoint_atol = atol
+    if adjoint_method is None:
+        adjoint_method = method
+    if adjoint_method != method and options is not None and adjoint_options is None:   # adjoint.py:174-176
+        raise ValueError("If `adjoint_method != method` then we cannot infer `adjoint_options` from `options`. So as "
+                         "`options` has been passed then `adjoint_options` must be passed as well.")
+    if adjoint_options is None:                                                        # adjoint.py:178-182
+        adjoint_options = {k: v for k, v in options.items() if k != "norm"} if options is not None else {}
+    else:
+        adjoint_options = adjoint_options.copy()
+    if adjoint_params is None:                                                         # adjoint.py:184-187
+        adjoint_params = tuple(find_parameters(func))
+    else:
+        adjoint_params = tuple(adjoint_params)
+    oldlen_ = len(adjoint_params)                                                      # adjoint.py:190-197
+    adjoint_params = tuple(q for q in adjoint_params if q.requires_grad)
+    if len(adjoint_params) != oldlen_:
+        if 'norm' in adjoint_options and callable(adjoint_options['norm']):
+            warnings.warn("An adjoint parameter was passed without requiring gradient. For efficiency this will be "
+                          "excluded from the adjoint pass, and will not appear as a tensor in the adjoint norm.")
+
+    p = normalise(func, y0, t, rtol, atol, method, options, event_fn)
+    if adjoint_method is None:
+        adjoint_method = 'dopri5'
+    if adjoint_method not in ADAPTIVE_METHODS:
+        raise NotImplementedError('adjoint_method "{}" is not implemented on the B200 path; adaptive methods: {}'
+                                  .format(adjoint_method, ADAPTIVE_METHODS))
+    if p.is_tuple:
+        y0_flat = p.layout.flatten(list(y0))          # differentiable wrt every piece (copy_ into zeros)
+    else:
+        y0_flat = y0.reshape(-1)
+    sol = _AdjointFunction.apply(p, adjoint_rtol, adjoint_atol, adjoint_method, adjoint_options, t.requires_grad,
+                                 t, y0_flat, *adjoint_params)
+    return _unflatten(p, sol)

@@ -1,0 +1,433 @@
+// tdq_ctrl.cu -- scalar side of the adaptive loop, kept on the device:
+//   start-of-attempt bookkeeping   rk_common.py:266-308, :61-78
+//   accept / reject + I controller rk_common.py:323-361, misc.py:85-95
+//   initial step selection         misc.py:36-77
+// One thread does the arithmetic (a few hundred flops); what matters is that nothing here needs the
+// host, so a whole attempt can sit inside a CUDA graph.
+#include "tdq_common.cuh"
+
+namespace {
+
+template <typename T> __device__ __forceinline__ T prev_repr(T t);   // misc.py:358-364, Perturb.PREV
+template <> __device__ __forceinline__ float prev_repr<float>(float t) { return nextafterf(t, __fsub_rn(t, 1.0f)); }
+template <> __device__ __forceinline__ double prev_repr<double>(double t) { return nextafter(t, __dsub_rn(t, 1.0)); }
+
+template <typename T> __device__ __forceinline__ void store_T(unsigned char *raw, int i, T v) {
+    reinterpret_cast<T *>(raw)[i] = v;
+}
+
+// rk_common.py:266-308 (+ :246-247) for the attempt that starts at rk_state.t1 with rk_state.dt,
+// then the casts and products of _runge_kutta_step (:61-79, :89) and _interp_fit's dt (:365-366).
+template <typename T> __device__ void prepare_attempt(TdqCtrl &c) {
+    if (c.halt) return;
+    if (c.n_steps_interval >= c.max_num_steps) {                     // rk_common.py:247
+        c.status = TDQ_RUN_MAX_STEPS;
+        c.halt = 1;
+        return;
+    }
+    double dt = c.dt;
+    if (!isfinite(dt)) dt = c.min_step;                               // :269-270
+    dt = fmin(fmax(dt, c.min_step), c.max_step);                      // :271
+    const double t0 = c.t1;
+    double t1 = t0 + dt;                                              // :273
+    c.att_t0 = t0;
+    c.att_dt = dt;
+    if (!(t0 + dt > t0)) {                                            // :286
+        c.status = TDQ_RUN_DT_UNDERFLOW;
+        c.halt = 1;
+        return;
+    }
+    c.on_step_t = 0;
+    if (c.n_step_t > 0) {                                             // :293-300
+        const double nxt = c.step_t[c.next_step_index];
+        if (t0 < nxt && nxt < t0 + dt) {
+            c.on_step_t = 1;
+            t1 = nxt;
+            dt = t1 - t0;
+        }
+    }
+    c.att_dt = dt;
+    c.att_t1 = t1;
+
+    using A = Ar<T>;
+    const T t0T = (T)t0, dtT = (T)dt, t1T = (T)t1;                    // :61-65
+    const T sgn = (T)c.t_sign;
+    c.att_dtT = (double)dtT;
+    const int S = c.n_stages;
+    for (int i = 0; i < S; ++i) {                                     // :72-78
+        const T a = (T)c.alpha[i];
+        T ti;
+        if (a == (T)1) ti = prev_repr<T>(t1T);
+        else ti = A::add(t0T, A::mul(a, dtT));
+        store_T<T>(c.tstage, i, A::mul(sgn, ti));
+    }
+    const int rows = c.fsal ? S : S + 1;
+    for (int r = 0; r < rows; ++r)
+        for (int m = 0; m < c.row_nnz[r]; ++m)                        // :79 (beta_i * dt), :85 (dt * c_sol)
+            c.coef[r][m] = (double)A::mul(sgn, A::mul((T)c.beta[r][m], dtT));
+    for (int m = 0; m < c.err_nnz; ++m)                               // :89
+        c.ecoef[m] = (double)A::mul(sgn, A::mul(dtT, (T)c.c_err[m]));
+}
+
+// Value of the norm from per-segment sums: max over segments of sqrt(mean), each rounded to the
+// ratio dtype (misc.py:22-23 _rms_norm, misc.py:30-33 _mixed_norm, adjoint.py:247-250).
+template <typename T>
+__device__ double norm_from_sums(const TdqCtrl &c, const double *sums, const int64_t *counts, int n_seg) {
+    double best = 0.0;
+    bool nan = false;
+    for (int s = 0; s < n_seg; ++s) {
+        const double cnt = counts ? (double)counts[s] : (double)c.n_global;
+        if (cnt <= 0.0) continue;
+        double r = sqrt(sums[s] / cnt);
+        if (!c.ratio_f64) r = (double)(T)r;
+        if (r != r) nan = true;
+        if (r > best) best = r;
+    }
+    return nan ? CUDART_NAN : best;
+}
+
+__device__ void write_mailbox(TdqCtrl &c, double fin_t0, double fin_dt) {
+    c.seq += 1;
+    tdq_mailbox *m = c.mbox;
+    if (!m) return;
+    m->status = c.status;
+    m->accept = c.accept;
+    m->done = c.done;
+    m->out_cursor = c.out_cursor;
+    m->n_accept = c.n_accept;
+    m->n_reject = c.n_reject;
+    m->t0 = c.t0;
+    m->t1 = c.t1;
+    m->dt = c.dt;
+    m->ratio = c.ratio;
+    m->att_t0 = fin_t0;
+    m->att_dt = fin_dt;
+    m->next_t0 = c.att_t0;
+    m->next_dt = c.att_dt;
+    __threadfence_system();
+    m->seq = c.seq;
+    __threadfence_system();
+}
+
+// rk_common.py:323-361 + misc.py:85-95, then the next attempt's constants.
+template <typename T>
+__device__ void controller(TdqCtrl &c, const double *norm_in, const int64_t *seg_counts, int n_seg,
+                           const void *ratio_dev) {
+    if (c.halt) {
+        // Attempts issued after the end are no-ops; the mailbox still ticks so a host that runs
+        // ahead can account for every attempt it queued.  Clearing `accept` keeps fit/eval of such an
+        // attempt from touching the finished solution.
+        c.accept = 0;
+        c.emit_lo = c.emit_hi;
+        write_mailbox(c, c.att_t0, c.att_dt);
+        return;
+    }
+    using A = Ar<T>;
+    double ratio;
+    if (ratio_dev) {
+        ratio = c.ratio_f64 ? *reinterpret_cast<const double *>(ratio_dev)
+                            : (double)*reinterpret_cast<const T *>(ratio_dev);
+        ratio = fabs(ratio);                                          // misc.py:82 .abs()
+    } else {
+        ratio = norm_from_sums<T>(c, norm_in, seg_counts, n_seg);
+    }
+    const bool y1_nonfinite = norm_in && norm_in[n_seg] > 0.0;
+    if (y1_nonfinite && !ratio_dev) ratio = CUDART_NAN;               // a non-finite y1 poisons err/tol
+    c.ratio = ratio;
+
+    const double dt = c.att_dt;
+    bool accept = ratio <= 1.0;                                       // :324
+    if (dt > c.max_step) accept = false;                              // :327-328
+    if (dt <= c.min_step) accept = true;                              // :329-330
+    c.accept = accept ? 1 : 0;
+
+    if (accept) {                                                     // :338-352
+        c.t0 = c.att_t0;
+        c.t1 = c.att_t1;
+        c.n_accept += 1;
+        if (c.on_step_t && c.next_step_index != c.n_step_t - 1) c.next_step_index += 1;
+        // constants _interp_fit needs from THIS attempt (rk_common.py:363-369)
+        const T dtT = (T)c.att_dtT, sgn = (T)c.t_sign;
+        c.fit_sdt = (double)A::mul(sgn, dtT);
+        for (int m = 0; m < c.mid_nnz; ++m)
+            c.fit_mcoef[m] = (double)A::mul(sgn, A::mul(dtT, (T)c.c_mid[m]));
+        if (y1_nonfinite) {                                           // the next attempt would trip :287
+            c.status = TDQ_RUN_NONFINITE;
+            c.halt = 1;
+        }
+    } else {                                                          // :353-357
+        c.t0 = c.att_t0;
+        c.t1 = c.att_t0;
+        c.n_reject += 1;
+    }
+
+    // misc.py:85-95 _optimal_step_size (float64), then the clamp of rk_common.py:359
+    double dt_next;
+    if (ratio == 0.0) {
+        dt_next = dt * c.ifactor;
+    } else {
+        const double dfac = (ratio < 1.0) ? 1.0 : c.dfactor;
+        const double expo = 1.0 / (double)c.order;
+        const double cand = c.safety / pow(ratio, expo);
+        double inner = (cand != cand || dfac != dfac) ? CUDART_NAN : fmax(cand, dfac);   // torch.max
+        double factor = (inner != inner) ? CUDART_NAN : fmin(c.ifactor, inner);          // torch.min
+        dt_next = dt * factor;
+    }
+    if (dt_next == dt_next) dt_next = fmin(fmax(dt_next, c.min_step), c.max_step);
+    c.dt = dt_next;
+
+    // Output cursor: solvers.py:33-34 asks for t[i] one at a time; every t[i] <= t1 is now covered
+    // by this accepted interval (rk_common.py:246 loop condition `next_t > t1` is false for them).
+    c.emit_lo = c.out_cursor;
+    c.n_steps_interval += 1;
+    if (accept) {
+        int cur = c.out_cursor;
+        while (cur < c.n_out && !(c.t_out[cur] > c.t1)) ++cur;
+        if (cur != c.out_cursor) c.n_steps_interval = 0;
+        c.out_cursor = cur;
+    }
+    c.emit_hi = c.out_cursor;
+    if (c.out_cursor >= c.n_out) {
+        c.done = 1;
+        c.halt = 1;
+    }
+    const double fin_t0 = c.att_t0, fin_dt = c.att_dt;
+    prepare_attempt<T>(c);
+    write_mailbox(c, fin_t0, fin_dt);
+}
+
+// misc.py:55-63: h0 from d0, d1.
+template <typename T>
+__device__ void initial_h0(TdqCtrl &c, const double *s0, const double *s1, const int64_t *counts, int n_seg) {
+    using A = Ar<T>;
+    const double d0d = norm_from_sums<T>(c, s0, counts, n_seg);
+    const double d1d = norm_from_sums<T>(c, s1, counts, n_seg);
+    double h0;
+    if (c.ratio_f64) {
+        h0 = (d0d < 1e-5 || d1d < 1e-5) ? (double)(T)1e-6 : fabs(0.01 * d0d / d1d);
+    } else {
+        const T d0 = (T)d0d, d1 = (T)d1d;
+        T h;
+        if (d0 < (T)1e-5 || d1 < (T)1e-5) h = (T)1e-6;                 // :60-61 (compare after promoting 1e-5)
+        else h = A::div(A::mul((T)0.01, d0), d1);                      // :63
+        h0 = (double)A::abs(h);
+    }
+    c.h0 = h0;
+    c.ratio = d1d;                                                     // stash d1 for the finish kernel
+    // probe time: t0 (f64) + h0 -> f64, cast to T by _PerturbFunc (misc.py:66-67, :187)
+    const T tp = (T)(c.t1 + h0);
+    store_T<T>(c.taux, 1, A::mul((T)c.t_sign, tp));
+}
+
+// misc.py:69-77
+template <typename T>
+__device__ void initial_finish(TdqCtrl &c, const double *s2, const int64_t *counts, int n_seg) {
+    using A = Ar<T>;
+    const double nd = norm_from_sums<T>(c, s2, counts, n_seg);
+    double dt;
+    const double order_p1 = (double)c.order;                           // called with order-1 (rk_common.py:217)
+    if (c.ratio_f64) {
+        const double d1 = c.ratio, h0 = c.h0;
+        const double d2 = fabs(nd / h0);
+        double h1;
+        if (d1 <= 1e-15 && d2 <= 1e-15) h1 = fmax((double)(T)1e-6, h0 * 1e-3);
+        else h1 = pow(0.01 / ((d2 > d1) ? d2 : d1), 1.0 / order_p1);
+        h1 = fabs(h1);
+        dt = fmin(100.0 * h0, h1);
+    } else {
+        const T d1 = (T)c.ratio, h0 = (T)c.h0;
+        const T d2 = A::abs(A::div((T)nd, h0));
+        T h1;
+        if (d1 <= (T)1e-15 && d2 <= (T)1e-15) {
+            const T a = (T)1e-6, b = A::mul(h0, (T)1e-3);
+            h1 = (a != a || b != b) ? (T)CUDART_NAN : (a > b ? a : b);
+        } else {
+            const T m = (d2 > d1) ? d2 : d1;                           // Python max(d1, d2)
+            const T base = A::div((T)0.01, m);
+            const T ex = (T)(1.0 / order_p1);
+            h1 = (T)pow((double)base, (double)ex);
+        }
+        h1 = A::abs(h1);
+        const T a = A::mul((T)100, h0);
+        const T r = (a != a || h1 != h1) ? (T)CUDART_NAN : (a < h1 ? a : h1);   // torch.min
+        dt = (double)r;
+    }
+    c.dt = dt;
+}
+
+template <typename T> __global__ void k_prepare(TdqCtrl *c) {
+    prepare_attempt<T>(*c);
+    if (c->mbox) {                       // first attempt of a solve: let the host see its (t0, dt) and status
+        c->mbox->status = c->status;
+        c->mbox->next_t0 = c->att_t0;
+        c->mbox->next_dt = c->att_dt;
+        __threadfence_system();
+    }
+}
+template <typename T>
+__global__ void k_controller(TdqCtrl *c, const double *norm_in, const int64_t *cnt, int n_seg, const void *ratio_dev) {
+    controller<T>(*c, norm_in, cnt, n_seg, ratio_dev);
+}
+template <typename T>
+__global__ void k_initial_h0(TdqCtrl *c, const double *s0, const double *s1, const int64_t *cnt, int n_seg) {
+    initial_h0<T>(*c, s0, s1, cnt, n_seg);
+}
+template <typename T>
+__global__ void k_initial_finish(TdqCtrl *c, const double *s2, const int64_t *cnt, int n_seg) {
+    initial_finish<T>(*c, s2, cnt, n_seg);
+}
+__global__ void k_set_first_step(TdqCtrl *c, double dt) { c->dt = dt; }
+__global__ void k_reset_interval(TdqCtrl *c) { c->n_steps_interval = 0; }
+__global__ void k_set_step_t(TdqCtrl *c, const double *st, int n) {
+    c->step_t = st;
+    c->n_step_t = n;
+    // rk_common.py:240: min(bisect(step_t, t0), len-1)
+    int idx = 0;
+    while (idx < n && !(st[idx] > c->t1)) ++idx;
+    c->next_step_index = (idx < n - 1) ? idx : (n - 1);
+    if (n <= 0) c->next_step_index = 0;
+}
+
+}  // namespace
+
+#define TDQ_DISPATCH_T(dtype, ...)                                         \
+    do {                                                                   \
+        if ((dtype) == TDQ_F32) { using T = float; __VA_ARGS__; }          \
+        else if ((dtype) == TDQ_F64) { using T = double; __VA_ARGS__; }    \
+        else { tdq_set_error("unsupported dtype %d", (int)(dtype)); return TDQ_ERR_INVALID; } \
+    } while (0)
+
+// The dtype is stored in the block, but launchers must not read device memory: the host passes it.
+extern "C" {
+
+size_t tdq_ctrl_size(void) { return (sizeof(TdqCtrl) + 255) & ~size_t(255); }
+size_t tdq_ctrl_tstage_offset(void) { return offsetof(TdqCtrl, tstage); }
+size_t tdq_ctrl_taux_offset(void) { return offsetof(TdqCtrl, taux); }
+
+static float round_f32(double x) { return (float)x; }
+
+int tdq_ctrl_init(void *ctrl_dev, const tdq_tableau *tab, const tdq_options *opt, const double *t_out_dev,
+                  double t_start, int32_t n_out, void *mailbox_dev, void *stream) {
+    TDQ_REQUIRE(ctrl_dev && tab && opt, "null argument");
+    TDQ_REQUIRE(tab->n_stages >= 1 && tab->n_stages <= TDQ_MAX_STAGES, "n_stages out of range");
+    TDQ_REQUIRE(opt->dtype == TDQ_F32 || opt->dtype == TDQ_F64, "unsupported dtype");
+    TDQ_REQUIRE(n_out >= 1, "need at least one output time");
+    static thread_local TdqCtrl h;   // ~10 KB: keep off the stack
+    memset(&h, 0, sizeof(h));
+    const bool f32 = opt->dtype == TDQ_F32;
+    auto rT = [&](double x) { return f32 ? (double)round_f32(x) : x; };   // rk_common.py:201-205 cast
+    const int S = tab->n_stages;
+    h.dtype = opt->dtype;
+    h.n_stages = S;
+    h.order = tab->order;
+    h.fsal = tab->fsal ? 1 : 0;
+    h.ratio_f64 = (opt->ratio_f64 || !f32) ? 1 : 0;
+    h.n_out = n_out;
+    for (int i = 0; i < S; ++i) {
+        h.alpha[i] = rT(tab->alpha[i]);
+        int m = 0;
+        for (int j = 0; j <= i; ++j)
+            if (tab->beta[i][j] != 0.0) { h.row_idx[i][m] = j; h.beta[i][m] = rT(tab->beta[i][j]); ++m; }
+        h.row_nnz[i] = m;
+    }
+    {
+        int m = 0;
+        for (int j = 0; j <= S; ++j)
+            if (tab->c_sol[j] != 0.0) { h.row_idx[S][m] = j; h.beta[S][m] = rT(tab->c_sol[j]); ++m; }
+        h.row_nnz[S] = m;
+        m = 0;
+        for (int j = 0; j <= S; ++j)
+            if (tab->c_err[j] != 0.0) { h.err_idx[m] = j; h.c_err[m] = rT(tab->c_err[j]); ++m; }
+        h.err_nnz = m;
+        m = 0;
+        for (int j = 0; j <= S; ++j)
+            if (tab->c_mid[j] != 0.0) { h.mid_idx[m] = j; h.c_mid[m] = rT(tab->c_mid[j]); ++m; }
+        h.mid_nnz = m;
+    }
+    h.rtol = opt->rtol;
+    h.atol = opt->atol;
+    h.min_step = opt->min_step;
+    h.max_step = opt->max_step;
+    h.safety = opt->safety;
+    h.ifactor = opt->ifactor;
+    h.dfactor = opt->dfactor;
+    h.t_sign = (opt->t_sign < 0) ? -1.0 : 1.0;
+    h.max_num_steps = opt->max_num_steps;
+    h.n_global = opt->n_global;
+    h.t_out = t_out_dev;
+    h.mbox = reinterpret_cast<tdq_mailbox *>(mailbox_dev);
+    h.t0 = h.t1 = t_start;                                            // rk_common.py:221
+    h.dt = 0.0;
+    h.out_cursor = 1;                                                 // solution[0] = y0 (solvers.py:30)
+    h.emit_lo = h.emit_hi = 1;
+    if (n_out <= 1) { h.done = 1; h.halt = 1; }
+    if (f32) {
+        float v = (float)h.t_sign * (float)t_start;
+        memcpy(h.taux, &v, sizeof(v));
+    } else {
+        double v = h.t_sign * t_start;
+        memcpy(h.taux, &v, sizeof(v));
+    }
+    // Pageable source: the runtime stages the bytes before returning, so `h` may be reused.
+    TDQ_CHECK_CUDA(cudaMemcpyAsync(ctrl_dev, &h, sizeof(h), cudaMemcpyHostToDevice, (cudaStream_t)stream));
+    return TDQ_OK;
+}
+
+int tdq_ctrl_set_step_t(void *ctrl_dev, const double *step_t_dev, int32_t n, void *stream) {
+    TDQ_REQUIRE(ctrl_dev, "null ctrl");
+    k_set_step_t<<<1, 1, 0, (cudaStream_t)stream>>>((TdqCtrl *)ctrl_dev, step_t_dev, n);
+    TDQ_CHECK_CUDA(cudaGetLastError());
+    return TDQ_OK;
+}
+
+int tdq_prepare_attempt(void *ctrl_dev, int32_t dtype, void *stream) {
+    TDQ_REQUIRE(ctrl_dev, "null ctrl");
+    TDQ_DISPATCH_T(dtype, (k_prepare<T><<<1, 1, 0, (cudaStream_t)stream>>>((TdqCtrl *)ctrl_dev)));
+    TDQ_CHECK_CUDA(cudaGetLastError());
+    return TDQ_OK;
+}
+
+int tdq_controller(void *ctrl_dev, int32_t dtype, const double *norm_in, const int64_t *seg_counts_dev,
+                   int32_t n_seg, const void *ratio_dev, void *stream) {
+    TDQ_REQUIRE(ctrl_dev, "null ctrl");
+    TDQ_REQUIRE(norm_in || ratio_dev, "need norm sums or an explicit ratio");
+    TDQ_REQUIRE(n_seg >= 1 && n_seg <= TDQ_MAX_SEGS, "n_seg out of range");
+    TDQ_DISPATCH_T(dtype, (k_controller<T><<<1, 1, 0, (cudaStream_t)stream>>>(
+                               (TdqCtrl *)ctrl_dev, norm_in, seg_counts_dev, n_seg, ratio_dev)));
+    TDQ_CHECK_CUDA(cudaGetLastError());
+    return TDQ_OK;
+}
+
+int tdq_initial_step_h0(void *ctrl_dev, int32_t dtype, const double *d0_sumsq, const double *d1_sumsq,
+                        const int64_t *seg_counts_dev, int32_t n_seg, void *stream) {
+    TDQ_REQUIRE(ctrl_dev && d0_sumsq && d1_sumsq, "null argument");
+    TDQ_DISPATCH_T(dtype, (k_initial_h0<T><<<1, 1, 0, (cudaStream_t)stream>>>(
+                               (TdqCtrl *)ctrl_dev, d0_sumsq, d1_sumsq, seg_counts_dev, n_seg)));
+    TDQ_CHECK_CUDA(cudaGetLastError());
+    return TDQ_OK;
+}
+
+int tdq_initial_step_finish(void *ctrl_dev, int32_t dtype, const double *d2_sumsq,
+                            const int64_t *seg_counts_dev, int32_t n_seg, void *stream) {
+    TDQ_REQUIRE(ctrl_dev && d2_sumsq, "null argument");
+    TDQ_DISPATCH_T(dtype, (k_initial_finish<T><<<1, 1, 0, (cudaStream_t)stream>>>(
+                               (TdqCtrl *)ctrl_dev, d2_sumsq, seg_counts_dev, n_seg)));
+    TDQ_CHECK_CUDA(cudaGetLastError());
+    return TDQ_OK;
+}
+
+int tdq_set_first_step(void *ctrl_dev, double first_step, void *stream) {
+    TDQ_REQUIRE(ctrl_dev, "null ctrl");
+    k_set_first_step<<<1, 1, 0, (cudaStream_t)stream>>>((TdqCtrl *)ctrl_dev, first_step);
+    TDQ_CHECK_CUDA(cudaGetLastError());
+    return TDQ_OK;
+}
+
+int tdq_ctrl_reset_interval(void *ctrl_dev, void *stream) {
+    TDQ_REQUIRE(ctrl_dev, "null ctrl");
+    k_reset_interval<<<1, 1, 0, (cudaStream_t)stream>>>((TdqCtrl *)ctrl_dev);
+    TDQ_CHECK_CUDA(cudaGetLastError());
+    return TDQ_OK;
+}
+
+}  // extern "C"

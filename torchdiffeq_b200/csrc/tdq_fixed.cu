@@ -1,0 +1,214 @@
+// tdq_fixed.cu -- fixed-grid RK4 (3/8 rule) and the augmented-state pack.
+//
+//   k_rk4        stage values and the final update of rk4_alt_step_func   rk_common.py:110-118, fixed_grid.py:24-29, solvers.py:115
+//   k_fixed_emit outputs of one grid step by linear interpolation         solvers.py:117-125, :175-181
+//   k_pack       concat + per-segment scale of the augmented dynamics     misc.py:137-145, :158-165, adjoint.py:94-105
+//
+// The step size comes from a device array indexed by a device step counter so that one captured
+// step graph serves the whole grid.
+#include "tdq_common.cuh"
+
+namespace {
+
+constexpr int kThreads = 256;
+
+// 1/3 as Python computes it (rk_common.py:94 `_one_third = 1 / 3`), then cast to T by torch when it
+// multiplies a T tensor.
+template <typename T, int WHICH, bool VECTOR>
+__global__ void __launch_bounds__(kThreads)
+k_rk4(T *__restrict__ out, const T *__restrict__ y0, const T *__restrict__ k1, const T *__restrict__ k2,
+      const T *__restrict__ k3, const T *__restrict__ k4, const T *__restrict__ dt_arr,
+      const int64_t *__restrict__ step, size_t n) {
+    using A = Ar<T>;
+    const T dt = dt_arr[step ? *step : 0];
+    const T third = (T)(1.0 / 3.0);
+    auto f = [&](T y, T a, T b, T c_, T d) -> T {
+        if (WHICH == 1) return A::add(y, A::mul(A::mul(dt, a), third));                 // y0 + dt*k1*_one_third
+        if (WHICH == 2) return A::add(y, A::mul(dt, A::sub(b, A::mul(a, third))));      // y0 + dt*(k2 - k1*_one_third)
+        if (WHICH == 3) return A::add(y, A::mul(dt, A::add(A::sub(a, b), c_)));         // y0 + dt*(k1 - k2 + k3)
+        // y0 + (k1 + 3*(k2 + k3) + k4)*dt*0.125
+        const T s = A::add(A::add(a, A::mul((T)3, A::add(b, c_))), d);
+        return A::add(y, A::mul(A::mul(s, dt), (T)0.125));
+    };
+    if (VECTOR) {
+        using V = Vec<T>;
+        const size_t nvec = n / V::N;
+        const size_t v = (size_t)blockIdx.x * kThreads + threadIdx.x;
+        if (v < nvec) {
+            const size_t i0 = v * V::N;
+            V y = ld_stream<T>(y0 + i0), a = ld_stream<T>(k1 + i0), b, c_, d;
+            if (WHICH >= 2) b = ld_stream<T>(k2 + i0);
+            if (WHICH >= 3) c_ = ld_stream<T>(k3 + i0);
+            if (WHICH >= 4) d = ld_stream<T>(k4 + i0);
+            V r;
+#pragma unroll
+            for (int e = 0; e < V::N; ++e)
+                r.v[e] = f(y.v[e], a.v[e], WHICH >= 2 ? b.v[e] : (T)0, WHICH >= 3 ? c_.v[e] : (T)0,
+                           WHICH >= 4 ? d.v[e] : (T)0);
+            st_vec<T>(out + i0, r);
+        }
+        if (blockIdx.x == gridDim.x - 1) {
+            const size_t i = nvec * V::N + threadIdx.x;
+            if (i < n)
+                out[i] = f(y0[i], k1[i], WHICH >= 2 ? k2[i] : (T)0, WHICH >= 3 ? k3[i] : (T)0,
+                           WHICH >= 4 ? k4[i] : (T)0);
+        }
+    } else {
+        for (size_t i = (size_t)blockIdx.x * kThreads + threadIdx.x; i < n; i += (size_t)gridDim.x * kThreads)
+            out[i] = f(y0[i], k1[i], WHICH >= 2 ? k2[i] : (T)0, WHICH >= 3 ? k3[i] : (T)0,
+                       WHICH >= 4 ? k4[i] : (T)0);
+    }
+}
+
+template <typename T, int WHICH>
+void launch_rk4(void *out, const void *y0, const void *k1, const void *k2, const void *k3, const void *k4,
+                const void *dt, const int64_t *step, size_t n, bool vec, cudaStream_t st) {
+    if (vec) {
+        const size_t nvec = n / Vec<T>::N;
+        size_t blocks = (nvec + kThreads - 1) / kThreads;
+        if (blocks == 0) blocks = 1;
+        k_rk4<T, WHICH, true><<<(unsigned)blocks, kThreads, 0, st>>>((T *)out, (const T *)y0, (const T *)k1,
+                                                                      (const T *)k2, (const T *)k3, (const T *)k4,
+                                                                      (const T *)dt, step, n);
+    } else {
+        size_t blocks = (n + kThreads - 1) / kThreads;
+        if (blocks == 0) blocks = 1;
+        if (blocks > 148 * 16) blocks = 148 * 16;
+        k_rk4<T, WHICH, false><<<(unsigned)blocks, kThreads, 0, st>>>((T *)out, (const T *)y0, (const T *)k1,
+                                                                       (const T *)k2, (const T *)k3, (const T *)k4,
+                                                                       (const T *)dt, step, n);
+    }
+}
+
+// Linear-interpolation outputs of the step that just finished, then the carry y0 <- y1.
+// mode 0: y0 (t == t0), 1: y1 (t == t1), 2: y0 + slope*(y1 - y0) (solvers.py:175-181).
+template <typename T>
+__global__ void __launch_bounds__(kThreads)
+k_fixed_emit(T *__restrict__ y0, const T *__restrict__ y1, T *__restrict__ solution,
+             const int32_t *__restrict__ rec_begin, const int32_t *__restrict__ out_idx,
+             const int32_t *__restrict__ mode, const T *__restrict__ slope, const int64_t *__restrict__ step,
+             size_t n) {
+    using A = Ar<T>;
+    const int64_t s = *step;
+    const int lo = rec_begin[s], hi = rec_begin[s + 1];
+    for (size_t i = (size_t)blockIdx.x * kThreads + threadIdx.x; i < n; i += (size_t)gridDim.x * kThreads) {
+        const T a = y0[i], b = y1[i];
+        for (int r = lo; r < hi; ++r) {
+            const int md = mode[r];
+            solution[(size_t)out_idx[r] * n + i] = (md == 0) ? a : (md == 1) ? b : A::add(a, A::mul(slope[r], A::sub(b, a)));
+        }
+        y0[i] = b;                                            // solvers.py:126  y0 = y1
+    }
+}
+// Advance the device step counter and stage the next step's four func times (state dtype).
+__global__ void k_step_advance(int64_t *step, const unsigned char *tst_all, unsigned char *tcur, int64_t n_steps,
+                               int esize) {
+    const int64_t s = *step + 1;
+    *step = s;
+    if (s < n_steps)
+        for (int b = 0; b < 4 * esize; ++b) tcur[b] = tst_all[s * 4 * esize + b];
+}
+
+struct PackArgs {
+    const void *src[TDQ_MAX_SEGS];
+    int64_t off[TDQ_MAX_SEGS];
+    int64_t len[TDQ_MAX_SEGS];
+    double scale[TDQ_MAX_SEGS];
+};
+
+template <typename T>
+__global__ void __launch_bounds__(kThreads) k_pack(T *__restrict__ dst, PackArgs a, int n_src) {
+    using A = Ar<T>;
+    const int s = blockIdx.y;
+    if (s >= n_src) return;
+    const T *src = reinterpret_cast<const T *>(a.src[s]);
+    T *d = dst + a.off[s];
+    const int64_t len = a.len[s];
+    const T sc = (T)a.scale[s];
+    const bool plain = (sc == (T)1);
+    const bool neg = (sc == (T)-1);
+    for (int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x; i < len; i += (int64_t)gridDim.x * kThreads) {
+        T v = src ? src[i] : (T)0;
+        if (!plain) v = neg ? -v : A::mul(sc, v);
+        d[i] = v;
+    }
+}
+
+}  // namespace
+
+#define TDQ_DISPATCH_T(dtype, ...)                                         \
+    do {                                                                   \
+        if ((dtype) == TDQ_F32) { using T = float; __VA_ARGS__; }          \
+        else if ((dtype) == TDQ_F64) { using T = double; __VA_ARGS__; }    \
+        else { tdq_set_error("unsupported dtype %d", (int)(dtype)); return TDQ_ERR_INVALID; } \
+    } while (0)
+
+extern "C" {
+
+int tdq_rk4_stage(int32_t dtype, int32_t which, void *y_out, const void *y0, const void *k1, const void *k2,
+                  const void *k3, const void *k4, const void *dt_dev, const int64_t *step_dev, size_t n,
+                  void *stream) {
+    TDQ_REQUIRE(y_out && y0 && k1 && dt_dev, "null argument");
+    TDQ_REQUIRE(which >= 1 && which <= 4, "which must be 1..4");
+    TDQ_REQUIRE(which < 2 || k2, "k2 required");
+    TDQ_REQUIRE(which < 3 || k3, "k3 required");
+    TDQ_REQUIRE(which < 4 || k4, "k4 required");
+    if (n == 0) return TDQ_OK;
+    bool vec = tdq_aligned16(y_out) && tdq_aligned16(y0) && tdq_aligned16(k1) && (which < 2 || tdq_aligned16(k2)) &&
+               (which < 3 || tdq_aligned16(k3)) && (which < 4 || tdq_aligned16(k4));
+    cudaStream_t st = (cudaStream_t)stream;
+    switch (which) {
+        case 1: TDQ_DISPATCH_T(dtype, (launch_rk4<T, 1>(y_out, y0, k1, k2, k3, k4, dt_dev, step_dev, n, vec, st))); break;
+        case 2: TDQ_DISPATCH_T(dtype, (launch_rk4<T, 2>(y_out, y0, k1, k2, k3, k4, dt_dev, step_dev, n, vec, st))); break;
+        case 3: TDQ_DISPATCH_T(dtype, (launch_rk4<T, 3>(y_out, y0, k1, k2, k3, k4, dt_dev, step_dev, n, vec, st))); break;
+        default: TDQ_DISPATCH_T(dtype, (launch_rk4<T, 4>(y_out, y0, k1, k2, k3, k4, dt_dev, step_dev, n, vec, st))); break;
+    }
+    TDQ_CHECK_CUDA(cudaGetLastError());
+    return TDQ_OK;
+}
+
+int tdq_fixed_emit(int32_t dtype, void *y0, const void *y1, void *solution, const int32_t *rec_begin_dev,
+                   const int32_t *out_idx_dev, const int32_t *mode_dev, const void *slope_dev, int64_t *step_dev,
+                   const void *tstage_all_dev, void *tstage_cur_dev, int64_t n_steps, size_t n, void *stream) {
+    TDQ_REQUIRE(y0 && y1 && solution && rec_begin_dev && out_idx_dev && mode_dev && slope_dev && step_dev &&
+                    tstage_all_dev && tstage_cur_dev,
+                "null argument");
+    cudaStream_t st = (cudaStream_t)stream;
+    size_t blocks = (n + kThreads - 1) / kThreads;
+    if (blocks == 0) blocks = 1;
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    TDQ_DISPATCH_T(dtype, (k_fixed_emit<T><<<(unsigned)blocks, kThreads, 0, st>>>(
+                               (T *)y0, (const T *)y1, (T *)solution, rec_begin_dev, out_idx_dev, mode_dev,
+                               (const T *)slope_dev, step_dev, n)));
+    k_step_advance<<<1, 1, 0, st>>>(step_dev, (const unsigned char *)tstage_all_dev, (unsigned char *)tstage_cur_dev,
+                                    n_steps, dtype == TDQ_F32 ? 4 : 8);
+    TDQ_CHECK_CUDA(cudaGetLastError());
+    return TDQ_OK;
+}
+
+int tdq_pack_segments(int32_t dtype, void *dst, const void *const *src, const int64_t *offsets, const int64_t *lens,
+                      const double *scales, int32_t n_src, void *stream) {
+    TDQ_REQUIRE(dst && src && offsets && lens && scales, "null argument");
+    TDQ_REQUIRE(n_src >= 1 && n_src <= TDQ_MAX_SEGS, "n_src out of range");
+    PackArgs a;
+    memset(&a, 0, sizeof(a));
+    int64_t max_len = 0;
+    for (int i = 0; i < n_src; ++i) {
+        a.src[i] = src[i];
+        a.off[i] = offsets[i];
+        a.len[i] = lens[i];
+        a.scale[i] = scales[i];
+        TDQ_REQUIRE(lens[i] >= 0 && offsets[i] >= 0, "negative segment");
+        if (lens[i] > max_len) max_len = lens[i];
+    }
+    if (max_len == 0) return TDQ_OK;
+    size_t bx = (size_t)((max_len + kThreads * 4 - 1) / (kThreads * 4));
+    if (bx == 0) bx = 1;
+    if (bx > 148 * 8) bx = 148 * 8;
+    dim3 grid((unsigned)bx, (unsigned)n_src);
+    TDQ_DISPATCH_T(dtype, (k_pack<T><<<grid, kThreads, 0, (cudaStream_t)stream>>>((T *)dst, a, n_src)));
+    TDQ_CHECK_CUDA(cudaGetLastError());
+    return TDQ_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,316 @@
+"""odeint -- the reference's public entry point (torchdiffeq/_impl/odeint.py:49-108) on the B200 path.
+
+Same signature, argument meaning, output layout and error behaviour; the work between input
+normalisation and the returned tensor runs as libtdq kernels.  Input normalisation restates
+misc.py:200-345 (_check_inputs) with two differences that are not observable in results:
+  * tuple states are laid out with 16-byte aligned pieces instead of back-to-back (misc.py:220);
+  * reverse-time integration does not wrap func in a multiply-by-minus-one (misc.py:158-165):
+    the sign is folded into the Runge-Kutta coefficients on the device.
+"""
+import warnings
+
+import torch
+
+from . import _lib
+from ._engine import AdaptiveEngine, Layout
+from ._fixed import FixedRK4Engine, grid_from_step_size
+
+ADAPTIVE_METHODS = ("dopri5", "dopri8", "bosh3", "fehlberg2", "adaptive_heun")
+FIXED_METHODS = ("rk4",)
+# Every name the reference registers (odeint.py:19-46); the ones outside SURVEY.md section 8 are
+# recognised and rejected explicitly rather than reported as "invalid".
+REFERENCE_METHODS = (
+    "dopri8", "dopri5", "tsit5", "bosh3", "fehlberg2", "adaptive_heun", "euler", "midpoint", "heun2", "heun3",
+    "rk4", "explicit_adams", "implicit_adams", "implicit_euler", "implicit_midpoint", "trapezoid", "radauIIA3",
+    "gl4", "radauIIA5", "gl6", "sdirk2", "trbdf2", "fixed_adams", "scipy_solver")
+
+_CALLBACK_NAMES = ["callback_step", "callback_accept_step", "callback_reject_step"]   # misc.py:9
+_ADJOINT_CALLBACK_NAMES = [name + "_adjoint" for name in _CALLBACK_NAMES]             # misc.py:10
+_ADAPTIVE_OPTIONS = {"min_step", "max_step", "first_step", "step_t", "jump_t", "safety", "ifactor", "dfactor",
+                     "max_num_steps", "dtype", "norm"}
+_FIXED_OPTIONS = {"step_size", "grid_constructor", "interp", "perturb", "norm"}
+_OUR_OPTIONS = {"graph", "run_ahead", "process_group"}
+
+
+def _rms_norm(tensor):
+    """misc.py:22-23; recognised by identity so the default norm stays fused."""
+    return tensor.abs().pow(2).mean().sqrt()
+
+
+def _mixed_norm(tensor_tuple):
+    """misc.py:30-33."""
+    if len(tensor_tuple) == 0:
+        return 0.
+    return max([_rms_norm(tensor) for tensor in tensor_tuple])
+
+
+class Problem:
+    """Normalised inputs of one solve (what misc.py:200-345 returns as a 10-tuple)."""
+    pass
+
+
+def _check_timelike(name, timelike, can_grad):                                         # misc.py:367-374
+    assert isinstance(timelike, torch.Tensor), '{} must be a torch.Tensor'.format(name)
+    if not torch.is_floating_point(timelike):                                          # misc.py:110-112
+        raise TypeError('`{}` must be a floating point Tensor but is a {}'.format(name, timelike.type()))
+    assert timelike.ndimension() == 1, "{} must be one dimensional".format(name)
+    if not can_grad:
+        assert not timelike.requires_grad, "{} cannot require gradient".format(name)
+    diff = timelike[1:] > timelike[:-1]
+    assert diff.all() or (~diff).all(), '{} must be strictly increasing or decreasing'.format(name)
+
+
+def _tol_vector(name, tol, layout, shape, device):
+    """Scalar tolerance -> (float, None).  Tuple of tolerances for a tuple state (misc.py:115-123
+    _tuple_tol) or a tensor broadcastable to a tensor state -> (None, per-element float64 vector), the
+    dtype the solver casts tolerances to (rk_common.py:186-187)."""
+    if isinstance(tol, torch.Tensor):
+        if tol.ndim == 0:
+            return float(tol), None
+        if layout is None:
+            return None, tol.detach().to(device=device, dtype=torch.float64).expand(shape).reshape(-1).contiguous()
+    else:
+        try:
+            iter(tol)
+        except TypeError:
+            return float(tol), None
+    assert layout is not None, "tupled {} needs a tuple y0".format(name)
+    tol = tuple(tol)
+    assert len(tol) == len(layout.shapes), \
+        "If using tupled {} it must have the same length as the tuple y0".format(name)
+    vec = torch.ones(layout.n, dtype=torch.float64, device=device)   # padding: any finite non-zero value
+    for tol_, o, l, shp in zip(tol, layout.offsets, layout.lens, layout.shapes):
+        # torch.as_tensor(python float) is float32 in the reference before the float64 cast: keep that rounding
+        v = torch.as_tensor(tol_).to(device)
+        vec[o:o + l] = v.expand(shp).reshape(-1).to(torch.float64)
+    return None, vec
+
+
+def normalise(func, y0, t, rtol, atol, method, options, event_fn, adjoint=False):
+    """Restatement of misc.py:200-345 for our engines."""
+    if event_fn is not None:
+        if len(t) != 2:                                                                # misc.py:203-204
+            raise ValueError(f"We require len(t) == 2 when in event handling mode, but got len(t)={len(t)}.")
+        raise NotImplementedError("event handling (odeint_event / event_fn) is outside the B200 hot path "
+                                  "(SURVEY.md section 8(f) item 3)")
+    p = Problem()
+    p.original_func = func
+    p.is_tuple = not isinstance(y0, torch.Tensor)
+    if p.is_tuple:
+        assert isinstance(y0, tuple), 'y0 must be either a torch.Tensor or a tuple'   # misc.py:216
+        p.layout = Layout([y_.shape for y_ in y0], y0[0].dtype)
+        p.device = y0[0].device
+        p.dtype = y0[0].dtype
+    else:
+        p.layout = None
+        p.device = y0.device
+        p.dtype = y0.dtype
+    options = {} if options is None else options.copy()                               # misc.py:226-229
+    if method is None:
+        method = 'dopri5'
+    if method not in REFERENCE_METHODS:                                               # misc.py:232-234
+        raise ValueError('Invalid method "{}". Must be one of {}'.format(
+            method, '{"' + '", "'.join(REFERENCE_METHODS) + '"}.'))
+    if method not in ADAPTIVE_METHODS + FIXED_METHODS:
+        raise NotImplementedError('method "{}" is not part of the B200 hot path; implemented: {}'.format(
+            method, ADAPTIVE_METHODS + FIXED_METHODS))
+    p.method, p.options = method, options
+
+    _check_timelike('t', t, True)
+    t_cpu = t.detach().to("cpu")                                                       # the one host read of t
+    p.t_reversed = bool(len(t_cpu) > 1 and t_cpu[0] > t_cpu[1])                        # misc.py:270-271
+    p.t_sign = -1.0 if p.t_reversed else 1.0
+    p.t_cpu = -t_cpu if p.t_reversed else t_cpu                                        # ascending from here on
+    if p.t_reversed:
+        for name in ("step_t", "jump_t"):                                              # misc.py:292-293
+            if isinstance(options.get(name), torch.Tensor):
+                options[name] = -options[name]
+        if "grid_constructor" in options:                                             # misc.py:283-289
+            _gc = options["grid_constructor"]
+            options["grid_constructor"] = lambda func, y0, t: -_gc(func, y0, -t)
+    assert (p.t_cpu[1:] > p.t_cpu[:-1]).all(), 't must be strictly increasing or decreasing'   # misc.py:296
+
+    if torch.is_tensor(rtol):                                                          # misc.py:299-302
+        assert not rtol.requires_grad, "rtol cannot require gradient"
+    if torch.is_tensor(atol):
+        assert not atol.requires_grad, "atol cannot require gradient"
+    if t.device != p.device:                                                           # misc.py:305-307
+        warnings.warn("t is not on the same device as y0. Coercing to y0.device.")
+
+    shape_ = None if p.is_tuple else y0.shape
+    p.rtol, p.rtol_vec = _tol_vector('rtol', rtol, p.layout, shape_, p.device)
+    p.atol, p.atol_vec = _tol_vector('atol', atol, p.layout, shape_, p.device)
+    if (p.rtol_vec is None) != (p.atol_vec is None):                                   # mixed scalar/vector
+        if p.rtol_vec is None:
+            p.rtol_vec = torch.full_like(p.atol_vec, p.rtol)
+        else:
+            p.atol_vec = torch.full_like(p.rtol_vec, p.atol)
+
+    # callbacks (misc.py:313-343)
+    p.callbacks = {}
+    for name in _CALLBACK_NAMES:
+        cb = getattr(func, name, None)
+        if cb is not None:
+            p.callbacks[name] = cb
+    valid = set(_CALLBACK_NAMES) if method in ADAPTIVE_METHODS else {"callback_step"}
+    invalid = set(p.callbacks) - valid
+    if invalid:
+        warnings.warn("Solver '{}' does not support callbacks {}".format(method, invalid))
+        for name in invalid:
+            del p.callbacks[name]
+    if p.callbacks:
+        layout, sign = p.layout, p.t_sign
+        def _wrap(cb):
+            def _cb(t0, y0_flat, dt):
+                y_ = layout.views(y0_flat) if layout is not None else y0_flat.view(p.shape)
+                return cb(t0 * sign, y_, dt)                                           # misc.py:326-331
+            return _cb
+        p.callbacks = {k: _wrap(v) for k, v in p.callbacks.items()}
+
+    # flat state + flat func
+    if p.is_tuple:
+        p.shape = None
+        p.y0_flat = p.layout.flatten([y_.detach() for y_ in y0])
+        p.n = p.layout.n
+        layout = p.layout
+        def fn(t_, y_flat):
+            f = func(t_, layout.views(y_flat))                                         # misc.py:143-145
+            return tuple(f)
+        p.fn = fn
+        p.pieces = (list(layout.offsets), list(layout.lens), [1.0] * len(layout.lens))
+        p.segs = list(zip(layout.offsets, layout.lens))                                # misc.py:247 _mixed_norm
+    else:
+        p.shape = y0.shape
+        p.y0_flat = y0.detach().reshape(-1)
+        p.n = p.y0_flat.numel()
+        shape = p.shape
+        p.fn = lambda t_, y_flat: func(t_, y_flat.view(shape))
+        p.pieces = None
+        p.segs = None
+
+    # norm (misc.py:237-266): the defaults stay fused; a user callable takes the compatibility path
+    p.norm_fn = None
+    p.q_view = None
+    user_norm = options.get("norm", None)
+    if user_norm is not None and user_norm is not _rms_norm and not (p.is_tuple and user_norm is _mixed_norm):
+        p.norm_fn = user_norm
+        if p.is_tuple:
+            p.q_view = lambda q: layout.views(q)
+        else:
+            p.q_view = lambda q: q.view(shape)
+    return p
+
+
+def _warn_unused(solver_name, options, known):                                        # misc.py:13-15
+    unused = {k: v for k, v in options.items() if k not in known and k not in _OUR_OPTIONS}
+    if unused:
+        warnings.warn('{}: Unexpected arguments {}'.format(solver_name, unused))
+
+
+def _make_adaptive_engine(p, method, rtol, atol, rtol_vec, atol_vec, options, fn=None, n=None, segs=None,
+                          pieces=None, norm_fn=None, q_view=None, callbacks=None, solver_name=None):
+    o = options
+    _warn_unused(solver_name or method, o, _ADAPTIVE_OPTIONS)
+    if o.get("jump_t") is not None:
+        raise NotImplementedError("jump_t is not implemented on the B200 path yet (SURVEY.md section 8(f) item 2)")
+    if o.get("dtype", torch.float64) != torch.float64:
+        raise NotImplementedError("time dtype other than float64 (options['dtype']) is not implemented")
+    step_t = o.get("step_t")
+    if step_t is not None:
+        st = torch.as_tensor(step_t, dtype=torch.float64).to("cpu")
+        st = torch.sort(st[st >= p.t_cpu[0].double()]).values                          # rk_common.py:372-375
+        if (st.unique(return_counts=True)[1] > 1).any():                               # :234-236
+            raise ValueError("`step_t` and `jump_t` must not have any repeated elements between them.")
+        step_t = st.to(p.device)
+    reduce_fn, n_global, seg_counts_global = None, None, None
+    pg = o.get("process_group")
+    if pg is not None:
+        from .dist import make_reduce
+        reduce_fn, n_global, seg_counts_global = make_reduce(pg, segs if segs is not None else
+                                                             [(0, n if n is not None else p.n)], p.device)
+    return AdaptiveEngine(
+        fn if fn is not None else p.fn, n if n is not None else p.n, p.dtype, p.device, method,
+        rtol=rtol, atol=atol, rtol_vec=rtol_vec, atol_vec=atol_vec,
+        segs=segs, t_sign=p.t_sign, pieces=pieces,
+        min_step=o.get("min_step", 0), max_step=o.get("max_step", float("inf")),
+        first_step=o.get("first_step"), step_t=step_t,
+        safety=o.get("safety", 0.9), ifactor=o.get("ifactor", 10.0), dfactor=o.get("dfactor", 0.2),
+        max_num_steps=o.get("max_num_steps", 2 ** 31 - 1),
+        norm_fn=norm_fn, q_view=q_view, graph=o.get("graph", "auto"), run_ahead=o.get("run_ahead", 2),
+        reduce_fn=reduce_fn, n_global=n_global, seg_counts_global=seg_counts_global, callbacks=callbacks)
+
+
+def _solve(p):
+    """Run the normalised problem; returns the flat solution [len(t), n] and the engine."""
+    if p.method in ADAPTIVE_METHODS:
+        eng = _make_adaptive_engine(p, p.method, p.rtol, p.atol, p.rtol_vec, p.atol_vec, p.options,
+                                    segs=p.segs, pieces=p.pieces, norm_fn=p.norm_fn, q_view=p.q_view,
+                                    callbacks=p.callbacks)
+        t64 = p.t_cpu.to(torch.float64).to(p.device)                                   # solvers.py:31
+        sol = eng.solve(p.y0_flat, t64, t_start=float(p.t_cpu[0]))
+        return sol, eng
+    # fixed grid RK4 (solvers.py:55-128)
+    o = p.options
+    _warn_unused("RK4", o, _FIXED_OPTIONS)
+    step_size, gc = o.get("step_size"), o.get("grid_constructor")
+    if step_size is None:
+        grid_constructor = gc if gc is not None else (lambda f, y0, t: t)
+    else:
+        if gc is not None:
+            raise ValueError("step_size and grid_constructor are mutually exclusive arguments.")   # solvers.py:79
+        grid_constructor = grid_from_step_size(step_size)
+    interp = o.get("interp", "linear")
+    if interp == "cubic":
+        raise NotImplementedError("interp='cubic' is not implemented on the B200 path yet")
+    if interp != "linear":
+        raise ValueError(f"Unknown interpolation method {interp}")
+    y0_view = p.layout.views(p.y0_flat) if p.is_tuple else p.y0_flat.view(p.shape)
+    grid = grid_constructor(p.original_func, y0_view, p.t_cpu)
+    grid = grid.detach().to("cpu")
+    assert grid[0] == p.t_cpu[0] and grid[-1] == p.t_cpu[-1]                           # solvers.py:104
+    fn = p.fn
+    if p.is_tuple:
+        layout = p.layout
+        def fn(t_, y_flat, _f=p.fn):
+            out = torch.zeros(layout.n, dtype=p.dtype, device=p.device)
+            return layout.flatten(list(_f(t_, y_flat)), out=out)
+    eng = FixedRK4Engine(fn, p.n, p.dtype, p.device, t_sign=p.t_sign, perturb=o.get("perturb", False),
+                         graph=o.get("graph", "auto"), callbacks=p.callbacks)
+    sol = eng.solve(p.y0_flat, grid, p.t_cpu)
+    return sol, eng
+
+
+def _unflatten(p, sol):
+    if p.is_tuple:
+        return p.layout.views(sol, (sol.shape[0],))                                    # odeint.py:102-103
+    return sol.view(sol.shape[0], *p.shape)
+
+
+def _func_requires_grad(func):
+    if isinstance(func, torch.nn.Module):
+        return any(q.requires_grad for q in func.parameters())
+    return False
+
+
+def odeint(func, y0, t, *, rtol=1e-7, atol=1e-9, method=None, options=None, event_fn=None):
+    """Integrate dy/dt = func(t, y), y(t[0]) = y0 and return y at every t (odeint.py:49-108).
+
+    Arguments, defaults, output shape/dtype and errors are the reference's.  `options` additionally
+    accepts `graph` (True/False/'auto'), `run_ahead` (int; 0 reproduces the reference's exact func
+    call sequence) and `process_group` (batch-sharded solve with a common step size).
+    Gradients are provided by odeint_adjoint; plain odeint returns a tensor without history.
+    """
+    p = normalise(func, y0, t, rtol, atol, method, options, event_fn)
+    if torch.is_grad_enabled():
+        y_req = any(y_.requires_grad for y_ in y0) if p.is_tuple else y0.requires_grad
+        if y_req or t.requires_grad:
+            raise NotImplementedError(
+                "backpropagation through the solver's internals is not part of the B200 hot path "
+                "(SURVEY.md section 8(f) item 4); use odeint_adjoint for gradients or call odeint under "
+                "torch.no_grad()")
+        if _func_requires_grad(func):
+            warnings.warn("torchdiffeq_b200.odeint returns a tensor without autograd history; use "
+                          "odeint_adjoint to train func's parameters", stacklevel=2)
+    with torch.no_grad():
+        sol, _ = _solve(p)
+    return _unflatten(p, sol)
