@@ -1,0 +1,314 @@
+#!/usr/bin/env python
+"""bench.py -- trajectories/sec of the dopri5 hot path on BASELINE.json's configs[1]
+(dopri5 adaptive, batch=65536 dim=128 linear ODE y' = A y, float32, rtol=1e-5, atol=1e-7, t in [0, 10]).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+A "step" is one complete odeint solve of the batch (about 74 step attempts, 446 func evaluations).
+N > 1 (torchrun, one rank per GPU): every rank integrates its own 65536 trajectories (weak scaling,
+configs[4] at N=8) and the ranks share one scalar all-reduce per attempt so that all take the common
+dt of the unsharded problem.
+
+Prints ONE JSON line (rank 0).  `value` is measured with inputs resident in HBM; `e2e` goes through the
+public API with pinned HOST buffers (H2D of y0 and D2H of y(t_end) inside the timed region);
+`roofline` is the stage-combine kernel's algorithmic bytes / its CUDA-event time against the measured
+HBM peak; `cpu_baseline` is the CPU oracle (a port of the reference's algorithm, oracle/) on a bounded
+sample.  --impl reference times that CPU port alone on the host cores.
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+import torch  # noqa: E402
+
+B_PER_GPU, DIM = 65536, 128
+T_SPAN = (0.0, 10.0)
+RTOL, ATOL = 1e-5, 1e-7
+METRIC = "trajectories/sec (dopri5, batch=65536 dim=128)"
+
+
+def make_problem(device, batch, rank=0):
+    import problems as P
+    f = P.BatchedLinear(DIM, torch.float32).to(device)
+    g = torch.Generator().manual_seed(1 + rank)
+    y0 = torch.randn(batch, DIM, generator=g)
+    t = torch.tensor(T_SPAN)
+    return f, y0, t
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            return json.load(f).get("hbm_gbs", 6650.0), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled during the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.rows, self.proc, self.index = [], None, index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm = sorted(int(r[0]) for r in self.rows if r and r[0].isdigit())
+        mx = [int(r[1]) for r in self.rows if len(r) > 1 and r[1].isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({n for r in self.rows if len(r) >= 6 for n, v in zip(names, r[2:6]) if v.lower().startswith("active")})
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
+                "samples": len(sm)}
+
+
+def cpu_port_run(batch, threads):
+    """One solve of the workload at `batch` rows with the CPU oracle; returns (seconds, stats)."""
+    from oracle import ode_oracle as O
+    torch.set_num_threads(threads)
+    f, y0, t = make_problem("cpu", batch)
+    rec = {}
+    with torch.no_grad():
+        t0 = time.perf_counter()
+        O.odeint_adaptive(f, y0, t, "dopri5", rtol=RTOL, atol=ATOL, record=rec)
+        dt = time.perf_counter() - t0
+    return dt, rec
+
+
+def run_reference(args):
+    """--impl reference: the CPU port of the reference's algorithm on the host cores, bounded sample."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    sample_b = 4096
+    for _ in range(max(1, min(args.warmup, 1))):
+        cpu_port_run(sample_b, threads)
+    times = []
+    steps = max(1, args.steps)
+    for _ in range(steps):
+        dt, rec = cpu_port_run(sample_b, threads)
+        times.append(dt)
+    total = sum(times)
+    value = sample_b * steps / total
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": "trajectories/s", "n_gpus": args.gpus,
+        "steps": steps, "warmup": min(args.warmup, 1), "ms_per_step": 1e3 * total / steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "configs[1]: dopri5 linear ODE dim=128 f32 rtol=1e-5 atol=1e-7 t=[0,10]",
+                   "sample": "batch=%d rows of the 65536-row workload per step (same t span, tolerances, seeds)" % sample_b},
+        "cpu_baseline": {"value": value, "unit": "trajectories/s", "cores": threads, "kind": "port",
+                         "sample": "batch=%d, %d attempts/solve" % (sample_b, rec["n_accept"] + rec["n_reject"])},
+        "e2e": {"value": value, "unit": "trajectories/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+def roofline_probe(dev, n_elems, reps=20):
+    """CUDA-event time of the stage-combine and error-norm launches of ONE dopri5 attempt at the benchmark's
+    size, issued through the C ABI on buffers larger than L2 (9 arrays x 33.5 MB).  Returns per-launch
+    durations (ms) for the 6 combine rows and the norm."""
+    from torchdiffeq_b200 import _lib
+    from torchdiffeq_b200._engine import AdaptiveEngine, _stream
+    eng = AdaptiveEngine(lambda t, y: y, n_elems, torch.float32, dev, "dopri5", rtol=RTOL, atol=ATOL, first_step=0.05)
+    eng.t_out = torch.tensor([0.0, 10.0], dtype=torch.float64, device=dev)
+    eng.solution = torch.zeros(2, 4, dtype=torch.float32, device=dev)
+    lib = eng.lib
+    _lib.check(lib.tdq_ctrl_init(eng.ctrl.data_ptr(), C.byref(eng.tab), C.byref(eng.opt), eng.t_out.data_ptr(), 0.0, 2,
+                                 eng.mbox_dev, _stream()))
+    _lib.check(lib.tdq_set_first_step(eng.ctrl.data_ptr(), 0.05, _stream()))
+    _lib.check(lib.tdq_prepare_attempt(eng.ctrl.data_ptr(), eng.dt_code, _stream()))
+    ks = [torch.randn(n_elems, device=dev) * 1e-3 for _ in range(7)]
+    y0 = torch.randn(n_elems, device=dev)
+    outs = [torch.empty(n_elems, device=dev) for _ in range(2)]
+    kp = _lib.ptr_array([k.data_ptr() for k in ks])
+    ctrl, tab, dc = eng.ctrl.data_ptr(), C.byref(eng.tab), eng.dt_code
+
+    def combine(row):
+        _lib.check(lib.tdq_stage_combine(ctrl, tab, dc, row, outs[row & 1].data_ptr(), y0.data_ptr(), kp, n_elems, _stream()))
+
+    def norm():
+        _lib.check(lib.tdq_error_norm(ctrl, tab, dc, y0.data_ptr(), outs[1].data_ptr(), kp, None, None, eng.seg_off,
+                                      eng.seg_len, 1, n_elems, eng.partials.data_ptr(), eng.norm_out.data_ptr(), None,
+                                      _stream()))
+    launches = [lambda r=r: combine(r) for r in range(6)] + [norm]
+    for fn in launches * 2:
+        fn()
+    torch.cuda.synchronize()
+    ms = [0.0] * 7
+    for _ in range(reps):
+        for i, fn in enumerate(launches):
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            fn()
+            b.record()
+            b.synchronize()
+            ms[i] += a.elapsed_time(b)
+    return [m / reps for m in ms]
+
+
+def run_ours(args):
+    import torch.distributed as dist
+    import torchdiffeq_b200 as tdq
+    from torchdiffeq_b200 import _lib
+    _lib.load()                                       # fail loudly if the CUDA library is missing
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (there is no CPU path)"
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    pg = None
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+        pg = True
+    f, y0_host, t = make_problem(dev, B_PER_GPU, rank)
+    y0_host = y0_host.pin_memory()
+    y0 = y0_host.to(dev)
+    t_dev = t.to(dev)
+    opts = {"graph": True, "run_ahead": 2}
+    if pg:
+        opts["process_group"] = pg
+    stats = {}
+
+    def solve(y):
+        with torch.no_grad():
+            return tdq.odeint(f, y, t_dev, method="dopri5", rtol=RTOL, atol=ATOL, options=dict(opts), _stats=stats)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    W = max(3, args.warmup)
+    for _ in range(W):
+        out = solve(y0)
+    barrier()
+    # ---- device-resident metric ------------------------------------------------------------------
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    launches0 = stats.get("launches", 0)
+    barrier()
+    ev0.record()
+    for _ in range(args.steps):
+        out = solve(y0)
+    ev1.record()
+    barrier()
+    ms = ev0.elapsed_time(ev1)
+    launches = stats.get("launches", 0) - launches0
+    clocks = sampler.stop() if rank == 0 else None
+    # ---- end to end: pinned host y0 -> device -> solve -> y(t_end) back to pinned host -----------------
+    res_host = torch.empty(B_PER_GPU, DIM, dtype=torch.float32).pin_memory()
+    for _ in range(2):
+        res_host.copy_(solve(y0_host.to(dev, non_blocking=True))[-1], non_blocking=True)
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        res_host.copy_(solve(y0_host.to(dev, non_blocking=True))[-1], non_blocking=True)
+    e1.record()
+    barrier()
+    ms_e2e = e0.elapsed_time(e1)
+    if world > 1:
+        tm = torch.tensor([ms, ms_e2e], device=dev, dtype=torch.float64)
+        dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+        ms, ms_e2e = float(tm[0]), float(tm[1])
+    # sanity of the result (norm preservation of the skew field) -- a wrong answer must not be timed silently
+    n0, n1 = y0.norm(dim=1), out[-1].norm(dim=1)
+    drift = float(((n1 - n0).abs() / n0).max())
+    assert drift < 5e-3, "solution drifted: %g" % drift
+
+    if rank == 0:
+        n_elems = B_PER_GPU * DIM
+        peak, peak_src = measured_peaks()
+        probe = roofline_probe(dev, n_elems)
+        nnz = [1, 2, 3, 4, 5, 5]                          # non-zero beta entries per dopri5 row
+        comb_bytes = sum((k + 2) * n_elems * 4 for k in nnz)          # 32*N*s
+        comb_ms = sum(probe[:6])
+        norm_bytes = 8 * n_elems * 4
+        achieved = comb_bytes / (comb_ms * 1e-3) / 1e9
+        group = (comb_bytes + norm_bytes) / ((comb_ms + probe[6]) * 1e-3) / 1e9
+        threads = os.cpu_count() or 1
+        cpu_b = 4096
+        cpu_s, cpu_rec = cpu_port_run(cpu_b, threads) if args.cpu_baseline and world == 1 else (None, None)
+        total_traj = B_PER_GPU * world * args.steps
+        line = {
+            "metric": METRIC, "value": total_traj / (ms * 1e-3), "unit": "trajectories/s", "n_gpus": world,
+            "steps": args.steps, "warmup": W, "ms_per_step": ms / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "configs[1]: dopri5 adaptive, batch=65536 dim=128 linear ODE y'=Ay, f32, rtol=1e-5 "
+                                   "atol=1e-7, t=[0,10]" + (" x %d ranks (configs[4] layout)" % world if world > 1 else ""),
+                       "batch_per_gpu": B_PER_GPU, "dim": DIM, "exec": "cuda-graph step body, run_ahead=2",
+                       "attempts_per_solve": stats.get("attempts"), "nfe_per_solve": stats.get("nfe"),
+                       "l2": "working set 20 arrays x 33.5 MB >> 126 MB L2 (no flush needed)",
+                       "parallelism": "batch-sharded, 1 all-reduce(3 x f64)/attempt" if world > 1 else "single GPU"},
+            "e2e": {"value": total_traj / (ms_e2e * 1e-3), "unit": "trajectories/s",
+                    "h2d_bytes_per_step": y0_host.numel() * 4 * world, "d2h_bytes_per_step": res_host.numel() * 4 * world},
+            "gpu_launches": launches,
+            "clocks": clocks,
+            "roofline": {"bound": "hbm", "kernel": "k_combine (6 launches per attempt)", "achieved": achieved,
+                         "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                         "peak_source": peak_src, "algorithmic_bytes_per_attempt": comb_bytes,
+                         "ms_per_launch": [round(x, 5) for x in probe[:6]],
+                         "combine_plus_error_norm": {"achieved": group, "frac": group / peak,
+                                                     "bytes": comb_bytes + norm_bytes, "ms": comb_ms + probe[6]},
+                         "error_norm": {"achieved": norm_bytes / (probe[6] * 1e-3) / 1e9, "ms": probe[6]}},
+            "result_check": {"max_rel_norm_drift": drift},
+        }
+        if cpu_s is not None:
+            line["cpu_baseline"] = {"value": cpu_b / cpu_s, "unit": "trajectories/s", "cores": threads, "kind": "port",
+                                    "sample": "batch=%d rows of the workload, one solve, %d attempts, %.1f s" %
+                                              (cpu_b, cpu_rec["n_accept"] + cpu_rec["n_reject"], cpu_s)}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", dest="cpu_baseline", action="store_false")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

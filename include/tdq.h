@@ -95,6 +95,9 @@ typedef struct {
 
 /* ---- library ------------------------------------------------------------------------------ */
 int tdq_abi_version(void);
+/* sizeof the ABI structs as compiled (0: tdq_tableau, 1: tdq_options, 2: tdq_mailbox); lets a foreign
+ * binding verify its own struct definitions. */
+size_t tdq_sizeof(int32_t which);
 const char *tdq_last_error(void);
 /* Number of SMs of the current device (grid sizing). */
 int tdq_device_sm_count(int *out);

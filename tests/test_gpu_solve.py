@@ -1,0 +1,244 @@
+"""Whole-solve parity of the CUDA path (through the public odeint / odeint_adjoint API and hence the
+C ABI) against (a) the CPU oracle on the same seeded inputs and (b) the committed golden vectors
+produced by the unmodified reference.  Tolerances are the north_star's: 1e-4/1e-6 float32,
+1e-5/1e-7 float64 (rtol/atol) on solutions, 1e-4 relative on adjoint gradients; the reference's own
+acceptance thresholds against exact solutions (tests/odeint_tests.py:45-58) are asserted as well."""
+import os
+import warnings
+
+import pytest
+import torch
+
+import problems as P
+from oracle import ode_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+G = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+ld = lambda name: torch.load(os.path.join(G, name), weights_only=False)
+DEV = "cuda:0"
+TOL = {torch.float32: dict(rtol=1e-4, atol=1e-6), torch.float64: dict(rtol=1e-5, atol=1e-7)}
+MODES = {"lockstep": {"run_ahead": 0, "graph": False}, "eager": {"run_ahead": 2, "graph": False},
+         "graph": {"run_ahead": 2, "graph": True}}
+
+
+def tdq():
+    import torchdiffeq_b200
+    return torchdiffeq_b200
+
+
+class Counted(torch.nn.Module):
+    def __init__(self, f):
+        super().__init__()
+        self.f, self.nfe = f, 0
+
+    def forward(self, t, y):
+        self.nfe += 1
+        return self.f(t, y)
+
+
+ZOO = ld("zoo.pt")
+ZOO_KEYS = [k for k in sorted(ZOO) if k.split("/")[1] in ("dopri5", "dopri8", "rk4", "bosh3")]
+
+
+@pytest.mark.parametrize("key", ZOO_KEYS)
+def test_zoo_lockstep(key):
+    """The reference's TestSolverError.test_odeint (odeint_tests.py:17-58) on the CUDA path, plus the
+    golden/oracle comparison and the exact NFE identity of lock-step mode."""
+    ode, method, dt, direction = key.split("/")
+    dtype = getattr(torch, dt)
+    case = ZOO[key]
+    f, y0, t, sol = P.construct_problem(DEV, ode=ode, reverse=direction == "rev", dtype=dtype)
+    cf = Counted(f)
+    kw = dict(case["kw"])
+    opts = {"run_ahead": 0, "graph": False}
+    with torch.no_grad():
+        y = tdq().odeint(cf, y0, t, method=method, options=opts, **kw)
+    assert y.shape == sol.shape and y.dtype == dtype and y.device.type == "cuda"
+    eps = {"constant": 3e-4, "sine": 3e-4, "linear": 2e-3, "exp": 5e-2}[ode]
+    if method == "bosh3":
+        eps = {"constant": 1e-3, "sine": 5e-3, "linear": 2e-3, "exp": 5e-2}[ode]
+    rel = ((sol - y) / sol).abs().max()
+    assert rel < eps, rel
+    tol = 5e-4 if dtype == torch.float32 else 1e-6
+    assert torch.allclose(y.cpu(), case["y"], rtol=tol, atol=tol * 1e-2), (y.cpu() - case["y"]).abs().max()
+    if method == "rk4":
+        assert torch.equal(y.cpu(), case["y"])            # fixed grid: same roundings as the reference, bitwise
+        assert cf.nfe == case["nfe"]
+
+
+@pytest.mark.parametrize("mode", sorted(MODES))
+@pytest.mark.parametrize("dtype", [torch.float32, torch.float64])
+@pytest.mark.parametrize("name", ["span", "dense"])
+def test_linear_batch_vs_oracle(name, dtype, mode):
+    """C2-shaped problem at B=64: CUDA vs oracle (same summation order => same step sequence) vs reference golden."""
+    case = ld("linear_batch.pt")["%s/%s" % (name, str(dtype).split(".")[1])]
+    f = P.BatchedLinear(128, dtype)
+    y0 = torch.randn(64, 128, generator=torch.Generator().manual_seed(1)).to(dtype)
+    rec = {}
+    co = O.Counter(f)
+    with torch.no_grad():
+        want = O.odeint_adaptive(co, y0, case["t"], "dopri5", rtol=1e-5, atol=1e-7, record=rec)
+    cf = Counted(f.to(DEV))
+    with torch.no_grad():
+        got = tdq().odeint(cf, y0.to(DEV), case["t"].to(DEV), method="dopri5", rtol=1e-5, atol=1e-7,
+                           options=dict(MODES[mode]))
+    assert torch.allclose(got.cpu(), want, **TOL[dtype]), (got.cpu() - want).abs().max()
+    assert torch.allclose(got.cpu(), case["y"], **TOL[dtype])
+    if mode == "lockstep":
+        assert cf.nfe == co.nfe == 2 + 6 * (rec["n_accept"] + rec["n_reject"])
+
+
+def test_full_size_properties():
+    """BASELINE config 2 at full size (B=65536, D=128, float32, t in [0, 1]): properties that do not need
+    the oracle.  The skew-symmetric field preserves every trajectory's 2-norm; integrating forward then
+    backward returns to y0; the batch result equals the result of its first rows solved alone only up to
+    the common-dt coupling, so instead we check linearity: odeint(a*y0) == a*odeint(y0) for a power of 2
+    with atol scaled (bitwise, every operation is homogeneous)."""
+    f = P.BatchedLinear(128).to(DEV)
+    y0 = torch.randn(65536, 128, generator=torch.Generator().manual_seed(1)).to(DEV)
+    t = torch.tensor([0., 1.], device=DEV)
+    with torch.no_grad():
+        y = tdq().odeint(f, y0, t, method="dopri5", rtol=1e-5, atol=1e-7)
+        n0, n1 = y0.norm(dim=1), y[-1].norm(dim=1)
+        assert ((n1 - n0).abs() / n0).max() < 5e-4
+        back = tdq().odeint(f, y[-1], t.flip(0), method="dopri5", rtol=1e-5, atol=1e-7)
+        assert torch.allclose(back[-1], y0, rtol=1e-3, atol=1e-4)
+        y2 = tdq().odeint(f, 4 * y0, t, method="dopri5", rtol=1e-5, atol=4 * 1e-7)
+        assert torch.equal(y2, 4 * y)
+
+
+def test_spiral_rk4_golden():
+    case = ld("spiral_rk4.pt")
+    f = P.Spiral().to(DEV)
+    with torch.no_grad():
+        y = tdq().odeint(f, case["y0"].to(DEV), torch.linspace(0., 25., 1000).to(DEV), method="rk4")
+        y2 = tdq().odeint(f, case["y0"][:16].to(DEV), case["t2"].to(DEV), method="rk4", options={"step_size": 0.03})
+    # elementwise part is bitwise the reference's; func (a 2x2 mm) may differ in the last bit between CPU and GPU
+    assert torch.allclose(y[case["rows"]].cpu(), case["y_rows"], rtol=1e-4, atol=1e-6)
+    assert torch.allclose(y2.cpu(), case["y2"], rtol=1e-4, atol=1e-6)
+
+
+@pytest.mark.parametrize("mode", ["lockstep", "graph"])
+@pytest.mark.parametrize("key", sorted(ld("adjoint_mlp.pt")))
+def test_adjoint_golden(key, mode):
+    """odeint_adjoint gradients vs the reference's (gradient_tests.py:34-86 style), 1e-4 relative."""
+    case = ld("adjoint_mlp.pt")[key]
+    name, norm, dt = key.split("/")
+    dtype = getattr(torch, dt)
+    f = P.MLPField(dim=8, hidden=16, seed=0, dtype=dtype).to(DEV)
+    y0 = torch.randn(32, 8, generator=torch.Generator().manual_seed(1)).to(dtype).to(DEV).requires_grad_(True)
+    t = case["t"].to(DEV)
+    ao = dict(MODES[mode])
+    if norm == "seminorm":
+        ao["norm"] = "seminorm"
+    y = tdq().odeint_adjoint(f, y0, t, method="dopri5", rtol=1e-6, atol=1e-8, options=dict(MODES[mode]),
+                             adjoint_options=ao)
+    loss = y[-1].pow(2).mean() + (y[1].sum() * 0.01 if len(t) > 2 else 0)
+    loss.backward()
+    tol = 1e-4
+    assert torch.allclose(y.detach().cpu(), case["y"], rtol=tol, atol=1e-6)
+    scale = case["gy0"].abs().max()
+    assert (y0.grad.cpu() - case["gy0"]).abs().max() <= tol * scale
+    for q, want in zip(f.parameters(), case["gp"]):
+        assert (q.grad.cpu() - want).abs().max() <= tol * max(want.abs().max(), 1e-6), (q.grad.cpu() - want).abs().max()
+
+
+DET = ld("detest.pt")
+
+
+@pytest.mark.parametrize("key", [k for k in sorted(DET) if k.split("/")[0] in ("A3", "B1", "B4", "B5")])
+def test_detest_batched(key):
+    """BASELINE config 4 style: DETEST problem replicated over a trailing batch of 4096 (identical columns,
+    so the global RMS norm equals the single-trajectory norm and the reference's NFE table applies)."""
+    name, method, tol = key.split("/")
+    tol = float(tol)
+    f, y0, t0 = P.detest(name)
+    y0 = torch.tensor(y0, dtype=torch.float64)
+    y0 = (y0[0] if name.startswith("A") else y0)
+    yb = y0.unsqueeze(-1).repeat(*([1] * y0.dim()), 4096).to(DEV)
+    cf = Counted(f)
+    with torch.no_grad():
+        y = tdq().odeint(cf, yb, torch.tensor([t0, 20.0], dtype=torch.float64, device=DEV), method=method,
+                         rtol=tol, atol=tol, options={"run_ahead": 0, "graph": False})
+    S = 6 if method == "dopri5" else 13
+    assert abs(cf.nfe - DET[key]["nfe"]) <= max(2 * S, DET[key]["nfe"] // 20), (cf.nfe, DET[key]["nfe"])
+    ytol = max(100 * tol, 1e-3 if method == "dopri8" else 1e-6)
+    assert torch.allclose(y[-1][..., 0].cpu(), DET[key]["y"], rtol=ytol, atol=ytol)
+    assert torch.equal(y[-1][..., 0], y[-1][..., -1])          # columns stay identical
+
+
+@pytest.mark.parametrize("key", ["min_step", "max_step", "first_step", "step_t", "factors"])
+def test_options_golden(key):
+    case = ld("options.pt")[key]
+    f, y0, t, _ = P.construct_problem(DEV, ode="linear", dtype=torch.float64)
+    opts = dict(case["opts"], run_ahead=0, graph=False)
+    with torch.no_grad():
+        y = tdq().odeint(f, y0, t, method="dopri5", options=opts)
+    assert abs(f.nfe - case["nfe"]) <= max(12, case["nfe"] // 10), (f.nfe, case["nfe"])
+    if key in ("min_step", "max_step", "step_t"):
+        assert f.nfe == case["nfe"]                               # odeint_tests.py:251-268 (26 with min_step=2)
+    assert torch.allclose(y.cpu(), case["y"], rtol=1e-6, atol=1e-8)
+
+
+def test_tuple_state_and_vector_tol():
+    """api_tests.py:12-26: tuple state == flattened tensor state; misc.py:115-123 per-piece tolerances."""
+    case = ld("options.pt")["tuple"]
+    A = P.skew_matrix(6, torch.float64).to(DEV)
+
+    def tf(t_, state):
+        a, b = state
+        return (a @ A.t(), -0.5 * b + a[:, :2].sum())
+    ya, yb, tt = case["ya"].to(DEV), case["yb"].to(DEV), case["t"].to(DEV)
+    with torch.no_grad():
+        sol = tdq().odeint(tf, (ya, yb), tt, method="dopri5", rtol=1e-6, atol=1e-8)
+        sol_v = tdq().odeint(tf, (ya, yb), tt, method="dopri5", rtol=(1e-6, 1e-4), atol=(1e-8, 1e-7))
+    assert isinstance(sol, tuple) and sol[0].shape == (5, 5, 6) and sol[1].shape == (5, 3)
+    for got, want in zip(sol, case["sol"]):
+        assert torch.allclose(got.cpu(), want, rtol=1e-6, atol=1e-8)
+    for got, want in zip(sol_v, case["sol_vtol"]):
+        assert torch.allclose(got.cpu(), want, rtol=1e-4, atol=1e-6)
+
+
+def test_no_integration_and_errors():
+    """odeint_tests.py:98-111 (len(t) == 1 returns y0) and the error conventions of SURVEY.md 8(b)."""
+    f, y0, t, _ = P.construct_problem(DEV, ode="constant", dtype=torch.float64)
+    with torch.no_grad():
+        y = tdq().odeint(f, y0, t[0:1], method="dopri5")
+    assert (y[0] - y0).abs().max() < 1e-12
+    with pytest.raises(ValueError):
+        tdq().odeint(f, y0, t, method="nope")
+    with pytest.raises(AssertionError, match="max_num_steps exceeded"):
+        tdq().odeint(f, y0, t, method="dopri5", options={"max_num_steps": 2, "run_ahead": 0})
+    with pytest.raises(AssertionError, match="underflow in dt"):
+        fs, ys, ts, _ = P.construct_problem(DEV, ode="sine", dtype=torch.float64)
+        tdq().odeint(lambda t_, y_: y_ * float("inf"), ys, ts, method="dopri5")
+    with pytest.raises(TypeError):
+        tdq().odeint(f, y0, torch.tensor([0, 1], device=DEV), method="dopri5")
+
+
+def test_callbacks_counts():
+    """odeint_tests.py:289-386: accept + reject == step callbacks; lock step is forced."""
+    class F(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.A = P.skew_matrix(10, torch.float64).to(DEV)
+            self.n = {"step": 0, "accept": 0, "reject": 0}
+
+        def forward(self, t, y):
+            return self.A @ y
+
+        def callback_step(self, t0, y0, dt):
+            self.n["step"] += 1
+            assert t0.dtype == torch.float64 and y0.shape == (10,)
+
+        def callback_accept_step(self, t0, y0, dt):
+            self.n["accept"] += 1
+
+        def callback_reject_step(self, t0, y0, dt):
+            self.n["reject"] += 1
+    f = F()
+    with torch.no_grad():
+        tdq().odeint(f, torch.ones(10, dtype=torch.float64, device=DEV),
+                     torch.linspace(1, 8, 10, dtype=torch.float64, device=DEV), method="dopri5", rtol=1e-3, atol=1e-5)
+    assert f.n["step"] > 0 and f.n["accept"] + f.n["reject"] == f.n["step"]

@@ -158,6 +158,8 @@ class AdaptiveEngine:
         self._graph_keep = None
         self.n_attempts = 0              # attempts that did work (from the mailbox counters)
         self.nfe = 0                     # func evaluations issued by the host
+        self.launches = 0                # libtdq kernel launches issued (graph replays count their nodes)
+        self._graph_launches = 0
 
     def __del__(self):
         try:
@@ -207,10 +209,14 @@ class AdaptiveEngine:
             srcs.append(p.data_ptr())
         for lo in range(0, len(srcs), _lib.TDQ_MAX_SEGS):
             hi = min(lo + _lib.TDQ_MAX_SEGS, len(srcs))
-            _lib.check(self.lib.tdq_pack_segments(
+            self._launch(self.lib.tdq_pack_segments(
                 self.dt_code, buf.data_ptr(), _lib.ptr_array(srcs[lo:hi]), _lib.i64_array(offs[lo:hi]),
                 _lib.i64_array(lens[lo:hi]), _lib.dbl_array(scales[lo:hi]), hi - lo, _stream()))
         return buf
+
+    def _launch(self, rc):
+        _lib.check(rc)
+        self.launches += 1
 
     def _slot(self, i):
         if i not in self.kslots:
@@ -228,7 +234,7 @@ class AdaptiveEngine:
             self.reduce_fn(buf)
 
     def _sumsq(self, x, x2, out):
-        _lib.check(self.lib.tdq_scaled_sumsq(
+        self._launch(self.lib.tdq_scaled_sumsq(
             self.ctrl.data_ptr(), self.dt_code, x.data_ptr(), x2.data_ptr() if x2 is not None else None,
             self.y0w.data_ptr(),
             self.rtol_vec.data_ptr() if self.rtol_vec is not None else None,
@@ -245,16 +251,16 @@ class AdaptiveEngine:
         keep = [self.k0]
         for i in range(S):
             out = self.y1 if (i == S - 1 and self.fsal) else self.ytmp
-            _lib.check(lib.tdq_stage_combine(ctrl, tab, dc, i, out.data_ptr(), self.y0w.data_ptr(),
+            self._launch(lib.tdq_stage_combine(ctrl, tab, dc, i, out.data_ptr(), self.y0w.data_ptr(),
                                              _lib.ptr_array(k), self.n, st))
             f = self._call_fn(self.tstage[i], out, i + 1)
             keep.append(f)
             k[i + 1] = f.data_ptr()
         if not self.fsal:
-            _lib.check(lib.tdq_stage_combine(ctrl, tab, dc, S, self.y1.data_ptr(), self.y0w.data_ptr(),
+            self._launch(lib.tdq_stage_combine(ctrl, tab, dc, S, self.y1.data_ptr(), self.y0w.data_ptr(),
                                              _lib.ptr_array(k), self.n, st))
         kp = _lib.ptr_array(k)
-        _lib.check(lib.tdq_error_norm(
+        self._launch(lib.tdq_error_norm(
             ctrl, tab, dc, self.y0w.data_ptr(), self.y1.data_ptr(), kp,
             self.rtol_vec.data_ptr() if self.rtol_vec is not None else None,
             self.atol_vec.data_ptr() if self.atol_vec is not None else None,
@@ -268,7 +274,7 @@ class AdaptiveEngine:
             ratio_ptr = self.ratio_buf.data_ptr()
         else:
             self._reduce(self.norm_out)
-        _lib.check(lib.tdq_controller(ctrl, dc, self.norm_out.data_ptr(), self.seg_counts.data_ptr(), self.n_seg,
+        self._launch(lib.tdq_controller(ctrl, dc, self.norm_out.data_ptr(), self.seg_counts.data_ptr(), self.n_seg,
                                       ratio_ptr, st))
         self._k_last = (k, kp, keep)
         return k, kp, keep
@@ -276,9 +282,9 @@ class AdaptiveEngine:
     def _attempt_back(self, kp):
         """Accepted-step work (predicated on the device accept flag)."""
         lib, ctrl, tab, dc, st = self.lib, self.ctrl.data_ptr(), C.byref(self.tab), self.dt_code, _stream()
-        _lib.check(lib.tdq_interp_fit_commit(ctrl, tab, dc, self.y0w.data_ptr(), self.y1.data_ptr(), kp,
+        self._launch(lib.tdq_interp_fit_commit(ctrl, tab, dc, self.y0w.data_ptr(), self.y1.data_ptr(), kp,
                                              self.coeff_ptrs, self.n, st))
-        _lib.check(lib.tdq_interp_eval(ctrl, dc, self.coeff_ptrs, self.solution.data_ptr(), self.n, st))
+        self._launch(lib.tdq_interp_eval(ctrl, dc, self.coeff_ptrs, self.solution.data_ptr(), self.n, st))
 
     def _attempt(self):
         k, kp, keep = self._attempt_front()
@@ -335,7 +341,7 @@ class AdaptiveEngine:
         _lib.check(lib.tdq_ctrl_init(self.ctrl.data_ptr(), C.byref(self.tab), C.byref(self.opt),
                                      self.t_out.data_ptr(), t_start, n_out, self.mbox_dev, st))
         if self.step_t is not None and self.step_t.numel() > 0:
-            _lib.check(lib.tdq_ctrl_set_step_t(self.ctrl.data_ptr(), self.step_t.data_ptr(),
+            self._launch(lib.tdq_ctrl_set_step_t(self.ctrl.data_ptr(), self.step_t.data_ptr(),
                                                int(self.step_t.numel()), st))
         dc, ctrl = self.dt_code, self.ctrl.data_ptr()
 
@@ -350,18 +356,18 @@ class AdaptiveEngine:
             else:
                 self._sumsq(self.y0w, None, self.dsum[0])
                 self._sumsq(self.k0, None, self.dsum[1])
-                _lib.check(lib.tdq_initial_step_h0(ctrl, dc, self.dsum[0].data_ptr(), self.dsum[1].data_ptr(),
+                self._launch(lib.tdq_initial_step_h0(ctrl, dc, self.dsum[0].data_ptr(), self.dsum[1].data_ptr(),
                                                    self.seg_counts.data_ptr(), self.n_seg, st))
-                _lib.check(lib.tdq_initial_step_probe(ctrl, dc, self.ytmp.data_ptr(), self.y0w.data_ptr(),
+                self._launch(lib.tdq_initial_step_probe(ctrl, dc, self.ytmp.data_ptr(), self.y0w.data_ptr(),
                                                       self.k0.data_ptr(), self.n, st))
                 f1 = self._call_fn(self.taux[1], self.ytmp, 1)
                 self._sumsq(f1, self.k0, self.dsum[2])
                 del f1
-                _lib.check(lib.tdq_initial_step_finish(ctrl, dc, self.dsum[2].data_ptr(),
+                self._launch(lib.tdq_initial_step_finish(ctrl, dc, self.dsum[2].data_ptr(),
                                                        self.seg_counts.data_ptr(), self.n_seg, st))
         else:
-            _lib.check(lib.tdq_set_first_step(ctrl, float(self.first_step), st))
-        _lib.check(lib.tdq_prepare_attempt(ctrl, dc, st))
+            self._launch(lib.tdq_set_first_step(ctrl, float(self.first_step), st))
+        self._launch(lib.tdq_prepare_attempt(ctrl, dc, st))
 
         if n_out > 1:
             if self.callbacks or self.run_ahead == 0:
@@ -427,6 +433,7 @@ class AdaptiveEngine:
             if self._graph is not None:
                 self._graph.replay()
                 self.nfe += self.S
+                self.launches += self._graph_launches
             else:
                 self._attempt()
             issued += 1
@@ -437,10 +444,11 @@ class AdaptiveEngine:
     def _capture(self):
         try:
             g = torch.cuda.CUDAGraph()
-            nfe = self.nfe
+            nfe, launches = self.nfe, self.launches
             with torch.cuda.graph(g):
                 keep = self._attempt()
-            self.nfe = nfe                                  # capture runs no kernels
+            self._graph_launches = self.launches - launches
+            self.nfe, self.launches = nfe, launches         # capture runs no kernels
             self._graph, self._graph_keep = g, keep
         except Exception as e:                              # func is not capturable: stay eager
             self._graph = None
@@ -478,4 +486,4 @@ class AdaptiveEngine:
             h1 = (0.01 / max(d1, d2)) ** (1. / float(order + 1))
         h1 = h1.abs()
         dt = float(torch.min(100 * h0, h1).to(torch.float64))
-        _lib.check(self.lib.tdq_set_first_step(self.ctrl.data_ptr(), dt, _stream()))
+        self._launch(self.lib.tdq_set_first_step(self.ctrl.data_ptr(), dt, _stream()))

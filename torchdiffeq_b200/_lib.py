@@ -59,6 +59,7 @@ _ptab = C.POINTER(Tableau)
 # name -> (restype, argtypes); mirrors include/tdq.h one to one
 _SIGNATURES = {
     "tdq_abi_version": (C.c_int, []),
+    "tdq_sizeof": (_sz, [_i32]),
     "tdq_last_error": (C.c_char_p, []),
     "tdq_device_sm_count": (C.c_int, [C.POINTER(C.c_int)]),
     "tdq_tableau_get": (C.c_int, [C.c_char_p, _ptab]),
@@ -112,6 +113,9 @@ def load():
         fn.argtypes = args
     if lib.tdq_abi_version() != 1:
         raise TdqError("libtdq.so ABI version mismatch")
+    for which, st in ((0, Tableau), (1, Options), (2, Mailbox)):
+        if lib.tdq_sizeof(which) != C.sizeof(st):
+            raise TdqError("libtdq.so struct layout mismatch for %s; rebuild it" % st.__name__)
     _lib = lib
     return lib
 

@@ -173,6 +173,15 @@ extern "C" {
 
 int tdq_abi_version(void) { return TDQ_ABI_VERSION; }
 
+size_t tdq_sizeof(int32_t which) {
+    switch (which) {
+        case 0: return sizeof(tdq_tableau);
+        case 1: return sizeof(tdq_options);
+        case 2: return sizeof(tdq_mailbox);
+    }
+    return 0;
+}
+
 const char *tdq_last_error(void) { return g_err; }
 
 int tdq_device_sm_count(int *out) {
