@@ -156,6 +156,7 @@ class AdaptiveEngine:
         self._graph = None
         self._graph_failed = False
         self._graph_keep = None
+        self.capture_in_solve = True     # False: only a prime()d graph is used (solves run inside autograd backward)
         self.n_attempts = 0              # attempts that did work (from the mailbox counters)
         self.nfe = 0                     # func evaluations issued by the host
         self.launches = 0                # libtdq kernel launches issued (graph replays count their nodes)
@@ -318,6 +319,34 @@ class AdaptiveEngine:
         """Integrate from t64[0] through t64[-1] (ascending float64 device tensor); returns
         solution [len(t), n] (solvers.py:28-35).  The returned tensor is owned by the engine and is
         overwritten by the next solve() with the same number of output times."""
+        n_out = self._begin(y0_flat, t64, t_start)
+        if n_out > 1:
+            if self.callbacks or self.run_ahead == 0:
+                self._loop_lockstep()
+            else:
+                self._loop_run_ahead()
+        mb = self.mbox_host.contents
+        self.n_accept, self.n_reject = int(mb.n_accept), int(mb.n_reject)
+        self.n_attempts = self.n_accept + self.n_reject
+        return self.solution
+
+    def prime(self, y0_flat, t64, t_start=None):
+        """Warm up and capture the attempt graph ahead of time on representative inputs (one eager
+        attempt, then capture).  Used by odeint_adjoint to capture the backward step body during the
+        FORWARD call: capturing inside autograd's backward is unsafe (a re-entrant engine call may run
+        unrelated nodes of the outer graph on the legacy stream in the middle of the capture)."""
+        if self.graph_opt not in (True, "auto") or self.callbacks or self.run_ahead == 0:
+            return False
+        n_out = self._begin(y0_flat, t64, t_start)
+        if n_out <= 1:
+            return False
+        self._attempt()
+        self._capture()
+        torch.cuda.current_stream().synchronize()
+        return self._graph is not None
+
+    def _begin(self, y0_flat, t64, t_start=None):
+        """Everything of a solve that precedes the first attempt (rk_common.py:166-241)."""
         lib = self.lib
         n_out = int(t64.numel())
         self.t_out = t64.contiguous()
@@ -368,16 +397,7 @@ class AdaptiveEngine:
         else:
             self._launch(lib.tdq_set_first_step(ctrl, float(self.first_step), st))
         self._launch(lib.tdq_prepare_attempt(ctrl, dc, st))
-
-        if n_out > 1:
-            if self.callbacks or self.run_ahead == 0:
-                self._loop_lockstep()
-            else:
-                self._loop_run_ahead()
-        mb = self.mbox_host.contents
-        self.n_accept, self.n_reject = int(mb.n_accept), int(mb.n_reject)
-        self.n_attempts = self.n_accept + self.n_reject
-        return self.solution
+        return n_out
 
     # ---- lock step: the reference's exact call sequence --------------------------------------
     def _loop_lockstep(self):
@@ -417,7 +437,7 @@ class AdaptiveEngine:
         D = max(1, self.run_ahead)
         mb = self.mbox_host.contents
         issued = 0
-        use_graph = self.graph_opt in (True, "auto") and not self._graph_failed
+        use_graph = self.graph_opt in (True, "auto") and not self._graph_failed and self.capture_in_solve
         # attempt 1 runs eagerly: it is a real attempt and doubles as the warm-up torch wants before capture
         if self._graph is None:
             self._attempt()

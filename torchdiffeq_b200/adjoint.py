@@ -36,6 +36,178 @@ def find_parameters(module):
     return list(module.parameters())
 
 
+class _BackwardSolver:
+    """The backward half of adjoint.py:36-153: augmented layout, dynamics, norm and one adaptive engine
+    shared by every output interval.  Built (and, in graph mode, captured) during the forward call."""
+
+    def __init__(self, p, adjoint_params, adjoint_rtol, adjoint_atol, adjoint_method, adjoint_options,
+                 t_requires_grad):
+        self.p = p
+        self.params = adjoint_params = tuple(adjoint_params)
+        self.t_requires_grad = t_requires_grad
+        dev, T, n = p.device, p.dtype, p.n
+        # ---- augmented layout: [vjp_t | y | adj_y | params...]   (adjoint.py:64-65) ----------
+        self.lay = lay = Layout([(1,), (n,), (n,)] + [q.shape for q in adjoint_params], T)
+        self.o_t, self.o_y, self.o_a = o_t, o_y, o_a = lay.offsets[0], lay.offsets[1], lay.offsets[2]
+        base_fn, fwd_layout = p.fn, p.layout
+        self.base_fn, self.fwd_layout = base_fn, fwd_layout
+
+        # ---- augmented dynamics (adjoint.py:72-105), returning RAW pieces ------------------
+        def aug_fn(t_, aug_flat):
+            y_ = aug_flat[o_y:o_y + n]
+            adj = aug_flat[o_a:o_a + n]
+            with torch.enable_grad():
+                tt = t_.detach()
+                if t_requires_grad:
+                    tt = tt.clone().requires_grad_(True)
+                yy = y_.detach().requires_grad_(True)
+                f = base_fn(tt, yy)                                  # Tensor, or tuple of pieces (tuple state)
+                if isinstance(f, tuple):
+                    outs = [f_.reshape(-1) for f_ in f]
+                    gouts = [adj[o:o + l] for o, l in zip(fwd_layout.offsets, fwd_layout.lens)]
+                else:
+                    outs = [f.reshape(-1)]
+                    gouts = [adj]
+                keep = [(o_, g_) for o_, g_ in zip(outs, gouts) if o_.requires_grad]
+                inputs = ((tt,) if t_requires_grad else ()) + (yy,) + adjoint_params
+                if keep:
+                    grads = torch.autograd.grad([o_ for o_, _ in keep], inputs, [g_ for _, g_ in keep],
+                                                allow_unused=True)   # +adj: the minus sits in the pack scale
+                else:
+                    grads = (None,) * len(inputs)
+            if t_requires_grad:
+                vjp_t, vjp_y, *vjp_params = grads
+            else:
+                vjp_t = None
+                vjp_y, *vjp_params = grads
+            if isinstance(f, tuple):
+                return (vjp_t, *[f_.detach() for f_ in f], vjp_y, *vjp_params)
+            return (vjp_t, f.detach(), vjp_y, *vjp_params)
+
+        # Pieces and their scales.  Reference: k_ref = mul * (vjp_t, f, vjp_y, vjp_p) with
+        # vjp = grad(f, ., -adj); the backward solve runs against the forward time direction, so after
+        # misc.py:273-279 either mul = -1 (forward ascending) or mul = +1 with the roles of the signs
+        # swapped -- in both cases the RAW slot (before the engine's t_sign) must hold
+        # (-g_t, +f, -g_y, -g_p) with g = grad(f, ., +adj).
+        if p.is_tuple:
+            f_offs = [o_y + o for o in fwd_layout.offsets]
+            f_lens = list(fwd_layout.lens)
+        else:
+            f_offs, f_lens = [o_y], [n]
+        offs = [o_t] + f_offs + [o_a] + list(lay.offsets[3:])
+        lens = [1] + f_lens + [n] + list(lay.lens[3:])
+        scales = [-1.0] + [1.0] * len(f_offs) + [-1.0] + [-1.0] * len(adjoint_params)
+        pieces = (offs, lens, scales)
+
+        # ---- adjoint norm (adjoint.py:243-288) -------------------------------------------
+        opts = dict(adjoint_options)
+        y_segs = [(o_y + o, l) for o, l in zip(fwd_layout.offsets, fwd_layout.lens)] if p.is_tuple else [(o_y, n)]
+        a_segs = [(o_a + o, l) for o, l in zip(fwd_layout.offsets, fwd_layout.lens)] if p.is_tuple else [(o_a, n)]
+        p_segs = [(o, l) for o, l in zip(lay.offsets[3:], lay.lens[3:]) if l > 0]
+        norm_fn, q_view, segs = None, None, None
+        adj_norm = opts.pop("norm", None)
+
+        def views_of(q):
+            yq, aq = q[o_y:o_y + n], q[o_a:o_a + n]
+            if p.is_tuple:
+                yq, aq = fwd_layout.views(yq), fwd_layout.views(aq)
+            else:
+                yq, aq = yq.view(p.shape), aq.view(p.shape)
+            return q[o_t:o_t + 1].view(()), yq, aq, [q[o:o + l].view(s) for o, l, s in
+                                                     zip(lay.offsets[3:], lay.lens[3:], lay.shapes[3:])]
+        self.views_of = views_of
+        if adj_norm is None or adj_norm == "seminorm":
+            segs = [(o_t, 1)] + y_segs + a_segs + ([] if adj_norm == "seminorm" else p_segs)
+            if p.norm_fn is not None or len(segs) > _lib.TDQ_MAX_SEGS:
+                state_norm = p.norm_fn if p.norm_fn is not None else (_mixed_norm if p.is_tuple else _rms_norm)
+                semi = adj_norm == "seminorm"
+
+                def norm_fn(parts):                                  # adjoint.py:247-250 / :267-271
+                    tq, yq, aq, pq = parts
+                    vals = [tq.abs(), state_norm(yq), state_norm(aq)]
+                    if not semi:
+                        vals.append(_mixed_norm(pq))
+                    return max(vals)
+                q_view, segs = views_of, None
+        else:
+            # user callable: gets (t, y, adj_y, *adj_params), y/adj_y expanded for tuple states (:273-288)
+            def norm_fn(parts):
+                tq, yq, aq, pq = parts
+                if p.is_tuple:
+                    return adj_norm((tq, *yq, *aq, *pq))
+                return adj_norm((tq, yq, aq, *pq))
+            q_view = views_of
+
+        # adjoint callbacks (adjoint.py:107-114)
+        callbacks = {}
+        for name, adj_name in zip(_CALLBACK_NAMES, _ADJOINT_CALLBACK_NAMES):
+            cb = getattr(p.original_func, adj_name, None)
+            if cb is not None:
+                def _cb(t0, y_flat, dt, _cb_=cb):
+                    tq, yq, aq, pq = views_of(y_flat)
+                    state = (tq, *yq, *aq, *pq) if p.is_tuple else (tq, yq, aq, *pq)
+                    return _cb_(t0 * self.bsign, state, dt)               # misc.py:330-331
+                callbacks[name] = _cb
+
+        # The backward solve always runs against the forward time direction (adjoint.py:136
+        # t[i-1:i+1].flip(0)).  The engine integrates ascending s = bsign * t, bsign = -fwd_sign.
+        fwd_sign = -1.0 if p.t_reversed else 1.0
+        self.bsign = -fwd_sign
+        bp = Problem()                       # the backward problem as the engine factory sees it
+        bp.t_sign, bp.device, bp.dtype, bp.n, bp.fn = self.bsign, dev, T, lay.n, aug_fn
+        bp.t_cpu = (p.t_cpu.to(torch.float64) * fwd_sign * self.bsign).flip(0)
+        rtol_s, rtol_v = _adj_tol(adjoint_rtol, lay, dev)
+        atol_s, atol_v = _adj_tol(adjoint_atol, lay, dev)
+        if (rtol_v is None) != (atol_v is None):
+            if rtol_v is None:
+                rtol_v = torch.full_like(atol_v, rtol_s)
+            else:
+                atol_v = torch.full_like(rtol_v, atol_s)
+        self.eng = _make_adaptive_engine(bp, adjoint_method, rtol_s, atol_s, rtol_v, atol_v, opts, fn=aug_fn,
+                                         n=lay.n, segs=segs, pieces=pieces, norm_fn=norm_fn, q_view=q_view,
+                                         callbacks=callbacks, solver_name=adjoint_method)
+        # solves run inside autograd's backward: never capture there (see AdaptiveEngine.prime)
+        self.eng.capture_in_solve = False
+
+    def prime(self, t, y_last):
+        """Capture the backward step graph now (forward call, main thread) on stand-in data."""
+        lay, n = self.lay, self.p.n
+        aug = torch.zeros(lay.n, dtype=self.p.dtype, device=self.p.device)
+        aug[self.o_y:self.o_y + n] = y_last
+        t64 = t.detach().to(device=self.p.device, dtype=torch.float64)
+        pair = torch.stack([t64[-1], t64[-2]]) * self.bsign
+        return self.eng.prime(aug, pair)
+
+    def run(self, t, y, grad_sol):
+        """adjoint.py:116-153."""
+        p, lay, eng, n = self.p, self.lay, self.eng, self.p.n
+        o_t, o_y, o_a = self.o_t, self.o_y, self.o_a
+        dev, T = p.device, p.dtype
+        aug = torch.zeros(lay.n, dtype=T, device=dev)
+        aug[o_y:o_y + n] = y[-1]
+        aug[o_a:o_a + n] = grad_sol[-1]
+        t64 = t.detach().to(device=dev, dtype=torch.float64)
+        time_vjps = torch.empty(len(t), dtype=t.dtype, device=t.device) if self.t_requires_grad else None
+        for i in range(len(t) - 1, 0, -1):                            # adjoint.py:124-141
+            if self.t_requires_grad:
+                fe = self.base_fn(t[i].to(T), y[i])
+                if isinstance(fe, tuple):
+                    fe = self.fwd_layout.flatten([f_.detach() for f_ in fe])
+                dLd_cur_t = fe.reshape(-1).dot(grad_sol[i].reshape(-1))
+                aug[o_t] -= dLd_cur_t
+                time_vjps[i] = dLd_cur_t
+            pair = torch.stack([t64[i], t64[i - 1]]) * self.bsign        # ascending for the engine
+            sol = eng.solve(aug, pair)
+            aug.copy_(sol[1])
+            aug[o_y:o_y + n] = y[i - 1]                               # adjoint.py:140
+            aug[o_a:o_a + n] += grad_sol[i - 1]                       # adjoint.py:141
+        if self.t_requires_grad:
+            time_vjps[0] = aug[o_t]
+        adj_y = aug[o_a:o_a + n].clone()
+        adj_params = [aug[o:o + l].view(s).clone() for o, l, s in zip(lay.offsets[3:], lay.lens[3:], lay.shapes[3:])]
+        return time_vjps, adj_y, adj_params
+
+
 class _AdjointFunction(torch.autograd.Function):
     """adjoint.py:8-153 OdeintAdjointMethod."""
 
@@ -43,12 +215,22 @@ class _AdjointFunction(torch.autograd.Function):
     def forward(ctx, p, adjoint_rtol, adjoint_atol, adjoint_method, adjoint_options, t_requires_grad, t, y0_flat,
                 *adjoint_params):
         ctx.p = p
-        ctx.adjoint_rtol, ctx.adjoint_atol = adjoint_rtol, adjoint_atol
-        ctx.adjoint_method, ctx.adjoint_options = adjoint_method, adjoint_options
-        ctx.t_requires_grad = t_requires_grad
+        ctx.bargs = (adjoint_rtol, adjoint_atol, adjoint_method, adjoint_options, t_requires_grad)
+        ctx.bsolver = None
         with torch.no_grad():
             sol, _ = _solve(p)                                          # adjoint.py:23-24
-            sol = sol.clone() if sol._base is not None else sol
+            graph_opt = adjoint_options.get("graph", "auto")
+            if any(ctx.needs_input_grad) and len(t) > 1 and graph_opt in (True, "auto") \
+                    and int(adjoint_options.get("run_ahead", 2)) > 0:
+                try:
+                    bs = _BackwardSolver(p, adjoint_params, *ctx.bargs)
+                    bs.prime(t, sol[-1])
+                    ctx.bsolver = bs
+                except Exception as e:
+                    if graph_opt is True:
+                        raise
+                    warnings.warn("torchdiffeq_b200: could not prepare the captured backward step (%s: %s); the "
+                                  "backward pass will use eager launches" % (type(e).__name__, e))
         ctx.save_for_backward(t, sol, *adjoint_params)                   # adjoint.py:28
         return sol
 
@@ -56,156 +238,14 @@ class _AdjointFunction(torch.autograd.Function):
     def backward(ctx, grad_sol):
         p = ctx.p
         t, y, *adjoint_params = ctx.saved_tensors
-        adjoint_params = tuple(adjoint_params)
-        t_requires_grad = ctx.t_requires_grad
-        dev, T = p.device, p.dtype
-        n = p.n
         grad_sol = grad_sol.contiguous()
         with torch.no_grad():
-            # ---- augmented layout: [vjp_t | y | adj_y | params...]   (adjoint.py:64-65) ----------
-            lay = Layout([(1,), (n,), (n,)] + [q.shape for q in adjoint_params], T)
-            o_t, o_y, o_a = lay.offsets[0], lay.offsets[1], lay.offsets[2]
-            aug = torch.zeros(lay.n, dtype=T, device=dev)
-            aug[o_y:o_y + n] = y[-1]
-            aug[o_a:o_a + n] = grad_sol[-1]
-
-            base_fn, fwd_layout = p.fn, p.layout
-
-            # ---- augmented dynamics (adjoint.py:72-105), returning RAW pieces ------------------
-            def aug_fn(t_, aug_flat):
-                y_ = aug_flat[o_y:o_y + n]
-                adj = aug_flat[o_a:o_a + n]
-                with torch.enable_grad():
-                    tt = t_.detach()
-                    if t_requires_grad:
-                        tt = tt.clone().requires_grad_(True)
-                    yy = y_.detach().requires_grad_(True)
-                    f = base_fn(tt, yy)                                  # Tensor, or tuple of pieces (tuple state)
-                    if isinstance(f, tuple):
-                        outs = [f_.reshape(-1) for f_ in f]
-                        gouts = [adj[o:o + l] for o, l in zip(fwd_layout.offsets, fwd_layout.lens)]
-                    else:
-                        outs = [f.reshape(-1)]
-                        gouts = [adj]
-                    keep = [(o_, g_) for o_, g_ in zip(outs, gouts) if o_.requires_grad]
-                    inputs = ((tt,) if t_requires_grad else ()) + (yy,) + adjoint_params
-                    if keep:
-                        grads = torch.autograd.grad([o_ for o_, _ in keep], inputs, [g_ for _, g_ in keep],
-                                                    allow_unused=True)   # +adj: the minus sits in the pack scale
-                    else:
-                        grads = (None,) * len(inputs)
-                if t_requires_grad:
-                    vjp_t, vjp_y, *vjp_params = grads
-                else:
-                    vjp_t = None
-                    vjp_y, *vjp_params = grads
-                if isinstance(f, tuple):
-                    # tuple state: write the pieces of f at their offsets inside the y segment
-                    return (vjp_t, *[f_.detach() for f_ in f], vjp_y, *vjp_params)
-                return (vjp_t, f.detach(), vjp_y, *vjp_params)
-
-            # pieces and their scales.  Reference: k_ref = mul * (vjp_t, f, vjp_y, vjp_p) with
-            # vjp = grad(f, ., -adj) and mul = -1 (time runs backwards, misc.py:165); the engine applies
-            # t_sign = -1 to every stage slot, so the RAW slot must hold -k_ref = (-g_t, +f, -g_y, -g_p)
-            # where g = grad(f, ., +adj).
-            if p.is_tuple:
-                f_offs = [o_y + o for o in fwd_layout.offsets]
-                f_lens = list(fwd_layout.lens)
-            else:
-                f_offs, f_lens = [o_y], [n]
-            offs = [o_t] + f_offs + [o_a] + list(lay.offsets[3:])
-            lens = [1] + f_lens + [n] + list(lay.lens[3:])
-            scales = [-1.0] + [1.0] * len(f_offs) + [-1.0] + [-1.0] * len(adjoint_params)
-            pieces = (offs, lens, scales)
-
-            # ---- adjoint norm (adjoint.py:243-288) -------------------------------------------
-            opts = dict(ctx.adjoint_options)
-            y_segs = [(o_y + o, l) for o, l in zip(fwd_layout.offsets, fwd_layout.lens)] if p.is_tuple else [(o_y, n)]
-            a_segs = [(o_a + o, l) for o, l in zip(fwd_layout.offsets, fwd_layout.lens)] if p.is_tuple else [(o_a, n)]
-            p_segs = [(o, l) for o, l in zip(lay.offsets[3:], lay.lens[3:]) if l > 0]
-            norm_fn, q_view, segs = None, None, None
-            adj_norm = opts.pop("norm", None)
-            fwd_norm_fused = p.norm_fn is None
-            def views_of(q):
-                yq, aq = q[o_y:o_y + n], q[o_a:o_a + n]
-                if p.is_tuple:
-                    yq, aq = fwd_layout.views(yq), fwd_layout.views(aq)
-                else:
-                    yq, aq = yq.view(p.shape), aq.view(p.shape)
-                return q[o_t:o_t + 1].view(()), yq, aq, [q[o:o + l].view(s) for o, l, s in
-                                                         zip(lay.offsets[3:], lay.lens[3:], lay.shapes[3:])]
-            if adj_norm is None or adj_norm == "seminorm":
-                segs = [(o_t, 1)] + y_segs + a_segs + ([] if adj_norm == "seminorm" else p_segs)
-                if not fwd_norm_fused or len(segs) > _lib.TDQ_MAX_SEGS:
-                    state_norm = p.norm_fn if p.norm_fn is not None else (_mixed_norm if p.is_tuple else _rms_norm)
-                    semi = adj_norm == "seminorm"
-                    def norm_fn(parts):                                  # adjoint.py:247-250 / :267-271
-                        tq, yq, aq, pq = parts
-                        vals = [tq.abs(), state_norm(yq), state_norm(aq)]
-                        if not semi:
-                            vals.append(_mixed_norm(pq))
-                        return max(vals)
-                    q_view, segs = views_of, None
-            else:
-                # user callable: gets (t, y, adj_y, *adj_params), y/adj_y expanded for tuple states (:273-288)
-                def norm_fn(parts):
-                    tq, yq, aq, pq = parts
-                    if p.is_tuple:
-                        return adj_norm((tq, *yq, *aq, *pq))
-                    return adj_norm((tq, yq, aq, *pq))
-                q_view = views_of
-
-            # adjoint callbacks (adjoint.py:107-114)
-            callbacks = {}
-            for name, adj_name in zip(_CALLBACK_NAMES, _ADJOINT_CALLBACK_NAMES):
-                cb = getattr(p.original_func, adj_name, None)
-                if cb is not None:
-                    def _cb(t0, y_flat, dt, _cb_=cb):
-                        tq, yq, aq, pq = views_of(y_flat)
-                        state = (tq, *yq, *aq, *pq) if p.is_tuple else (tq, yq, aq, *pq)
-                        return _cb_(-t0, state, dt)                       # time runs backwards (misc.py:330-331)
-                    callbacks[name] = _cb
-
-            # The backward solve always runs against the forward time direction (adjoint.py:136
-            # t[i-1:i+1].flip(0)).  The engine integrates ascending s = t_sign_b * t, t_sign_b = -fwd_sign.
-            fwd_sign = -1.0 if p.t_reversed else 1.0
-            bp = Problem()                       # the backward problem as the engine factory sees it
-            bp.t_sign, bp.device, bp.dtype, bp.n, bp.fn = -fwd_sign, dev, T, lay.n, aug_fn
-            bp.t_cpu = (t.detach().to("cpu").to(torch.float64) * (-fwd_sign)).flip(0)
-            a_rtol, a_atol = ctx.adjoint_rtol, ctx.adjoint_atol
-            # tolerances: scalars, or per-piece tuples expanded like misc.py:115-123 over the aug tuple
-            rtol_s, rtol_v = _adj_tol(a_rtol, lay, dev)
-            atol_s, atol_v = _adj_tol(a_atol, lay, dev)
-            if (rtol_v is None) != (atol_v is None):
-                if rtol_v is None:
-                    rtol_v = torch.full_like(atol_v, rtol_s)
-                else:
-                    atol_v = torch.full_like(rtol_v, atol_s)
-            eng = _make_adaptive_engine(bp, ctx.adjoint_method, rtol_s, atol_s, rtol_v, atol_v, opts, fn=aug_fn,
-                                        n=lay.n, segs=segs, pieces=pieces, norm_fn=norm_fn, q_view=q_view,
-                                        callbacks=callbacks, solver_name=ctx.adjoint_method)
-            t64 = t.detach().to(device=dev, dtype=torch.float64)
-
-            time_vjps = torch.empty(len(t), dtype=t.dtype, device=t.device) if t_requires_grad else None
-            for i in range(len(t) - 1, 0, -1):                            # adjoint.py:124-141
-                if t_requires_grad:
-                    fe = base_fn(t[i].to(T), y[i])
-                    if isinstance(fe, tuple):
-                        fe = fwd_layout.flatten([f_.detach() for f_ in fe])
-                    dLd_cur_t = fe.reshape(-1).dot(grad_sol[i].reshape(-1))
-                    aug[o_t] -= dLd_cur_t
-                    time_vjps[i] = dLd_cur_t
-                # ascending time for the engine: integrate s = -fwd_sign * t from s_i to s_{i-1}
-                pair = torch.stack([t64[i], t64[i - 1]]) * (-fwd_sign)
-                sol = eng.solve(aug, pair)
-                aug.copy_(sol[1])
-                aug[o_y:o_y + n] = y[i - 1]                               # adjoint.py:140
-                aug[o_a:o_a + n] += grad_sol[i - 1]                       # adjoint.py:141
-            if t_requires_grad:
-                time_vjps[0] = aug[o_t]
-            adj_y = aug[o_a:o_a + n].clone()
-            adj_params = [aug[o:o + l].view(s).clone() for o, l, s in zip(lay.offsets[3:], lay.lens[3:], lay.shapes[3:])]
-        ctx.backward_nfe = eng.nfe
+            bs = ctx.bsolver
+            if bs is None:
+                bs = _BackwardSolver(p, adjoint_params, *ctx.bargs)
+            time_vjps, adj_y, adj_params = bs.run(t, y, grad_sol)
+        ctx.backward_nfe = bs.eng.nfe
+        ctx.bsolver = None
         return (None, None, None, None, None, None, time_vjps, adj_y, *adj_params)
 
 
