@@ -156,9 +156,11 @@ class AdaptiveEngine:
         self._graph = None
         self._graph_failed = False
         self._graph_keep = None
+        self._side = None
         self.capture_in_solve = True     # False: only a prime()d graph is used (solves run inside autograd backward)
         self.n_attempts = 0              # attempts that did work (from the mailbox counters)
         self.nfe = 0                     # func evaluations issued by the host
+        self.nfe_total = 0
         self.launches = 0                # libtdq kernel launches issued (graph replays count their nodes)
         self._graph_launches = 0
 
@@ -340,7 +342,7 @@ class AdaptiveEngine:
         n_out = self._begin(y0_flat, t64, t_start)
         if n_out <= 1:
             return False
-        self._attempt()
+        self._warm_attempt()
         self._capture()
         torch.cuda.current_stream().synchronize()
         return self._graph is not None
@@ -348,6 +350,8 @@ class AdaptiveEngine:
     def _begin(self, y0_flat, t64, t_start=None):
         """Everything of a solve that precedes the first attempt (rk_common.py:166-241)."""
         lib = self.lib
+        self.nfe_total += self.nfe
+        self.nfe, self.launches = 0, 0                  # per-solve counters (engines are reused)
         n_out = int(t64.numel())
         self.t_out = t64.contiguous()
         if getattr(self, "solution", None) is None or self.solution.shape[0] != n_out:
@@ -440,10 +444,12 @@ class AdaptiveEngine:
         use_graph = self.graph_opt in (True, "auto") and not self._graph_failed and self.capture_in_solve
         # attempt 1 runs eagerly: it is a real attempt and doubles as the warm-up torch wants before capture
         if self._graph is None:
-            self._attempt()
-            issued += 1
             if use_graph:
+                self._warm_attempt()
                 self._capture()
+            else:
+                self._attempt()
+            issued += 1
         while True:
             seen = mb.seq
             if mb.status != _lib.RUN_OK or mb.done:
@@ -460,6 +466,20 @@ class AdaptiveEngine:
         mb = self._wait_seq(issued)
         self._raise_if_failed(mb)
         torch.cuda.current_stream().synchronize()
+
+    def _warm_attempt(self):
+        """The first attempt of a solve that is about to be captured: a real attempt, run on a side stream.
+        torch's capture recipe warms up on a non-default stream so that everything lazily initialised for
+        (thread, non-legacy stream) pairs -- notably on autograd's worker thread when func differentiates
+        inside the step -- exists before capture begins; otherwise that initialisation touches the legacy
+        stream in the middle of the capture and invalidates it."""
+        cur = torch.cuda.current_stream()
+        if self._side is None:
+            self._side = torch.cuda.Stream(device=self.device)
+        self._side.wait_stream(cur)
+        with torch.cuda.stream(self._side):
+            self._attempt()
+        cur.wait_stream(self._side)
 
     def _capture(self):
         try:

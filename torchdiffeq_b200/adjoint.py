@@ -21,8 +21,8 @@ import torch.nn as nn
 
 from . import _lib
 from ._engine import Layout
-from .odeint import (ADAPTIVE_METHODS, _ADJOINT_CALLBACK_NAMES, _CALLBACK_NAMES, _make_adaptive_engine,
-                     _mixed_norm, _rms_norm, _solve, _unflatten, normalise, Problem)
+from .odeint import (ADAPTIVE_METHODS, _ADJOINT_CALLBACK_NAMES, _CALLBACK_NAMES, _cache_get, _cache_key, _cache_put,
+                     _make_adaptive_engine, _mixed_norm, _rms_norm, _solve, _unflatten, normalise, Problem)
 
 
 def find_parameters(module):
@@ -208,6 +208,25 @@ class _BackwardSolver:
         return time_vjps, adj_y, adj_params
 
 
+def _backward_key(p, adjoint_params, bargs):
+    adjoint_rtol, adjoint_atol, adjoint_method, adjoint_options, t_requires_grad = bargs
+    fkey = _cache_key(p)
+    if fkey is None:
+        return None
+    items = []
+    for k, v in sorted(adjoint_options.items()):
+        if isinstance(v, torch.Tensor) or callable(v):
+            return None
+        items.append((k, v))
+    try:
+        key = ("adjoint", fkey, tuple(q.data_ptr() for q in adjoint_params), float(adjoint_rtol), float(adjoint_atol),
+               adjoint_method, tuple(items), t_requires_grad)
+        hash(key)
+    except (TypeError, ValueError):
+        return None
+    return key
+
+
 class _AdjointFunction(torch.autograd.Function):
     """adjoint.py:8-153 OdeintAdjointMethod."""
 
@@ -223,8 +242,14 @@ class _AdjointFunction(torch.autograd.Function):
             if any(ctx.needs_input_grad) and len(t) > 1 and graph_opt in (True, "auto") \
                     and int(adjoint_options.get("run_ahead", 2)) > 0:
                 try:
-                    bs = _BackwardSolver(p, adjoint_params, *ctx.bargs)
-                    bs.prime(t, sol[-1])
+                    bkey = _backward_key(p, adjoint_params, ctx.bargs)
+                    hit = _cache_get(bkey)
+                    if hit is not None:
+                        bs = hit[0]
+                    else:
+                        bs = _BackwardSolver(p, adjoint_params, *ctx.bargs)
+                        bs.prime(t, sol[-1])
+                        _cache_put(bkey, (bs, p.original_func))
                     ctx.bsolver = bs
                 except Exception as e:
                     if graph_opt is True:
@@ -244,7 +269,6 @@ class _AdjointFunction(torch.autograd.Function):
             if bs is None:
                 bs = _BackwardSolver(p, adjoint_params, *ctx.bargs)
             time_vjps, adj_y, adj_params = bs.run(t, y, grad_sol)
-        ctx.backward_nfe = bs.eng.nfe
         ctx.bsolver = None
         return (None, None, None, None, None, None, time_vjps, adj_y, *adj_params)
 

@@ -7,6 +7,7 @@ misc.py:200-345 (_check_inputs) with two differences that are not observable in 
   * reverse-time integration does not wrap func in a multiply-by-minus-one (misc.py:158-165):
     the sign is folded into the Runge-Kutta coefficients on the device.
 """
+import collections
 import warnings
 
 import torch
@@ -29,7 +30,7 @@ _ADJOINT_CALLBACK_NAMES = [name + "_adjoint" for name in _CALLBACK_NAMES]       
 _ADAPTIVE_OPTIONS = {"min_step", "max_step", "first_step", "step_t", "jump_t", "safety", "ifactor", "dfactor",
                      "max_num_steps", "dtype", "norm"}
 _FIXED_OPTIONS = {"step_size", "grid_constructor", "interp", "perturb", "norm"}
-_OUR_OPTIONS = {"graph", "run_ahead", "process_group"}
+_OUR_OPTIONS = {"graph", "run_ahead", "process_group", "cache"}
 
 
 def _rms_norm(tensor):
@@ -240,14 +241,84 @@ def _make_adaptive_engine(p, method, rtol, atol, rtol_vec, atol_vec, options, fn
         reduce_fn=reduce_fn, n_global=n_global, seg_counts_global=seg_counts_global, callbacks=callbacks)
 
 
+# ---- engine cache -------------------------------------------------------------------------------
+# An engine owns ~20 state-sized buffers and, in graph mode, a captured step graph with its private
+# memory pool; building and tearing that down costs far more than a solve of the benchmark size.
+# Engines are therefore kept (LRU) and reused when the same func is integrated again with the same
+# shapes and options -- the normal situation in a training or serving loop.  The key contains
+# everything a captured graph has baked in; anything unhashable (tensor options, callbacks, vector
+# tolerances, custom norms) simply disables caching.  options={'cache': False} opts out;
+# torchdiffeq_b200.clear_cache() drops the engines and their memory.
+_ENGINE_CACHE = collections.OrderedDict()
+_ENGINE_CACHE_MAX = 4
+
+
+def clear_cache():
+    _ENGINE_CACHE.clear()
+
+
+def _func_signature(func):
+    if isinstance(func, torch.nn.Module):
+        ps = tuple((q.data_ptr(), tuple(q.shape), q.dtype, q.requires_grad) for q in func.parameters())
+        bs = tuple((b.data_ptr(), tuple(b.shape), b.dtype) for b in func.buffers())
+        return (id(func), func.training, ps, bs)
+    return (id(func),)
+
+
+def _cache_key(p, extra=()):
+    o = p.options
+    if o.get("cache", True) is False or p.callbacks or p.norm_fn is not None or p.rtol_vec is not None:
+        return None
+    if o.get("graph", "auto") is False and False:
+        return None
+    items = []
+    for k, v in sorted(o.items()):
+        if k == "process_group":
+            v = id(v)
+        elif isinstance(v, torch.Tensor) or callable(v):
+            return None
+        items.append((k, v))
+    shapes = tuple(tuple(s_) for s_ in p.layout.shapes) if p.is_tuple else tuple(p.shape)
+    try:
+        key = (_func_signature(p.original_func), p.method, p.dtype, str(p.device), p.is_tuple, shapes, p.rtol, p.atol,
+               p.t_sign, tuple(items), torch.is_autocast_enabled(), extra)
+        hash(key)
+    except TypeError:
+        return None
+    return key
+
+
+def _cache_get(key):
+    if key is None or key not in _ENGINE_CACHE:
+        return None
+    _ENGINE_CACHE.move_to_end(key)
+    return _ENGINE_CACHE[key]
+
+
+def _cache_put(key, value):
+    if key is None:
+        return
+    _ENGINE_CACHE[key] = value
+    while len(_ENGINE_CACHE) > _ENGINE_CACHE_MAX:
+        _ENGINE_CACHE.popitem(last=False)
+
+
 def _solve(p):
     """Run the normalised problem; returns the flat solution [len(t), n] and the engine."""
     if p.method in ADAPTIVE_METHODS:
-        eng = _make_adaptive_engine(p, p.method, p.rtol, p.atol, p.rtol_vec, p.atol_vec, p.options,
-                                    segs=p.segs, pieces=p.pieces, norm_fn=p.norm_fn, q_view=p.q_view,
-                                    callbacks=p.callbacks)
+        key = _cache_key(p)
+        hit = _cache_get(key)
+        if hit is not None:
+            eng = hit[0]
+        else:
+            eng = _make_adaptive_engine(p, p.method, p.rtol, p.atol, p.rtol_vec, p.atol_vec, p.options,
+                                        segs=p.segs, pieces=p.pieces, norm_fn=p.norm_fn, q_view=p.q_view,
+                                        callbacks=p.callbacks)
+            _cache_put(key, (eng, p.original_func))     # the func reference keeps id(func) from being recycled
         t64 = p.t_cpu.to(torch.float64).to(p.device)                                   # solvers.py:31
         sol = eng.solve(p.y0_flat, t64, t_start=float(p.t_cpu[0]))
+        if key is not None:
+            sol = sol.clone()                           # the engine reuses its solution buffer
         return sol, eng
     # fixed grid RK4 (solvers.py:55-128)
     o = p.options
