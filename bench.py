@@ -92,7 +92,7 @@ class ClockSampler:
                 "samples": len(sm)}
 
 
-CPU_SAMPLE_B = 65536       # the whole workload: ~10 s on 8-16 cores, inside the 10-30 s budget
+CPU_SAMPLE_B = 8192        # ~7 s per solve on the GPU box's host (the full 65536 rows take 53 s there)
 
 
 def cpu_threads():

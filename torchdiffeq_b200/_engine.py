@@ -482,22 +482,33 @@ class AdaptiveEngine:
         cur.wait_stream(self._side)
 
     def _capture(self):
-        try:
-            g = torch.cuda.CUDAGraph()
-            nfe, launches = self.nfe, self.launches
-            with torch.cuda.graph(g):
-                keep = self._attempt()
-            self._graph_launches = self.launches - launches
-            self.nfe, self.launches = nfe, launches         # capture runs no kernels
-            self._graph, self._graph_keep = g, keep
-        except Exception as e:                              # func is not capturable: stay eager
-            self._graph = None
-            self._graph_failed = True
-            if self.graph_opt is True:
-                raise
-            import warnings
-            warnings.warn("torchdiffeq_b200: CUDA graph capture of the step body failed (%s: %s); "
-                          "continuing with eager launches" % (type(e).__name__, e))
+        """Capture one attempt.  A first capture that involves autograd (the adjoint's augmented dynamics)
+        can be invalidated by one-time initialisation inside autograd's worker thread that no eager
+        warm-up reaches; nothing has executed at that point and the engine state is untouched, so the
+        capture is simply retried once before giving up."""
+        last = None
+        for _try in range(2):
+            try:
+                g = torch.cuda.CUDAGraph()
+                nfe, launches = self.nfe, self.launches
+                try:
+                    with torch.cuda.graph(g):
+                        keep = self._attempt()
+                finally:
+                    self._graph_launches = self.launches - launches
+                    self.nfe, self.launches = nfe, launches     # capture runs no kernels
+                self._graph, self._graph_keep = g, keep
+                return
+            except Exception as e:                              # func is not capturable: stay eager
+                last = e
+                self._graph = None
+                torch.cuda.synchronize(self.device)
+        self._graph_failed = True
+        if self.graph_opt is True:
+            raise last
+        import warnings
+        warnings.warn("torchdiffeq_b200: CUDA graph capture of the step body failed (%s: %s); "
+                      "continuing with eager launches" % (type(last).__name__, last))
 
     def _initial_step_custom_norm(self):
         """misc.py:36-77 with a user norm callable: torch ops + one host read (compatibility path)."""
