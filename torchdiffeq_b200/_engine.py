@@ -30,6 +30,55 @@ def _stream():
     return torch.cuda.current_stream().cuda_stream
 
 
+_SOLVER_STREAMS = {}
+
+
+def solver_stream(device):
+    """The dedicated (non-default, non-blocking) stream every solve of a device runs on."""
+    idx = device.index if device.index is not None else torch.cuda.current_device()
+    st = _SOLVER_STREAMS.get(idx)
+    if st is None:
+        st = _SOLVER_STREAMS[idx] = torch.cuda.Stream(device=idx)
+    return st
+
+
+class on_solver_stream:
+    """Run a solve on the device's solver stream, ordered after the caller's stream on entry and before
+    it on exit.  Reasons: (1) CUDA graphs cannot be captured on the legacy default stream, and torch's
+    capture recipe wants the warm-up on the same kind of stream; (2) when func differentiates inside the
+    step (the adjoint's augmented dynamics), autograd synchronises every gradient's producer stream with
+    the stream its consumer node was CREATED on -- if that is the legacy stream the capture is
+    invalidated ("would make the legacy stream depend on a capturing stream").  Creating the
+    odeint_adjoint node, warming up, capturing and replaying all on this one stream removes that edge."""
+
+    def __init__(self, device):
+        self.device = device
+
+    def __enter__(self):
+        self.cur = torch.cuda.current_stream(self.device)
+        self.s = solver_stream(self.device)
+        if self.cur == self.s:
+            self.ctx = None
+            return self
+        self.s.wait_stream(self.cur)
+        self.ctx = torch.cuda.stream(self.s)
+        self.ctx.__enter__()
+        return self
+
+    def __exit__(self, *exc):
+        if self.ctx is not None:
+            self.ctx.__exit__(*exc)
+            self.cur.wait_stream(self.s)
+        return False
+
+    def publish(self, *tensors):
+        """Tensors allocated on the solver stream and handed to the caller's stream."""
+        if self.ctx is not None:
+            for t in tensors:
+                if isinstance(t, torch.Tensor) and t.is_cuda:
+                    t.record_stream(self.cur)
+
+
 class SolverFailure(AssertionError):
     """Raised for the reference's in-loop assertions (rk_common.py:247, :286, :287)."""
 
@@ -156,7 +205,6 @@ class AdaptiveEngine:
         self._graph = None
         self._graph_failed = False
         self._graph_keep = None
-        self._side = None
         self.capture_in_solve = True     # False: only a prime()d graph is used (solves run inside autograd backward)
         self.n_attempts = 0              # attempts that did work (from the mailbox counters)
         self.nfe = 0                     # func evaluations issued by the host
@@ -468,18 +516,9 @@ class AdaptiveEngine:
         torch.cuda.current_stream().synchronize()
 
     def _warm_attempt(self):
-        """The first attempt of a solve that is about to be captured: a real attempt, run on a side stream.
-        torch's capture recipe warms up on a non-default stream so that everything lazily initialised for
-        (thread, non-legacy stream) pairs -- notably on autograd's worker thread when func differentiates
-        inside the step -- exists before capture begins; otherwise that initialisation touches the legacy
-        stream in the middle of the capture and invalidates it."""
-        cur = torch.cuda.current_stream()
-        if self._side is None:
-            self._side = torch.cuda.Stream(device=self.device)
-        self._side.wait_stream(cur)
-        with torch.cuda.stream(self._side):
-            self._attempt()
-        cur.wait_stream(self._side)
+        """The first attempt of a solve that is about to be captured: a real attempt that doubles as the
+        warm-up torch wants before capture (we are already on the solver stream, never the legacy one)."""
+        self._attempt()
 
     def _capture(self):
         """Capture one attempt.  A first capture that involves autograd (the adjoint's augmented dynamics)
@@ -492,7 +531,7 @@ class AdaptiveEngine:
                 g = torch.cuda.CUDAGraph()
                 nfe, launches = self.nfe, self.launches
                 try:
-                    with torch.cuda.graph(g):
+                    with torch.cuda.graph(g, stream=solver_stream(self.device)):
                         keep = self._attempt()
                 finally:
                     self._graph_launches = self.launches - launches

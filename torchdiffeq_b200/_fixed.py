@@ -8,7 +8,7 @@ grid interval, indexed by a device step counter."""
 import torch
 
 from . import _lib
-from ._engine import _DTYPES, _stream
+from ._engine import _DTYPES, _stream, solver_stream
 
 _ONE_THIRD = 1 / 3      # rk_common.py:94-96
 _TWO_THIRDS = 2 / 3
@@ -140,7 +140,7 @@ class FixedRK4Engine:
             try:
                 graph = torch.cuda.CUDAGraph()
                 nfe = self.nfe
-                with torch.cuda.graph(graph):
+                with torch.cuda.graph(graph, stream=solver_stream(self.device)):
                     keep = self._step()
                 self.nfe = nfe
             except Exception as e:

@@ -20,7 +20,7 @@ import torch
 import torch.nn as nn
 
 from . import _lib
-from ._engine import Layout
+from ._engine import Layout, on_solver_stream
 from .odeint import (ADAPTIVE_METHODS, _ADJOINT_CALLBACK_NAMES, _CALLBACK_NAMES, _cache_get, _cache_key, _cache_put,
                      _make_adaptive_engine, _mixed_norm, _rms_norm, _solve, _unflatten, normalise, Problem)
 
@@ -331,6 +331,10 @@ def odeint_adjoint(func, y0, t, *, rtol=1e-7, atol=1e-9, method=None, options=No
         y0_flat = p.layout.flatten(list(y0))          # differentiable wrt every piece (copy_ into zeros)
     else:
         y0_flat = y0.reshape(-1)
-    sol = _AdjointFunction.apply(p, adjoint_rtol, adjoint_atol, adjoint_method, adjoint_options, t.requires_grad,
-                                 t, y0_flat, *adjoint_params)
+    # The autograd node is created on the solver stream, so that its backward -- and every gradient edge
+    # into the parameters -- lives on the stream the backward step graph is captured and replayed on.
+    with on_solver_stream(p.device) as ss:
+        sol = _AdjointFunction.apply(p, adjoint_rtol, adjoint_atol, adjoint_method, adjoint_options, t.requires_grad,
+                                     t, y0_flat, *adjoint_params)
+        ss.publish(sol)
     return _unflatten(p, sol)

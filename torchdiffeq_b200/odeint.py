@@ -13,7 +13,7 @@ import warnings
 import torch
 
 from . import _lib
-from ._engine import AdaptiveEngine, Layout
+from ._engine import AdaptiveEngine, Layout, on_solver_stream
 from ._fixed import FixedRK4Engine, grid_from_step_size
 
 ADAPTIVE_METHODS = ("dopri5", "dopri8", "bosh3", "fehlberg2", "adaptive_heun")
@@ -382,8 +382,9 @@ def odeint(func, y0, t, *, rtol=1e-7, atol=1e-9, method=None, options=None, even
         if _func_requires_grad(func):
             warnings.warn("torchdiffeq_b200.odeint returns a tensor without autograd history; use "
                           "odeint_adjoint to train func's parameters", stacklevel=2)
-    with torch.no_grad():
+    with torch.no_grad(), on_solver_stream(p.device) as ss:
         sol, eng = _solve(p)
+        ss.publish(sol)
     if _stats is not None:               # private: solver counters for bench.py and the tests
         _stats["nfe"] = eng.nfe
         _stats["launches"] = _stats.get("launches", 0) + getattr(eng, "launches", 0)
