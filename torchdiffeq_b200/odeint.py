@@ -116,6 +116,9 @@ def normalise(func, y0, t, rtol, atol, method, options, event_fn, adjoint=False)
         raise NotImplementedError('method "{}" is not part of the B200 hot path; implemented: {}'.format(
             method, ADAPTIVE_METHODS + FIXED_METHODS))
     p.method, p.options = method, options
+    if p.device.type != "cuda":
+        raise _lib.TdqError("torchdiffeq_b200 runs on CUDA devices only (got %s); there is no CPU path" % p.device)
+    _lib.load()                                   # fail loudly, before any work, if libtdq.so is missing
 
     _check_timelike('t', t, True)
     t_cpu = t.detach().to("cpu")                                                       # the one host read of t
