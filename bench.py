@@ -148,7 +148,7 @@ def run_reference(args):
 def roofline_probe(dev, n_elems, reps=20):
     """CUDA-event time of the stage-combine and error-norm launches of ONE dopri5 attempt at the benchmark's
     size, issued through the C ABI on buffers larger than L2 (9 arrays x 33.5 MB).  Returns per-launch
-    durations (ms) for the 6 combine rows and the norm."""
+    (ms per attempt) for the 6 combine rows alone and for combine + error norm."""
     from torchdiffeq_b200 import _lib
     from torchdiffeq_b200._engine import AdaptiveEngine, _stream
     eng = AdaptiveEngine(lambda t, y: y, n_elems, torch.float32, dev, "dopri5", rtol=RTOL, atol=ATOL, first_step=0.05)
@@ -172,20 +172,27 @@ def roofline_probe(dev, n_elems, reps=20):
         _lib.check(lib.tdq_error_norm(ctrl, tab, dc, y0.data_ptr(), outs[1].data_ptr(), kp, None, None, eng.seg_off,
                                       eng.seg_len, 1, n_elems, eng.partials.data_ptr(), eng.norm_out.data_ptr(), None,
                                       _stream()))
-    launches = [lambda r=r: combine(r) for r in range(6)] + [norm]
-    for fn in launches * 2:
-        fn()
-    torch.cuda.synchronize()
-    ms = [0.0] * 7
-    for _ in range(reps):
-        for i, fn in enumerate(launches):
-            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            a.record()
+    rows = [lambda r=r: combine(r) for r in range(6)]
+
+    def timed(fns, reps):
+        """Back-to-back launches between two events on the launching stream: the queue stays full, so the
+        time is device time (a per-launch event pair would add the host's launch latency to every kernel)."""
+        for fn in fns:
             fn()
-            b.record()
-            b.synchronize()
-            ms[i] += a.elapsed_time(b)
-    return [m / reps for m in ms]
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(reps):
+            for fn in fns:
+                fn()
+        b.record()
+        b.synchronize()
+        return a.elapsed_time(b) / reps
+
+    # every pass over the six rows touches 9 distinct 33.5 MB arrays (>> 126 MB L2), like a real attempt
+    comb_ms = timed(rows, reps)
+    group_ms = timed(rows + [norm], reps)
+    return comb_ms, group_ms
 
 
 def run_ours(args):
@@ -264,13 +271,12 @@ def run_ours(args):
     if rank == 0:
         n_elems = B_PER_GPU * DIM
         peak, peak_src = measured_peaks()
-        probe = roofline_probe(dev, n_elems)
+        comb_ms, group_ms = roofline_probe(dev, n_elems)
         nnz = [1, 2, 3, 4, 5, 5]                          # non-zero beta entries per dopri5 row
         comb_bytes = sum((k + 2) * n_elems * 4 for k in nnz)          # 32*N*s
-        comb_ms = sum(probe[:6])
         norm_bytes = 8 * n_elems * 4
         achieved = comb_bytes / (comb_ms * 1e-3) / 1e9
-        group = (comb_bytes + norm_bytes) / ((comb_ms + probe[6]) * 1e-3) / 1e9
+        group = (comb_bytes + norm_bytes) / (group_ms * 1e-3) / 1e9
         threads = cpu_threads()
         cpu_b = CPU_SAMPLE_B
         cpu_s, cpu_rec = cpu_port_run(cpu_b, threads) if args.cpu_baseline and world == 1 else (None, None)
@@ -292,10 +298,10 @@ def run_ours(args):
             "roofline": {"bound": "hbm", "kernel": "k_combine (6 launches per attempt)", "achieved": achieved,
                          "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
                          "peak_source": peak_src, "algorithmic_bytes_per_attempt": comb_bytes,
-                         "ms_per_launch": [round(x, 5) for x in probe[:6]],
+                         "ms_per_attempt": comb_ms, "launches_per_attempt": 6,
                          "combine_plus_error_norm": {"achieved": group, "frac": group / peak,
-                                                     "bytes": comb_bytes + norm_bytes, "ms": comb_ms + probe[6]},
-                         "error_norm": {"achieved": norm_bytes / (probe[6] * 1e-3) / 1e9, "ms": probe[6]}},
+                                                     "bytes": comb_bytes + norm_bytes, "ms": group_ms,
+                                                     "target": "BASELINE.md: >= 0.70 of the HBM roofline"}},
             "result_check": {"max_rel_norm_drift": drift},
         }
         if cpu_s is not None:

@@ -20,8 +20,15 @@ constexpr int kThreads = 256;
 // Stage combine.  NK = number of non-zero tableau entries in the row (compile time => the NK+1 loads
 // of a thread are all in flight before the first use).
 // ------------------------------------------------------------------------------------------------
-template <typename T, int NK, bool VECTOR>
-__global__ void __launch_bounds__(kThreads)
+// Launch shape, from the r1 tuning sweep on B200 (profiles/r1_combine_variants.txt): a persistent
+// grid-stride kernel beats one-tile-per-block by 1-15 % at 33.5 MB per operand because the last wave no
+// longer drains alone.  Rows with few operands need more bytes in flight per thread:
+//   NK <= 2 : 512 threads, 4 vectors per operand per thread, 2 blocks per SM
+//   NK >= 3 : 256 threads, 2 vectors per operand per thread, 8 blocks per SM
+// The bulk-async (TMA, cp.async.bulk + mbarrier ring through shared memory) variant measured 5-10 %
+// SLOWER than plain 128-bit loads for this pure streaming pattern, so it is not used.
+template <typename T, int NK, int THREADS, int U, bool VECTOR>
+__global__ void __launch_bounds__(THREADS)
 k_combine(const TdqCtrl *__restrict__ c, int row, T *__restrict__ out, const T *__restrict__ y0, KPtrs kp, size_t n) {
     if (c->halt) return;
     using A = Ar<T>;
@@ -34,36 +41,37 @@ k_combine(const TdqCtrl *__restrict__ c, int row, T *__restrict__ out, const T *
     }
     if (VECTOR) {
         using V = Vec<T>;
-        constexpr int U = 2;                               // 16-byte vectors per thread per operand
         const size_t nvec = n / V::N;
-        const size_t base = (size_t)blockIdx.x * (kThreads * U) + threadIdx.x;
-        V a[U], kv[U][NK];
+        const size_t stride = (size_t)gridDim.x * (THREADS * U);
+        for (size_t base = (size_t)blockIdx.x * (THREADS * U) + threadIdx.x; base < nvec; base += stride) {
+            V a[U], kv[U][NK];
 #pragma unroll
-        for (int u = 0; u < U; ++u) {
-            const size_t v = base + (size_t)u * kThreads;
-            if (v < nvec) {
-                a[u] = ld_stream<T>(y0 + v * V::N);
+            for (int u = 0; u < U; ++u) {
+                const size_t v = base + (size_t)u * THREADS;
+                if (v < nvec) {
+                    a[u] = ld_stream<T>(y0 + v * V::N);
 #pragma unroll
-                for (int m = 0; m < NK; ++m) kv[u][m] = ld_stream<T>(k[m] + v * V::N);
-            }
-        }
-#pragma unroll
-        for (int u = 0; u < U; ++u) {
-            const size_t v = base + (size_t)u * kThreads;
-            if (v < nvec) {
-                V r;
-#pragma unroll
-                for (int e = 0; e < V::N; ++e) {
-                    T acc = A::mul(kv[u][0].v[e], cf[0]);
-#pragma unroll
-                    for (int m = 1; m < NK; ++m) acc = A::add(acc, A::mul(kv[u][m].v[e], cf[m]));
-                    r.v[e] = A::add(a[u].v[e], acc);
+                    for (int m = 0; m < NK; ++m) kv[u][m] = ld_stream<T>(k[m] + v * V::N);
                 }
-                st_vec<T>(out + v * V::N, r);
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const size_t v = base + (size_t)u * THREADS;
+                if (v < nvec) {
+                    V r;
+#pragma unroll
+                    for (int e = 0; e < V::N; ++e) {
+                        T acc = A::mul(kv[u][0].v[e], cf[0]);
+#pragma unroll
+                        for (int m = 1; m < NK; ++m) acc = A::add(acc, A::mul(kv[u][m].v[e], cf[m]));
+                        r.v[e] = A::add(a[u].v[e], acc);
+                    }
+                    st_vec<T>(out + v * V::N, r);
+                }
             }
         }
-        // scalar tail (n not a multiple of the vector width): last block's first threads
-        if (blockIdx.x == gridDim.x - 1) {
+        // scalar tail (n not a multiple of the vector width): first threads of block 0
+        if (blockIdx.x == 0) {
             const size_t i = nvec * V::N + threadIdx.x;
             if (i < n) {
                 T acc = A::mul(k[0][i], cf[0]);
@@ -73,7 +81,7 @@ k_combine(const TdqCtrl *__restrict__ c, int row, T *__restrict__ out, const T *
             }
         }
     } else {
-        for (size_t i = (size_t)blockIdx.x * kThreads + threadIdx.x; i < n; i += (size_t)gridDim.x * kThreads) {
+        for (size_t i = (size_t)blockIdx.x * THREADS + threadIdx.x; i < n; i += (size_t)gridDim.x * THREADS) {
             T acc = A::mul(k[0][i], cf[0]);
 #pragma unroll
             for (int m = 1; m < NK; ++m) acc = A::add(acc, A::mul(k[m][i], cf[m]));
@@ -82,20 +90,38 @@ k_combine(const TdqCtrl *__restrict__ c, int row, T *__restrict__ out, const T *
     }
 }
 
+static int sm_count() {
+    static int sms = 0;
+    if (sms == 0) {
+        int dev = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess ||
+            cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0)
+            sms = 148;
+    }
+    return sms;
+}
+
 template <typename T, int NK>
 int launch_combine(const TdqCtrl *c, int row, void *out, const void *y0, const KPtrs &kp, size_t n, bool vec,
                    cudaStream_t st) {
+    constexpr bool kFew = NK <= 2;
+    constexpr int THREADS = kFew ? 512 : 256;
+    constexpr int U = kFew ? 4 : 2;
+    constexpr int PER_SM = kFew ? 2 : 8;
     if (vec) {
         using V = Vec<T>;
         const size_t nvec = n / V::N;
-        size_t blocks = (nvec + kThreads * 2 - 1) / (kThreads * 2);
+        size_t blocks = (nvec + (size_t)THREADS * U - 1) / ((size_t)THREADS * U);
+        const size_t cap = (size_t)sm_count() * PER_SM;       // one resident wave; the loop covers the rest
+        if (blocks > cap) blocks = cap;
         if (blocks == 0) blocks = 1;
-        k_combine<T, NK, true><<<(unsigned)blocks, kThreads, 0, st>>>(c, row, (T *)out, (const T *)y0, kp, n);
+        k_combine<T, NK, THREADS, U, true><<<(unsigned)blocks, THREADS, 0, st>>>(c, row, (T *)out, (const T *)y0, kp, n);
     } else {
-        size_t blocks = (n + kThreads - 1) / kThreads;
+        size_t blocks = (n + THREADS - 1) / THREADS;
+        const size_t cap = (size_t)sm_count() * PER_SM * 2;
+        if (blocks > cap) blocks = cap;
         if (blocks == 0) blocks = 1;
-        if (blocks > 148 * 16) blocks = 148 * 16;
-        k_combine<T, NK, false><<<(unsigned)blocks, kThreads, 0, st>>>(c, row, (T *)out, (const T *)y0, kp, n);
+        k_combine<T, NK, THREADS, U, false><<<(unsigned)blocks, THREADS, 0, st>>>(c, row, (T *)out, (const T *)y0, kp, n);
     }
     return 0;
 }
