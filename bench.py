@@ -92,7 +92,8 @@ class ClockSampler:
                 "samples": len(sm)}
 
 
-CPU_SAMPLE_B = 8192        # ~7 s per solve on the GPU box's host (the full 65536 rows take 53 s there)
+CPU_SAMPLE_B = 32768       # ~20-25 s per solve on the GPU box host (the full 65536 rows take 53 s there)
+REF_SAMPLE_B = 16384       # per step of `--impl reference`, so that K=10 steps end within a few minutes
 
 
 def cpu_threads():
@@ -122,7 +123,7 @@ def run_reference(args):
     if rank != 0:
         return
     threads = cpu_threads()
-    sample_b = CPU_SAMPLE_B
+    sample_b = REF_SAMPLE_B
     for _ in range(max(1, min(args.warmup, 1))):
         cpu_port_run(sample_b, threads)
     times = []
