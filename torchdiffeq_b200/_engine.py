@@ -127,7 +127,7 @@ class AdaptiveEngine:
                  safety=0.9, ifactor=10.0, dfactor=0.2, max_num_steps=2 ** 31 - 1,
                  rtol_vec=None, atol_vec=None, norm_fn=None, q_view=None,
                  graph="auto", run_ahead=2, reduce_fn=None, n_global=None, seg_counts_global=None,
-                 callbacks=None):
+                 agree_fn=None, callbacks=None):
         if device.type != "cuda":
             raise _lib.TdqError("torchdiffeq_b200 runs on CUDA devices only (got %s); there is no CPU path" % device)
         if dtype not in _DTYPES:
@@ -146,6 +146,7 @@ class AdaptiveEngine:
         self.norm_fn = norm_fn          # custom norm callable on err/tol (compatibility path)
         self.q_view = q_view            # how to present err/tol to norm_fn
         self.reduce_fn = reduce_fn
+        self.agree_fn = agree_fn        # sharded solves: host-side max over ranks of the attempts queued
         self.callbacks = callbacks or {}
         self.graph_opt = graph
         self.run_ahead = int(run_ahead)
@@ -511,6 +512,18 @@ class AdaptiveEngine:
             else:
                 self._attempt()
             issued += 1
+        if self.agree_fn is not None:
+            # every attempt holds a collective: all ranks must have queued the same number before anyone
+            # waits for its stream (trailing attempts are no-ops on the device)
+            target = self.agree_fn(issued)
+            while issued < target:
+                if self._graph is not None:
+                    self._graph.replay()
+                    self.nfe += self.S
+                    self.launches += self._graph_launches
+                else:
+                    self._attempt()
+                issued += 1
         mb = self._wait_seq(issued)
         self._raise_if_failed(mb)
         torch.cuda.current_stream().synchronize()

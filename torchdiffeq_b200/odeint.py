@@ -226,12 +226,13 @@ def _make_adaptive_engine(p, method, rtol, atol, rtol_vec, atol_vec, options, fn
         if (st.unique(return_counts=True)[1] > 1).any():                               # :234-236
             raise ValueError("`step_t` and `jump_t` must not have any repeated elements between them.")
         step_t = st.to(p.device)
-    reduce_fn, n_global, seg_counts_global = None, None, None
+    reduce_fn, n_global, seg_counts_global, agree_fn = None, None, None, None
     pg = o.get("process_group")
     if pg is not None:
-        from .dist import make_reduce
+        from .dist import make_agree, make_reduce
         reduce_fn, n_global, seg_counts_global = make_reduce(pg, segs if segs is not None else
                                                              [(0, n if n is not None else p.n)], p.device)
+        agree_fn = make_agree(pg)
     return AdaptiveEngine(
         fn if fn is not None else p.fn, n if n is not None else p.n, p.dtype, p.device, method,
         rtol=rtol, atol=atol, rtol_vec=rtol_vec, atol_vec=atol_vec,
@@ -241,7 +242,8 @@ def _make_adaptive_engine(p, method, rtol, atol, rtol_vec, atol_vec, options, fn
         safety=o.get("safety", 0.9), ifactor=o.get("ifactor", 10.0), dfactor=o.get("dfactor", 0.2),
         max_num_steps=o.get("max_num_steps", 2 ** 31 - 1),
         norm_fn=norm_fn, q_view=q_view, graph=o.get("graph", "auto"), run_ahead=o.get("run_ahead", 2),
-        reduce_fn=reduce_fn, n_global=n_global, seg_counts_global=seg_counts_global, callbacks=callbacks)
+        reduce_fn=reduce_fn, n_global=n_global, seg_counts_global=seg_counts_global, agree_fn=agree_fn,
+        callbacks=callbacks)
 
 
 # ---- engine cache -------------------------------------------------------------------------------
