@@ -386,8 +386,7 @@ k_fit_commit(const TdqCtrl *__restrict__ c, T *y0p, const T *__restrict__ y1p, K
     if (VECTOR) {
         using V = Vec<T>;
         const size_t nvec = n / V::N;
-        const size_t v = (size_t)blockIdx.x * kThreads + threadIdx.x;
-        if (v < nvec) {
+        for (size_t v = (size_t)blockIdx.x * kThreads + threadIdx.x; v < nvec; v += (size_t)gridDim.x * kThreads) {
             const size_t i0 = v * V::N;
             V a0 = ld_stream<T>(y0p + i0), a1 = ld_stream<T>(y1p + i0);
             V f0 = ld_stream<T>(k0 + i0), f1 = ld_stream<T>(kS + i0);
@@ -440,6 +439,8 @@ int launch_fit(const TdqCtrl *c, void *y0, const void *y1, const KPtrsMut &fl, c
     if (vec) {
         const size_t nvec = n / Vec<T>::N;
         size_t blocks = (nvec + kThreads - 1) / kThreads;
+        const size_t cap = (size_t)sm_count() * 8;           // persistent: a rejected attempt's no-op launch stays cheap
+        if (blocks > cap) blocks = cap;
         if (blocks == 0) blocks = 1;
         k_fit_commit<T, NK, true><<<(unsigned)blocks, kThreads, 0, st>>>(
             c, (T *)y0, (const T *)y1, fl, kmid, (T *)coeff[0], (T *)coeff[1], (T *)coeff[2], (T *)coeff[3],
@@ -506,8 +507,7 @@ k_interp_eval(const TdqCtrl *__restrict__ c, const T *__restrict__ ce, const T *
     if (VECTOR) {
         using V = Vec<T>;
         const size_t nvec = n / V::N;
-        const size_t v = (size_t)blockIdx.x * kThreads + threadIdx.x;
-        if (v < nvec) {
+        for (size_t v = (size_t)blockIdx.x * kThreads + threadIdx.x; v < nvec; v += (size_t)gridDim.x * kThreads) {
             const size_t i0 = v * V::N;
             const V e = ld_stream<T>(ce + i0), d = ld_stream<T>(cd + i0), q = ld_stream<T>(cc + i0),
                     b = ld_stream<T>(cb + i0), a = ld_stream<T>(ca + i0);
@@ -538,6 +538,8 @@ int launch_eval(const TdqCtrl *c, const void *const *coeff, void *solution, cons
     if (vec) {
         const size_t nvec = n / Vec<T>::N;
         size_t blocks = (nvec + kThreads - 1) / kThreads;
+        const size_t cap = (size_t)sm_count() * 8;           // most launches are no-ops (no output time in the step)
+        if (blocks > cap) blocks = cap;
         if (blocks == 0) blocks = 1;
         k_interp_eval<T, true, AT><<<(unsigned)blocks, kThreads, 0, st>>>(
             c, (const T *)coeff[0], (const T *)coeff[1], (const T *)coeff[2], (const T *)coeff[3],
