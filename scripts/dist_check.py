@@ -15,11 +15,18 @@ import problems as P            # noqa: E402
 import torchdiffeq_b200 as tdq  # noqa: E402
 
 
+def log(*a):
+    print("[rank %s]" % os.environ.get("RANK"), *a, file=sys.stderr, flush=True)
+
+
 def main():
+    import faulthandler
+    faulthandler.dump_traceback_later(int(os.environ.get("DIST_CHECK_DUMP_AFTER", "90")), exit=True)
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     dist.init_process_group("nccl", device_id=dev)
+    log("process group up")
     B, D = 4096, 128
     f = P.BatchedLinear(D, torch.float32).to(dev)
     y0 = torch.randn(B, D, generator=torch.Generator().manual_seed(1)).to(dev)
@@ -29,9 +36,11 @@ def main():
     ok = True
     for mode in ({"graph": False, "run_ahead": 0}, {"graph": True, "run_ahead": 2}):
         st = {}
+        log("mode", mode, "sharded solve ...")
         with torch.no_grad():
             y = tdq.odeint(f, y0[rows].contiguous(), t, method="dopri5", rtol=1e-5, atol=1e-7,
                            options=dict(mode, process_group=True), _stats=st)
+        log("sharded solve done", st.get("n_accept"), st.get("n_reject"))
         gathered = [torch.empty_like(y) for _ in range(world)]
         dist.all_gather(gathered, y)
         if rank == 0:
