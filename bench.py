@@ -311,6 +311,10 @@ def run_ours(args):
                                               (cpu_b, cpu_rec["n_accept"] + cpu_rec["n_reject"], cpu_s)}
         print(json.dumps(line), flush=True)
     if world > 1:
+        # captured step graphs hold NCCL kernels: drop them before tearing the communicator down
+        tdq.clear_cache()
+        torch.cuda.synchronize()
+        dist.barrier()
         dist.destroy_process_group()
 
 

@@ -55,6 +55,9 @@ def main():
             ok = ok and err < 1e-5 and same_steps
     flag = torch.tensor([1 if ok else 0], device=dev)
     dist.broadcast(flag, 0)
+    # captured step graphs hold NCCL kernels: drop them before tearing the communicator down
+    tdq.clear_cache()
+    torch.cuda.synchronize()
     dist.destroy_process_group()
     if rank == 0:
         print("DIST_CHECK", "OK" if ok else "FAILED", flush=True)
