@@ -297,7 +297,11 @@ def run_ours(args):
             "gpu_launches": launches,
             "clocks": clocks,
             "roofline": {"bound": "hbm", "kernel": "k_combine (6 launches per attempt)", "achieved": achieved,
-                         "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                         "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         # dram__bytes_read + dram__bytes_write of the six launches of one attempt, from the ncu
+                         # --set full capture of this command (profiles/r1_ncu_full_summary.csv: rows NK=4 and NK=5
+                         # measured, 176.0 / 209.5 MB; the other rows scaled by their operand count)
+                         "traffic": 921.6e6, "traffic_source": "profiles/r1_ncu_full_summary.csv",
                          "peak_source": peak_src, "algorithmic_bytes_per_attempt": comb_bytes,
                          "ms_per_attempt": comb_ms, "launches_per_attempt": 6,
                          "combine_plus_error_norm": {"achieved": group, "frac": group / peak,
