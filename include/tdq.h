@@ -28,6 +28,7 @@ extern "C" {
 #define TDQ_MAX_STAGES 16            /* func evaluations per attempt, excluding f0 (dopri8: 13)   */
 #define TDQ_MAX_K      (TDQ_MAX_STAGES + 1) /* stage slots k_0 .. k_S                              */
 #define TDQ_MAX_SEGS   64            /* segments of a mixed (max-of-rms) norm                      */
+#define TDQ_MAX_RANKS  16            /* ranks of one NVLink domain sharing a sharded solve         */
 
 typedef enum {
     TDQ_OK = 0,
@@ -44,7 +45,8 @@ typedef enum {
     TDQ_RUN_OK = 0,
     TDQ_RUN_DT_UNDERFLOW = 1,   /* rk_common.py:286  assert t0 + dt > t0                          */
     TDQ_RUN_NONFINITE = 2,      /* rk_common.py:287  assert isfinite(y0).all()                     */
-    TDQ_RUN_MAX_STEPS = 3       /* rk_common.py:247  assert n_steps < max_num_steps                */
+    TDQ_RUN_MAX_STEPS = 3,      /* rk_common.py:247  assert n_steps < max_num_steps                */
+    TDQ_RUN_EXCHANGE_TIMEOUT = 4 /* a peer rank never delivered its norm partials (sharded solves)  */
 } tdq_run_status;
 
 /* Butcher tableau of an explicit embedded RK method, float64 as in the reference
@@ -220,6 +222,24 @@ int tdq_fixed_emit(int32_t dtype, void *y0, const void *y1, void *solution,
                    const int32_t *rec_begin_dev, const int32_t *out_idx_dev, const int32_t *mode_dev,
                    const void *slope_dev, int64_t *step_dev, const void *tstage_all_dev,
                    void *tstage_cur_dev, int64_t n_steps, size_t n, void *stream);
+
+/* ---- sharded solves: norm partials exchanged over NVLink peer memory INSIDE tdq_controller ----- */
+/* The reference has no multi-GPU path; its RMS norm is a mean over the whole batch (misc.py:22-23), so
+ * batch-sharded ranks must sum their n_seg+1 float64 partials before every accept/reject decision.
+ * Instead of a separate collective launch, each rank's controller kernel stores its partials straight
+ * into every peer's exchange buffer (P2P stores, release flag), spins on its own buffer until all
+ * peers' flags for this attempt have arrived, and adds the R vectors in rank order -- every rank gets
+ * the bitwise identical sum.  The buffer is the one allocation the library makes itself, because it
+ * must be a whole cudaMalloc allocation to be exported with cudaIpcGetMemHandle. */
+typedef struct { unsigned char bytes[64]; } tdq_ipc_handle;
+int tdq_xchg_create(void **dev_ptr, tdq_ipc_handle *handle_out);
+int tdq_xchg_open(const tdq_ipc_handle *handle, void **peer_ptr);
+int tdq_xchg_close(void *peer_ptr);
+int tdq_xchg_destroy(void *dev_ptr);
+/* After tdq_ctrl_init: peer_ptrs[r] = rank r's exchange buffer as mapped in THIS process (own buffer at
+ * index `rank`); epoch must be the same on all ranks and differ from solve to solve. */
+int tdq_ctrl_set_exchange(void *ctrl_dev, const void *const *peer_ptrs, int32_t rank, int32_t world,
+                          uint64_t epoch, void *stream);
 
 /* ---- adjoint augmented state (adjoint.py:72-105, misc.py:137-165) ------------------------- */
 /* dst[offset_i .. offset_i + len_i) = scale_i * src_i for i < n_src, one launch

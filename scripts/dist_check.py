@@ -34,7 +34,9 @@ def main():
     per = B // world
     rows = slice(rank * per, (rank + 1) * per)
     ok = True
-    for mode in ({"graph": False, "run_ahead": 0}, {"graph": True, "run_ahead": 2}):
+    modes = ({"graph": False, "run_ahead": 0}, {"graph": True, "run_ahead": 2},
+             {"graph": False, "run_ahead": 0, "exchange": "nccl"}, {"graph": True, "run_ahead": 2, "exchange": "nccl"})
+    for mode in modes:
         st = {}
         log("mode", mode, "sharded solve ...")
         with torch.no_grad():
@@ -47,7 +49,8 @@ def main():
             full = torch.cat(gathered, dim=1)
             st1 = {}
             with torch.no_grad():
-                want = tdq.odeint(f, y0, t, method="dopri5", rtol=1e-5, atol=1e-7, options=dict(mode), _stats=st1)
+                want = tdq.odeint(f, y0, t, method="dopri5", rtol=1e-5, atol=1e-7,
+                                  options={k: v for k, v in mode.items() if k != "exchange"}, _stats=st1)
             err = (full - want).abs().max().item()
             same_steps = (st["n_accept"], st["n_reject"]) == (st1["n_accept"], st1["n_reject"])
             print("mode", mode, "max|sharded - unsharded| =", err, "steps", (st["n_accept"], st["n_reject"]),

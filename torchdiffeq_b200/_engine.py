@@ -127,7 +127,7 @@ class AdaptiveEngine:
                  safety=0.9, ifactor=10.0, dfactor=0.2, max_num_steps=2 ** 31 - 1,
                  rtol_vec=None, atol_vec=None, norm_fn=None, q_view=None,
                  graph="auto", run_ahead=2, reduce_fn=None, n_global=None, seg_counts_global=None,
-                 agree_fn=None, callbacks=None):
+                 agree_fn=None, exchange=None, callbacks=None):
         if device.type != "cuda":
             raise _lib.TdqError("torchdiffeq_b200 runs on CUDA devices only (got %s); there is no CPU path" % device)
         if dtype not in _DTYPES:
@@ -147,6 +147,9 @@ class AdaptiveEngine:
         self.q_view = q_view            # how to present err/tol to norm_fn
         self.reduce_fn = reduce_fn
         self.agree_fn = agree_fn        # sharded solves: host-side max over ranks of the attempts queued
+        self.exchange = exchange        # sharded solves: per-attempt all-reduce fused into tdq_controller
+        if exchange is not None:
+            self.agree_fn = None        # no collective launch inside an attempt: trailing no-ops need no agreement
         self.callbacks = callbacks or {}
         self.graph_opt = graph
         self.run_ahead = int(run_ahead)
@@ -324,7 +327,7 @@ class AdaptiveEngine:
             r = torch.as_tensor(r, device=self.device)
             self.ratio_buf.copy_(r.to(self.ratio_buf.dtype).reshape(()))
             ratio_ptr = self.ratio_buf.data_ptr()
-        else:
+        elif self.exchange is None:
             self._reduce(self.norm_out)
         self._launch(lib.tdq_controller(ctrl, dc, self.norm_out.data_ptr(), self.seg_counts.data_ptr(), self.n_seg,
                                       ratio_ptr, st))
@@ -362,6 +365,8 @@ class AdaptiveEngine:
             raise SolverFailure("underflow in dt {}".format(mb.next_dt))
         if s == _lib.RUN_NONFINITE:
             raise SolverFailure("non-finite values in state `y`: {}".format(self.y0w))
+        if s == _lib.RUN_EXCHANGE_TIMEOUT:
+            raise _lib.TdqError("a peer rank did not deliver its norm partials within 10 s (sharded solve)")
         if s == _lib.RUN_MAX_STEPS:
             raise SolverFailure("max_num_steps exceeded ({}>={})".format(self.opt.max_num_steps, self.opt.max_num_steps))
         raise SolverFailure("solver failed with status %d" % s)
@@ -422,6 +427,8 @@ class AdaptiveEngine:
         t_start = float(t64[0]) if t_start is None else float(t_start)
         _lib.check(lib.tdq_ctrl_init(self.ctrl.data_ptr(), C.byref(self.tab), C.byref(self.opt),
                                      self.t_out.data_ptr(), t_start, n_out, self.mbox_dev, st))
+        if self.exchange is not None:
+            self.exchange.arm(self.ctrl.data_ptr(), st)
         if self.step_t is not None and self.step_t.numel() > 0:
             self._launch(lib.tdq_ctrl_set_step_t(self.ctrl.data_ptr(), self.step_t.data_ptr(),
                                                int(self.step_t.numel()), st))

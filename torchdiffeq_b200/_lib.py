@@ -10,7 +10,12 @@ TDQ_MAX_STAGES = 16
 TDQ_MAX_K = TDQ_MAX_STAGES + 1
 TDQ_MAX_SEGS = 64
 TDQ_F32, TDQ_F64 = 0, 1
-RUN_OK, RUN_DT_UNDERFLOW, RUN_NONFINITE, RUN_MAX_STEPS = 0, 1, 2, 3
+RUN_OK, RUN_DT_UNDERFLOW, RUN_NONFINITE, RUN_MAX_STEPS, RUN_EXCHANGE_TIMEOUT = 0, 1, 2, 3, 4
+TDQ_MAX_RANKS = 16
+
+
+class IpcHandle(C.Structure):
+    _fields_ = [("bytes", C.c_ubyte * 64)]
 
 
 class Tableau(C.Structure):
@@ -87,6 +92,11 @@ _SIGNATURES = {
     "tdq_rk4_stage": (C.c_int, [_i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "tdq_fixed_emit": (C.c_int, [_i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _sz, _vp]),
     "tdq_pack_segments": (C.c_int, [_i32, _vp, _pp, _pi64, _pi64, _pdbl, _i32, _vp]),
+    "tdq_xchg_create": (C.c_int, [_pp, C.POINTER(IpcHandle)]),
+    "tdq_xchg_open": (C.c_int, [C.POINTER(IpcHandle), _pp]),
+    "tdq_xchg_close": (C.c_int, [_vp]),
+    "tdq_xchg_destroy": (C.c_int, [_vp]),
+    "tdq_ctrl_set_exchange": (C.c_int, [_vp, _pp, _i32, _i32, C.c_uint64, _vp]),
 }
 
 EXPORTED_SYMBOLS = tuple(_SIGNATURES)

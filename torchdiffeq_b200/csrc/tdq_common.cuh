@@ -35,6 +35,10 @@ struct TdqCtrl {
     const double *t_out;                     // ascending output times, float64, device
     const double *step_t;                    // optional sorted grid, float64, device
     tdq_mailbox *mbox;                       // mapped host memory (device view) or NULL
+    // ---- sharded solves: peer exchange of the norm partials (tdq_ctrl_set_exchange) ----------
+    void *xpeer[TDQ_MAX_RANKS];              // rank r's TdqXBuf as mapped in this process
+    unsigned long long xepoch;               // solve number, identical on all ranks
+    int32_t xrank, xworld;
     // ---- dynamic: rk_state (rk_common.py:18) ----------------------------------------------
     double t0, t1, dt;                       // last accepted interval [t0,t1]; dt = NEXT step size
     double att_t0, att_dt, att_t1;           // the attempt in flight
@@ -52,6 +56,13 @@ struct TdqCtrl {
     // ---- state-dtype scalars torch views alias (func's time argument) ----------------------
     alignas(16) unsigned char tstage[8 * TDQ_MAX_K];
     alignas(16) unsigned char taux[8 * 2];
+};
+
+// Exchange buffer of one rank; double-buffered by attempt parity (a rank can be at most one attempt ahead
+// of a peer: its next controller needs that peer's next flag).
+struct TdqXBuf {
+    double vals[2][TDQ_MAX_RANKS][TDQ_MAX_SEGS + 2];
+    unsigned long long flags[2][TDQ_MAX_RANKS];
 };
 
 // ------------------------------------------------------------------------------------------------

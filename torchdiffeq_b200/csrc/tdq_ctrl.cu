@@ -281,7 +281,50 @@ k_controller(TdqCtrl *c, const double *norm_in, const int64_t *cnt, int n_seg, c
     const unsigned long long *gw = reinterpret_cast<const unsigned long long *>(c);
     for (int i = threadIdx.x; i < kWords; i += kCtrlThreads) sw[i] = gw[i];
     __syncthreads();
-    if (threadIdx.x == 0) controller<T>(*reinterpret_cast<TdqCtrl *>(raw), norm_in, cnt, n_seg, ratio_dev);
+    TdqCtrl &sc = *reinterpret_cast<TdqCtrl *>(raw);
+    __shared__ double xsum[TDQ_MAX_SEGS + 2];
+    __shared__ int xfail;
+    if (sc.xworld > 1 && !sc.halt && norm_in != nullptr && ratio_dev == nullptr) {
+        // Fused all-reduce over NVLink peer memory: thread t talks to rank t.
+        const int R = sc.xworld, me = sc.xrank, nv = n_seg + 1;
+        const int par = (int)(sc.seq & 1ull);
+        const unsigned long long want = (sc.xepoch << 32) | (sc.seq + 1ull);
+        if (threadIdx.x == 0) xfail = 0;
+        __syncthreads();
+        if ((int)threadIdx.x < R) {
+            const int t = threadIdx.x;
+            TdqXBuf *peer = reinterpret_cast<TdqXBuf *>(sc.xpeer[t]);
+            for (int i = 0; i < nv; ++i) peer->vals[par][me][i] = norm_in[i];          // P2P store
+            __threadfence_system();
+            asm volatile("st.release.sys.global.u64 [%0], %1;" :: "l"(&peer->flags[par][me]), "l"(want) : "memory");
+            TdqXBuf *mine = reinterpret_cast<TdqXBuf *>(sc.xpeer[me]);
+            unsigned long long seen = 0, t0 = 0, now = 0;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+            do {
+                asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(seen) : "l"(&mine->flags[par][t]) : "memory");
+                if (seen == want) break;
+                asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+            } while (now - t0 < 10000000000ull);                                       // 10 s: a peer died
+            if (seen != want) atomicExch(&xfail, 1);
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            if (xfail) {
+                sc.status = TDQ_RUN_EXCHANGE_TIMEOUT;
+                sc.halt = 1;
+            } else {
+                const TdqXBuf *mine = reinterpret_cast<const TdqXBuf *>(sc.xpeer[me]);
+                for (int i = 0; i < nv; ++i) {
+                    double a = 0.0;
+                    for (int r = 0; r < R; ++r) a += __ldcg(&mine->vals[par][r][i]);       // rank order: same sum everywhere
+                    xsum[i] = a;
+                }
+            }
+        }
+        __syncthreads();
+        norm_in = xsum;
+    }
+    if (threadIdx.x == 0) controller<T>(sc, norm_in, cnt, n_seg, ratio_dev);
     __syncthreads();
     unsigned long long *go = reinterpret_cast<unsigned long long *>(c);
     for (int i = threadIdx.x; i < kWords; i += kCtrlThreads) go[i] = sw[i];
@@ -295,6 +338,13 @@ __global__ void k_initial_finish(TdqCtrl *c, const double *s2, const int64_t *cn
     initial_finish<T>(*c, s2, cnt, n_seg);
 }
 __global__ void k_set_first_step(TdqCtrl *c, double dt) { c->dt = dt; }
+struct XPtrs { const void *p[TDQ_MAX_RANKS]; };
+__global__ void k_set_exchange(TdqCtrl *c, XPtrs xp, int rank, int world, unsigned long long epoch) {
+    for (int r = 0; r < TDQ_MAX_RANKS; ++r) c->xpeer[r] = const_cast<void *>(xp.p[r]);
+    c->xrank = rank;
+    c->xworld = world;
+    c->xepoch = epoch;
+}
 __global__ void k_reset_interval(TdqCtrl *c) { c->n_steps_interval = 0; }
 __global__ void k_set_step_t(TdqCtrl *c, const double *st, int n) {
     c->step_t = st;
@@ -438,6 +488,59 @@ int tdq_set_first_step(void *ctrl_dev, double first_step, void *stream) {
     TDQ_REQUIRE(ctrl_dev, "null ctrl");
     k_set_first_step<<<1, 1, 0, (cudaStream_t)stream>>>((TdqCtrl *)ctrl_dev, first_step);
     TDQ_CHECK_CUDA(cudaGetLastError());
+    return TDQ_OK;
+}
+
+int tdq_ctrl_set_exchange(void *ctrl_dev, const void *const *peer_ptrs, int32_t rank, int32_t world, uint64_t epoch,
+                          void *stream) {
+    TDQ_REQUIRE(ctrl_dev && peer_ptrs, "null argument");
+    TDQ_REQUIRE(world >= 1 && world <= TDQ_MAX_RANKS && rank >= 0 && rank < world, "rank/world out of range");
+    XPtrs xp;
+    memset(&xp, 0, sizeof(xp));
+    for (int r = 0; r < world; ++r) {
+        TDQ_REQUIRE(peer_ptrs[r] != nullptr, "missing peer buffer");
+        xp.p[r] = peer_ptrs[r];
+    }
+    k_set_exchange<<<1, 1, 0, (cudaStream_t)stream>>>((TdqCtrl *)ctrl_dev, xp, rank, world, (unsigned long long)epoch);
+    TDQ_CHECK_CUDA(cudaGetLastError());
+    return TDQ_OK;
+}
+
+int tdq_xchg_create(void **dev_ptr, tdq_ipc_handle *handle_out) {
+    TDQ_REQUIRE(dev_ptr && handle_out, "null argument");
+    static_assert(sizeof(cudaIpcMemHandle_t) <= sizeof(tdq_ipc_handle), "IPC handle does not fit");
+    void *p = nullptr;
+    TDQ_CHECK_CUDA(cudaMalloc(&p, sizeof(TdqXBuf)));
+    TDQ_CHECK_CUDA(cudaMemset(p, 0, sizeof(TdqXBuf)));
+    TDQ_CHECK_CUDA(cudaDeviceSynchronize());
+    cudaIpcMemHandle_t h;
+    cudaError_t e = cudaIpcGetMemHandle(&h, p);
+    if (e != cudaSuccess) {
+        cudaFree(p);
+        tdq_set_error("cudaIpcGetMemHandle failed: %s", cudaGetErrorString(e));
+        return TDQ_ERR_CUDA;
+    }
+    memset(handle_out, 0, sizeof(*handle_out));
+    memcpy(handle_out->bytes, &h, sizeof(h));
+    *dev_ptr = p;
+    return TDQ_OK;
+}
+
+int tdq_xchg_open(const tdq_ipc_handle *handle, void **peer_ptr) {
+    TDQ_REQUIRE(handle && peer_ptr, "null argument");
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle->bytes, sizeof(h));
+    TDQ_CHECK_CUDA(cudaIpcOpenMemHandle(peer_ptr, h, cudaIpcMemLazyEnablePeerAccess));
+    return TDQ_OK;
+}
+
+int tdq_xchg_close(void *peer_ptr) {
+    if (peer_ptr) TDQ_CHECK_CUDA(cudaIpcCloseMemHandle(peer_ptr));
+    return TDQ_OK;
+}
+
+int tdq_xchg_destroy(void *dev_ptr) {
+    if (dev_ptr) TDQ_CHECK_CUDA(cudaFree(dev_ptr));
     return TDQ_OK;
 }
 

@@ -53,3 +53,61 @@ def make_reduce(process_group, segs, device):
         dist.all_reduce(buf, op=dist.ReduceOp.SUM, group=pg)
 
     return reduce_fn, sum(counts_list), counts_list
+
+
+class PeerExchange:
+    """NVLink peer-memory exchange of the norm partials, fused into tdq_controller (include/tdq.h).
+
+    One cudaMalloc'ed exchange buffer per rank, exported with CUDA IPC, opened by every peer of the
+    same node; the controller kernel then does the all-reduce itself (P2P stores + release/acquire
+    flags), so an attempt contains no collective launch at all."""
+
+    def __init__(self, process_group, device):
+        import ctypes as C
+        from . import _lib
+        self._lib_mod = _lib
+        self.lib = _lib.load()
+        pg = None if process_group is True else process_group
+        self.rank, self.world = dist.get_rank(pg), dist.get_world_size(pg)
+        if self.world > _lib.TDQ_MAX_RANKS:
+            raise _lib.TdqError("peer exchange supports at most %d ranks" % _lib.TDQ_MAX_RANKS)
+        own = C.c_void_p()
+        h = _lib.IpcHandle()
+        _lib.check(self.lib.tdq_xchg_create(C.byref(own), C.byref(h)))
+        self.own = own.value
+        handles = [None] * self.world
+        dist.all_gather_object(handles, bytes(h.bytes), group=pg)
+        self.peers, self._opened = [], []
+        for r, hb in enumerate(handles):
+            if r == self.rank:
+                self.peers.append(self.own)
+                continue
+            ph = _lib.IpcHandle()
+            C.memmove(ph.bytes, hb, 64)
+            ptr = C.c_void_p()
+            _lib.check(self.lib.tdq_xchg_open(C.byref(ph), C.byref(ptr)))
+            self.peers.append(ptr.value)
+            self._opened.append(ptr.value)
+        self.ptrs = _lib.ptr_array(self.peers)
+        self.epoch = 0
+        dist.barrier(group=pg)                 # everybody has mapped everybody before the first use
+
+    def arm(self, ctrl_ptr, stream):
+        """Call after tdq_ctrl_init of every solve (solves are collective, so epochs agree)."""
+        self.epoch += 1
+        self._lib_mod.check(self.lib.tdq_ctrl_set_exchange(ctrl_ptr, self.ptrs, self.rank, self.world, self.epoch,
+                                                           stream))
+
+    def close(self):
+        try:
+            for p in self._opened:
+                self.lib.tdq_xchg_close(p)
+            self._opened = []
+            if self.own:
+                self.lib.tdq_xchg_destroy(self.own)
+                self.own = None
+        except Exception:
+            pass
+
+    def __del__(self):
+        self.close()

@@ -30,7 +30,7 @@ _ADJOINT_CALLBACK_NAMES = [name + "_adjoint" for name in _CALLBACK_NAMES]       
 _ADAPTIVE_OPTIONS = {"min_step", "max_step", "first_step", "step_t", "jump_t", "safety", "ifactor", "dfactor",
                      "max_num_steps", "dtype", "norm"}
 _FIXED_OPTIONS = {"step_size", "grid_constructor", "interp", "perturb", "norm"}
-_OUR_OPTIONS = {"graph", "run_ahead", "process_group", "cache"}
+_OUR_OPTIONS = {"graph", "run_ahead", "process_group", "cache", "exchange"}
 
 
 def _rms_norm(tensor):
@@ -226,13 +226,20 @@ def _make_adaptive_engine(p, method, rtol, atol, rtol_vec, atol_vec, options, fn
         if (st.unique(return_counts=True)[1] > 1).any():                               # :234-236
             raise ValueError("`step_t` and `jump_t` must not have any repeated elements between them.")
         step_t = st.to(p.device)
-    reduce_fn, n_global, seg_counts_global, agree_fn = None, None, None, None
+    reduce_fn, n_global, seg_counts_global, agree_fn, exchange = None, None, None, None, None
     pg = o.get("process_group")
     if pg is not None:
         from .dist import make_agree, make_reduce
         reduce_fn, n_global, seg_counts_global = make_reduce(pg, segs if segs is not None else
                                                              [(0, n if n is not None else p.n)], p.device)
         agree_fn = make_agree(pg)
+        if o.get("exchange", "peer") == "peer" and norm_fn is None:
+            try:
+                from .dist import PeerExchange
+                exchange = PeerExchange(pg, p.device)
+            except Exception as e:      # e.g. CUDA IPC not permitted in this container: keep the NCCL all-reduce
+                warnings.warn("torchdiffeq_b200: NVLink peer exchange unavailable (%s: %s); using the process "
+                              "group's all-reduce" % (type(e).__name__, e))
     return AdaptiveEngine(
         fn if fn is not None else p.fn, n if n is not None else p.n, p.dtype, p.device, method,
         rtol=rtol, atol=atol, rtol_vec=rtol_vec, atol_vec=atol_vec,
@@ -243,7 +250,7 @@ def _make_adaptive_engine(p, method, rtol, atol, rtol_vec, atol_vec, options, fn
         max_num_steps=o.get("max_num_steps", 2 ** 31 - 1),
         norm_fn=norm_fn, q_view=q_view, graph=o.get("graph", "auto"), run_ahead=o.get("run_ahead", 2),
         reduce_fn=reduce_fn, n_global=n_global, seg_counts_global=seg_counts_global, agree_fn=agree_fn,
-        callbacks=callbacks)
+        exchange=exchange, callbacks=callbacks)
 
 
 # ---- engine cache -------------------------------------------------------------------------------
