@@ -26,7 +26,7 @@ sys.path.insert(0, "/root/reference")
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 import torchdiffeq                                   # noqa: E402  (the reference)
-from torchdiffeq._impl import adaptive_heun, bosh3, dopri5, dopri8, fehlberg2   # noqa: E402
+from torchdiffeq._impl import adaptive_heun, bosh3, dopri5, dopri8, fehlberg2, tsit5   # noqa: E402
 import problems as P                                 # noqa: E402
 
 assert torchdiffeq.__file__.startswith("/root/reference"), torchdiffeq.__file__
@@ -54,7 +54,8 @@ class Rec(torch.nn.Module):
 def dump_tableaus():
     out = {}
     for name, cls in [("dopri5", dopri5.Dopri5Solver), ("dopri8", dopri8.Dopri8Solver), ("bosh3", bosh3.Bosh3Solver),
-                      ("fehlberg2", fehlberg2.Fehlberg2), ("adaptive_heun", adaptive_heun.AdaptiveHeunSolver)]:
+                      ("fehlberg2", fehlberg2.Fehlberg2), ("adaptive_heun", adaptive_heun.AdaptiveHeunSolver),
+                      ("tsit5", tsit5.Tsit5Solver)]:
         tab = cls.tableau
         fsal = bool(tab.c_sol[-1] == 0 and (tab.c_sol[:-1] == tab.beta[-1]).all())     # rk_common.py:83
         out[name] = {"alpha": tab.alpha.tolist(), "beta": [b.tolist() for b in tab.beta], "c_sol": tab.c_sol.tolist(),
@@ -74,7 +75,7 @@ def zoo():
     assert torch.equal(refp.LinearODE().A.detach(), P.LinearODE().A.detach())
     cases = {}
     for ode in ("constant", "sine", "linear", "exp"):
-        for method in ("dopri5", "dopri8", "bosh3", "fehlberg2", "adaptive_heun", "rk4"):
+        for method in ("dopri5", "dopri8", "tsit5", "bosh3", "fehlberg2", "adaptive_heun", "rk4"):
             for dtype in (torch.float32, torch.float64):
                 for reverse in (False, True):
                     if method == "rk4" and ode != "constant":
@@ -184,6 +185,11 @@ def options_cases():
 
 
 if __name__ == "__main__":
+    only = sys.argv[1:]
+    if only:
+        for name in only:
+            globals()[name]()
+        sys.exit(0)
     dump_tableaus()
     zoo()
     linear_batch()

@@ -40,7 +40,7 @@ def test_struct_sizes(lib):
     assert lib.load().tdq_ctrl_tstage_offset() % 16 == 0
 
 
-@pytest.mark.parametrize("name", ["dopri5", "dopri8", "bosh3", "fehlberg2", "adaptive_heun"])
+@pytest.mark.parametrize("name", ["dopri5", "dopri8", "tsit5", "bosh3", "fehlberg2", "adaptive_heun"])
 def test_tableaus_match_reference(lib, name):
     ref = json.load(open(os.path.join(ROOT, "tests", "golden", "tableaus.json")))[name]
     got = lib.tableau_as_dict(name)

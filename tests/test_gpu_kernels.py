@@ -33,7 +33,7 @@ def _rand(n, dtype, seed):
 
 
 @pytest.mark.parametrize("dtype", [torch.float32, torch.float64])
-@pytest.mark.parametrize("method", ["dopri5", "dopri8", "fehlberg2"])
+@pytest.mark.parametrize("method", ["dopri5", "dopri8", "tsit5", "fehlberg2"])
 @pytest.mark.parametrize("n,t_sign", [(4096 + 3, 1.0), (1000, -1.0), (5, 1.0)])
 def test_stage_combine_bitwise(method, dtype, n, t_sign):
     dt, t0 = 0.0371, 0.5

@@ -38,7 +38,7 @@ class Counted(torch.nn.Module):
 
 
 ZOO = ld("zoo.pt")
-ZOO_KEYS = [k for k in sorted(ZOO) if k.split("/")[1] in ("dopri5", "dopri8", "rk4", "bosh3")]
+ZOO_KEYS = [k for k in sorted(ZOO) if k.split("/")[1] in ("dopri5", "dopri8", "tsit5", "rk4", "bosh3")]
 
 
 @pytest.mark.parametrize("key", ZOO_KEYS)

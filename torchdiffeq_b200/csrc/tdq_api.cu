@@ -140,6 +140,15 @@ void make_dopri8(tdq_tableau *t) {
     fill(t, 13, 8, 1, alpha, b, sizeof(b) / sizeof(b[0]), sol, 9, err, 9, mid, 10);
 }
 
+#include "tdq_tableau_tsit5.inc"
+
+void make_tsit5(tdq_tableau *t) {
+    // Not FSAL by the reference's own test (rk_common.py:83: c_sol[-1] = 1/66 != 0), so y1 comes from the c_sol row.
+    fill(t, 6, 5, 0, kTsit5Alpha, kTsit5Beta, (int)(sizeof(kTsit5Beta) / sizeof(kTsit5Beta[0])), kTsit5Sol,
+         (int)(sizeof(kTsit5Sol) / sizeof(kTsit5Sol[0])), kTsit5Err, (int)(sizeof(kTsit5Err) / sizeof(kTsit5Err[0])),
+         kTsit5Mid, (int)(sizeof(kTsit5Mid) / sizeof(kTsit5Mid[0])));
+}
+
 void make_bosh3(tdq_tableau *t) {
     const double alpha[] = {1. / 2, 3. / 4, 1.};
     const Entry b[] = {{0, 0, 1. / 2}, {1, 1, 3. / 4}, {2, 0, 2. / 9}, {2, 1, 1. / 3}, {2, 2, 4. / 9}};
@@ -196,6 +205,7 @@ int tdq_tableau_get(const char *name, tdq_tableau *out) {
     TDQ_REQUIRE(name && out, "null argument");
     if (!strcmp(name, "dopri5")) make_dopri5(out);
     else if (!strcmp(name, "dopri8")) make_dopri8(out);
+    else if (!strcmp(name, "tsit5")) make_tsit5(out);
     else if (!strcmp(name, "bosh3")) make_bosh3(out);
     else if (!strcmp(name, "fehlberg2")) make_fehlberg2(out);
     else if (!strcmp(name, "adaptive_heun")) make_adaptive_heun(out);

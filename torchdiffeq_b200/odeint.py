@@ -16,7 +16,7 @@ from . import _lib
 from ._engine import AdaptiveEngine, Layout, on_solver_stream
 from ._fixed import FixedRK4Engine, grid_from_step_size
 
-ADAPTIVE_METHODS = ("dopri5", "dopri8", "bosh3", "fehlberg2", "adaptive_heun")
+ADAPTIVE_METHODS = ("dopri5", "dopri8", "tsit5", "bosh3", "fehlberg2", "adaptive_heun")
 FIXED_METHODS = ("rk4",)
 # Every name the reference registers (odeint.py:19-46); the ones outside SURVEY.md section 8 are
 # recognised and rejected explicitly rather than reported as "invalid".
