@@ -93,6 +93,9 @@ typedef struct {
     volatile double ratio;            /* error ratio of the last attempt                            */
     volatile double att_t0, att_dt;   /* start time and step size the last attempt used             */
     volatile double next_t0, next_dt; /* the same for the attempt prepared next (callback_step)     */
+    volatile int32_t on_jump_t;       /* the accepted attempt ended on a jump_t point: the host must */
+                                      /* re-evaluate f at taux[2] = next(T(t1)) (rk_common.py:346-351) */
+    volatile int32_t reserved;
 } tdq_mailbox;
 
 /* ---- library ------------------------------------------------------------------------------ */
@@ -114,7 +117,8 @@ int tdq_mailbox_destroy(tdq_mailbox *host_ptr);
 /* ---- control block ------------------------------------------------------------------------ */
 /* Size in bytes of the device control block, and offsets of the state-dtype scalars torch views
  * alias as func's time argument: tstage[i] = time func sees at stage i (already perturbed and
- * sign-corrected); taux[0] = time of f0, taux[1] = probe time of the initial-step heuristic. */
+ * sign-corrected); taux[0] = time of f0, taux[1] = probe time of the initial-step heuristic,
+ * taux[2] = Perturb.NEXT time after a jump_t point (taux has 4 slots). */
 size_t tdq_ctrl_size(void);
 size_t tdq_ctrl_tstage_offset(void);
 size_t tdq_ctrl_taux_offset(void);
@@ -129,6 +133,10 @@ int tdq_ctrl_init(void *ctrl_dev, const tdq_tableau *tab, const tdq_options *opt
 
 /* Optional sorted step_t grid (device float64, values >= t[0]); rk_common.py:223-241, :293-300. */
 int tdq_ctrl_set_step_t(void *ctrl_dev, const double *step_t_dev, int32_t n, void *stream);
+/* Optional sorted jump_t points (discontinuities of func); rk_common.py:229-241, :302-308, :346-351.
+ * Steps are clipped to them on the device; after an accepted step that ended on one, the mailbox says
+ * so and taux[2] holds the Perturb.NEXT time at which the host re-evaluates f (lock-step callers). */
+int tdq_ctrl_set_jump_t(void *ctrl_dev, const double *jump_t_dev, int32_t n, void *stream);
 
 /* ---- norms: deterministic segmented sum of squares ---------------------------------------- */
 /* Doubles the caller must provide (zero-initialised ONCE) as `partials` for the two reductions

@@ -191,7 +191,7 @@ def interp_eval(coeffs, t0, t1, t):
 # adaptive driver
 # ------------------------------------------------------------------------------------------------
 def odeint_adaptive(func, y0, t, method="dopri5", rtol=1e-7, atol=1e-9, norm=rms, min_step=0.,
-                    max_step=float("inf"), first_step=None, step_t=None, safety=0.9, ifactor=10.0,
+                    max_step=float("inf"), first_step=None, step_t=None, jump_t=None, safety=0.9, ifactor=10.0,
                     dfactor=0.2, max_num_steps=2 ** 31 - 1, record=None):
     """solvers.py:28-35 + rk_common.py:213-361 for a flat or shaped tensor state and ascending or
     descending t.  Returns solution [len(t), *y0.shape].  `record`, if a dict, receives
@@ -205,6 +205,8 @@ def odeint_adaptive(func, y0, t, method="dopri5", rtol=1e-7, atol=1e-9, norm=rms
         t = -t
         if step_t is not None:
             step_t = -step_t
+        if jump_t is not None:
+            jump_t = -jump_t
     user = func
     if sign < 0:
         func = lambda tt, yy: -1.0 * user(-tt, yy)                  # misc.py:158-165
@@ -225,8 +227,13 @@ def odeint_adaptive(func, y0, t, method="dopri5", rtol=1e-7, atol=1e-9, norm=rms
         step_t = torch.tensor([], dtype=f64)
     else:
         step_t = torch.sort(as64(step_t)[as64(step_t) >= t[0]]).values   # rk_common.py:372-375
+    if jump_t is None:
+        jump_t = torch.tensor([], dtype=f64)
+    else:
+        jump_t = torch.sort(as64(jump_t)[as64(jump_t) >= t[0]]).values
     import bisect
     next_step = min(bisect.bisect(step_t.tolist(), t[0]), len(step_t) - 1)   # :240
+    next_jump = min(bisect.bisect(jump_t.tolist(), t[0]), len(jump_t) - 1)   # :241
     y, f, t_lo, t_hi = y0, f0, t[0], t[0]
     coeffs = [y0] * 5
     stats = {"n_accept": 0, "n_reject": 0, "dts": [], "accepted": []}
@@ -249,6 +256,14 @@ def odeint_adaptive(func, y0, t, method="dopri5", rtol=1e-7, atol=1e-9, norm=rms
                 if on_step_t:
                     a1 = nxt
                     dt = a1 - a0
+            on_jump_t = False
+            if len(jump_t):                                         # :302-308
+                nxt = jump_t[next_jump]
+                on_jump_t = bool(a0 < nxt < a0 + dt)
+                if on_jump_t:
+                    on_step_t = False
+                    a1 = nxt
+                    dt = a1 - a0
             y1, f1, err, ks = rk_attempt(func, y, f, a0, dt, a1, ct)
             ratio = error_ratio(err, rtol, atol, y, y1, norm)
             accept = bool(ratio <= 1)
@@ -262,6 +277,10 @@ def odeint_adaptive(func, y0, t, method="dopri5", rtol=1e-7, atol=1e-9, norm=rms
                 coeffs = interp_fit(y, y1, ks, dt, ct)
                 if on_step_t and next_step != len(step_t) - 1:
                     next_step += 1
+                if on_jump_t:                                       # :346-351
+                    if next_jump != len(jump_t) - 1:
+                        next_jump += 1
+                    f1 = func(_next(a1.to(T)), y1)
                 y, f, t_lo, t_hi = y1, f1, a0, a1
                 stats["n_accept"] += 1
             else:

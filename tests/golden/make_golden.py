@@ -181,6 +181,18 @@ def options_cases():
         sol = torchdiffeq.odeint(tf, (ya, yb), tt, method="dopri5", rtol=1e-6, atol=1e-8)
         sol_v = torchdiffeq.odeint(tf, (ya, yb), tt, method="dopri5", rtol=(1e-6, 1e-4), atol=(1e-8, 1e-7))
     out["tuple"] = {"ya": ya, "yb": yb, "t": tt, "sol": [s.clone() for s in sol], "sol_vtol": [s.clone() for s in sol_v]}
+    # jump_t (rk_common.py:302-308, :346-351; odeint_tests.py:126-161)
+    for method in ("dopri5", "tsit5", "bosh3"):
+        for dtype in (torch.float32, torch.float64):
+            x0 = torch.tensor([1.0, 2.0], dtype=dtype)
+            tj = torch.tensor([0., 1.0])
+            plain, better = P.JumpField(), P.JumpField()
+            with torch.no_grad():
+                y_plain = torchdiffeq.odeint(plain, x0, tj, atol=1e-6, method=method)
+                y_jump = torchdiffeq.odeint(better, x0, tj, rtol=1e-6, atol=1e-6, method=method,
+                                            options={"jump_t": torch.tensor([0.5])})
+            out["jump/%s/%s" % (method, str(dtype).split(".")[1])] = {
+                "y_plain": y_plain, "nfe_plain": plain.nfe, "y_jump": y_jump, "nfe_jump": better.nfe}
     torch.save(out, os.path.join(HERE, "options.pt"))
 
 

@@ -68,6 +68,20 @@ class ExpODE(torch.nn.Module):
         return torch.exp(-0.1 * t)
 
 
+class JumpField:
+    """A vector field with a discontinuity at t = 0.5 (the reference's _JumpF, odeint_tests.py:113-123);
+    branches on the host, so it is only usable in lock-step mode."""
+
+    def __init__(self):
+        self.nfe = 0
+
+    def __call__(self, t, x):
+        self.nfe += 1
+        if t < 0.5:
+            return -0.5 * x
+        return x ** 2
+
+
 PROBLEMS = {"constant": ConstantODE, "linear": LinearODE, "sine": SineODE, "exp": ExpODE}
 
 

@@ -246,3 +246,83 @@ def test_callbacks_counts():
         tdq().odeint(f, torch.ones(10, dtype=torch.float64, device=DEV),
                      torch.linspace(1, 8, 10, dtype=torch.float64, device=DEV), method="dopri5", rtol=1e-3, atol=1e-5)
     assert f.n["step"] > 0 and f.n["accept"] + f.n["reject"] == f.n["step"]
+
+
+def test_c3_full_size_adjoint_modes_agree():
+    """BASELINE config 3 at full size: odeint_adjoint dopri5, MLP 64-256-256-64 (P=98,880), B=8192, float32,
+    rtol=1e-4 atol=1e-6, loss = mean(y(1)^2).  The lock-step path (the reference's exact call sequence) and the
+    captured-graph path must produce the same gradients; a reduced batch is checked against the CPU oracle."""
+    f = P.MLPField(dim=64, hidden=256, seed=0).to(DEV)
+    y0 = torch.randn(8192, 64, generator=torch.Generator().manual_seed(1)).to(DEV)
+    t = torch.tensor([0., 1.], device=DEV)
+    grads = {}
+    for mode in ("lockstep", "graph"):
+        f.zero_grad()
+        yy = y0.clone().requires_grad_(True)
+        y = tdq().odeint_adjoint(f, yy, t, method="dopri5", rtol=1e-4, atol=1e-6, options=dict(MODES[mode]))
+        y[-1].pow(2).mean().backward()
+        grads[mode] = [yy.grad.clone()] + [q.grad.clone() for q in f.parameters()]
+        assert all(torch.isfinite(g).all() for g in grads[mode])
+    for a, b in zip(grads["lockstep"], grads["graph"]):
+        assert torch.allclose(a, b, rtol=1e-5, atol=1e-8 + 1e-5 * float(b.abs().max()))
+    # oracle at B=256 (same net): 1e-4 relative, the north_star's bar for adjoint gradients
+    fc = P.MLPField(dim=64, hidden=256, seed=0)
+    ys = y0[:256].cpu()
+    gy = torch.zeros(2, 256, 64)
+    with torch.no_grad():
+        yend = O.odeint_adaptive(fc, ys, t.cpu(), "dopri5", rtol=1e-6, atol=1e-8)[-1]
+    gy[-1] = 2 * yend / yend.numel()
+    _, gy0, gp = O.adjoint_gradients(fc, list(fc.parameters()), ys, t.cpu(), gy, "dopri5", rtol=1e-6, atol=1e-8)
+    f.zero_grad()
+    yy = y0[:256].clone().requires_grad_(True)
+    y = tdq().odeint_adjoint(f, yy, t, method="dopri5", rtol=1e-6, atol=1e-8)
+    y[-1].pow(2).mean().backward()
+    assert (yy.grad.cpu() - gy0).abs().max() <= 1e-4 * gy0.abs().max()
+    for q, want in zip(f.parameters(), gp):
+        assert (q.grad.cpu() - want).abs().max() <= 1e-4 * want.abs().max()
+
+
+def test_c3_bf16_autocast_forward():
+    """Config 3's 'bf16 fwd / fp32 adjoint': func evaluates under bf16 autocast, the state stays float32
+    (the solver casts func's output to the state dtype like the reference's k[..., i] = f assignment)."""
+    net = P.MLPField(dim=64, hidden=256, seed=0).to(DEV)
+
+    class AC(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.net = net
+
+        def forward(self, t, y):
+            with torch.autocast("cuda", dtype=torch.bfloat16):
+                return self.net(t, y)
+    y0 = torch.randn(1024, 64, generator=torch.Generator().manual_seed(1)).to(DEV)
+    t = torch.tensor([0., 1.], device=DEV)
+    with torch.no_grad():
+        y_bf = tdq().odeint(AC(), y0, t, method="dopri5", rtol=1e-3, atol=1e-4)
+        y_32 = tdq().odeint(net, y0, t, method="dopri5", rtol=1e-3, atol=1e-4)
+    assert y_bf.dtype == torch.float32
+    assert torch.allclose(y_bf, y_32, rtol=5e-2, atol=5e-2)
+    yy = y0.clone().requires_grad_(True)
+    out = tdq().odeint_adjoint(AC(), yy, t, method="dopri5", rtol=1e-3, atol=1e-4)
+    out[-1].pow(2).mean().backward()
+    assert torch.isfinite(yy.grad).all() and yy.grad.abs().max() > 0
+
+
+@pytest.mark.parametrize("key", sorted(k for k in ld("options.pt") if k.startswith("jump/")))
+def test_jump_t_golden(key):
+    """TestDiscontinuities.test_odeint_jump_t (odeint_tests.py:126-161): with jump_t the solver steps exactly to
+    the discontinuity and re-evaluates f beyond it, so it needs fewer evaluations; NFE equals the reference's."""
+    case = ld("options.pt")[key]
+    _, method, dt = key.split("/")
+    dtype = getattr(torch, dt)
+    x0 = torch.tensor([1.0, 2.0], dtype=dtype, device=DEV)
+    tj = torch.tensor([0., 1.0], device=DEV)
+    f = P.JumpField()
+    with torch.no_grad():
+        y = tdq().odeint(f, x0, tj, method=method, rtol=1e-6, atol=1e-6, options={"jump_t": torch.tensor([0.5], device=DEV)})
+    assert f.nfe == case["nfe_jump"] if dtype == torch.float64 else abs(f.nfe - case["nfe_jump"]) <= 24
+    assert f.nfe < case["nfe_plain"]
+    assert torch.allclose(y.cpu(), case["y_jump"], rtol=1e-5 if dtype == torch.float32 else 1e-9, atol=1e-6)
+    with pytest.raises(ValueError):
+        tdq().odeint(f, x0, tj, method=method, options={"jump_t": torch.tensor([0.5], device=DEV),
+                                                          "step_t": torch.tensor([0.5], device=DEV)})

@@ -152,3 +152,20 @@ def test_options(key):
     if key in ("min_step", "max_step", "step_t"):
         assert cf.nfe == case["nfe"] and rec["accepted"] == case["acc"]
     assert torch.allclose(y, case["y"], rtol=1e-6, atol=1e-8)
+
+
+@pytest.mark.parametrize("key", sorted(k for k in ld("options.pt") if k.startswith("jump/")))
+def test_jump_t(key):
+    """rk_common.py:302-308, :346-351 against the reference (odeint_tests.py:126-161)."""
+    case = ld("options.pt")[key]
+    _, method, dt = key.split("/")
+    dtype = getattr(torch, dt)
+    x0 = torch.tensor([1.0, 2.0], dtype=dtype)
+    tj = torch.tensor([0., 1.0])
+    f = P.JumpField()
+    with torch.no_grad():
+        y = O.odeint_adaptive(f, x0, tj, method, rtol=1e-6, atol=1e-6, jump_t=torch.tensor([0.5]))
+    # float32 at rtol 1e-6 sits on the precision floor: a noise-decided reject may differ (see _close)
+    assert f.nfe == case["nfe_jump"] if dtype == torch.float64 else abs(f.nfe - case["nfe_jump"]) <= 24
+    assert f.nfe < case["nfe_plain"]
+    assert torch.allclose(y, case["y_jump"], rtol=1e-5 if dtype == torch.float32 else 1e-9, atol=1e-6)

@@ -123,7 +123,7 @@ class AdaptiveEngine:
     """
 
     def __init__(self, fn, n, dtype, device, method, *, rtol, atol, segs=None, t_sign=1.0,
-                 pieces=None, min_step=0.0, max_step=float("inf"), first_step=None, step_t=None,
+                 pieces=None, min_step=0.0, max_step=float("inf"), first_step=None, step_t=None, jump_t=None,
                  safety=0.9, ifactor=10.0, dfactor=0.2, max_num_steps=2 ** 31 - 1,
                  rtol_vec=None, atol_vec=None, norm_fn=None, q_view=None,
                  graph="auto", run_ahead=2, reduce_fn=None, n_global=None, seg_counts_global=None,
@@ -153,7 +153,10 @@ class AdaptiveEngine:
         self.callbacks = callbacks or {}
         self.graph_opt = graph
         self.run_ahead = int(run_ahead)
-        if self.callbacks:
+        self.jump_t = jump_t
+        if self.callbacks or (jump_t is not None and jump_t.numel() > 0):
+            # both need the host between attempts: callbacks by definition, jump_t because f is re-evaluated on
+            # the far side of the discontinuity after the step that lands on it (rk_common.py:346-351)
             self.graph_opt = False
             self.run_ahead = 0
 
@@ -183,7 +186,7 @@ class AdaptiveEngine:
         o = self.lib.tdq_ctrl_tstage_offset()
         self.tstage = self.ctrl[o:o + 8 * _lib.TDQ_MAX_K].view(dtype)
         o = self.lib.tdq_ctrl_taux_offset()
-        self.taux = self.ctrl[o:o + 16].view(dtype)
+        self.taux = self.ctrl[o:o + 32].view(dtype)
         self.y0w = torch.zeros(self.n, **kw)
         self.ytmp = torch.zeros(self.n, **kw)
         self.y1 = torch.zeros(self.n, **kw)
@@ -429,6 +432,9 @@ class AdaptiveEngine:
                                      self.t_out.data_ptr(), t_start, n_out, self.mbox_dev, st))
         if self.exchange is not None:
             self.exchange.arm(self.ctrl.data_ptr(), st)
+        if self.jump_t is not None and self.jump_t.numel() > 0:
+            self._launch(lib.tdq_ctrl_set_jump_t(self.ctrl.data_ptr(), self.jump_t.data_ptr(),
+                                                 int(self.jump_t.numel()), st))
         if self.step_t is not None and self.step_t.numel() > 0:
             self._launch(lib.tdq_ctrl_set_step_t(self.ctrl.data_ptr(), self.step_t.data_ptr(),
                                                int(self.step_t.numel()), st))
@@ -477,8 +483,14 @@ class AdaptiveEngine:
                 name = "callback_accept_step" if mb.accept else "callback_reject_step"   # :339, :354
                 if cb.get(name) is not None:
                     cb[name](*self._with_y(mb.att_t0, mb.att_dt))
+            jumped = bool(mb.accept) and bool(mb.on_jump_t)
             self._attempt_back(kp)
             del k, kp, keep
+            if jumped:                                      # rk_common.py:346-351: f on the far side of the jump
+                f = self._call_fn(self.taux[2], self.y0w, 0)
+                if f.data_ptr() != self.k0.data_ptr():
+                    self.k0.copy_(f)
+                del f
             if mb.done:
                 break
         torch.cuda.current_stream().synchronize()

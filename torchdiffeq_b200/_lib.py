@@ -48,6 +48,7 @@ class Mailbox(C.Structure):
         ("t0", C.c_double), ("t1", C.c_double), ("dt", C.c_double),
         ("ratio", C.c_double), ("att_t0", C.c_double), ("att_dt", C.c_double),
         ("next_t0", C.c_double), ("next_dt", C.c_double),
+        ("on_jump_t", C.c_int32), ("reserved", C.c_int32),
     ]
 
 
@@ -75,6 +76,7 @@ _SIGNATURES = {
     "tdq_ctrl_taux_offset": (_sz, []),
     "tdq_ctrl_init": (C.c_int, [_vp, _ptab, C.POINTER(Options), _vp, _dbl, _i32, _vp, _vp]),
     "tdq_ctrl_set_step_t": (C.c_int, [_vp, _vp, _i32, _vp]),
+    "tdq_ctrl_set_jump_t": (C.c_int, [_vp, _vp, _i32, _vp]),
     "tdq_norm_partials_len": (_sz, [_sz, _i32]),
     "tdq_scaled_sumsq": (C.c_int, [_vp, _i32, _vp, _vp, _vp, _vp, _vp, _pi64, _pi64, _i32, _sz, _vp, _vp, _vp]),
     "tdq_initial_step_h0": (C.c_int, [_vp, _i32, _vp, _vp, _vp, _i32, _vp]),

@@ -34,6 +34,8 @@ struct TdqCtrl {
     int64_t max_num_steps, n_global;
     const double *t_out;                     // ascending output times, float64, device
     const double *step_t;                    // optional sorted grid, float64, device
+    const double *jump_t;                    // optional sorted discontinuity points, float64, device
+    int32_t n_jump_t, next_jump_index, on_jump_t, pad_jump;
     tdq_mailbox *mbox;                       // mapped host memory (device view) or NULL
     // ---- sharded solves: peer exchange of the norm partials (tdq_ctrl_set_exchange) ----------
     void *xpeer[TDQ_MAX_RANKS];              // rank r's TdqXBuf as mapped in this process
@@ -55,7 +57,7 @@ struct TdqCtrl {
     double att_dtT;                          // T(dt) of the attempt in flight
     // ---- state-dtype scalars torch views alias (func's time argument) ----------------------
     alignas(16) unsigned char tstage[8 * TDQ_MAX_K];
-    alignas(16) unsigned char taux[8 * 2];
+    alignas(16) unsigned char taux[8 * 4];
 };
 
 // Exchange buffer of one rank; double-buffered by attempt parity (a rank can be at most one attempt ahead

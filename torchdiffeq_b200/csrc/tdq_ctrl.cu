@@ -12,6 +12,10 @@ template <typename T> __device__ __forceinline__ T prev_repr(T t);   // misc.py:
 template <> __device__ __forceinline__ float prev_repr<float>(float t) { return nextafterf(t, __fsub_rn(t, 1.0f)); }
 template <> __device__ __forceinline__ double prev_repr<double>(double t) { return nextafter(t, __dsub_rn(t, 1.0)); }
 
+template <typename T> __device__ __forceinline__ T next_repr(T t);   // Perturb.NEXT
+template <> __device__ __forceinline__ float next_repr<float>(float t) { return nextafterf(t, __fadd_rn(t, 1.0f)); }
+template <> __device__ __forceinline__ double next_repr<double>(double t) { return nextafter(t, __dadd_rn(t, 1.0)); }
+
 template <typename T> __device__ __forceinline__ void store_T(unsigned char *raw, int i, T v) {
     reinterpret_cast<T *>(raw)[i] = v;
 }
@@ -42,6 +46,16 @@ template <typename T> __device__ void prepare_attempt(TdqCtrl &c) {
         const double nxt = c.step_t[c.next_step_index];
         if (t0 < nxt && nxt < t0 + dt) {
             c.on_step_t = 1;
+            t1 = nxt;
+            dt = t1 - t0;
+        }
+    }
+    c.on_jump_t = 0;
+    if (c.n_jump_t > 0) {                                             // :302-308 (after the step_t handling)
+        const double nxt = c.jump_t[c.next_jump_index];
+        if (t0 < nxt && nxt < t0 + dt) {
+            c.on_jump_t = 1;
+            c.on_step_t = 0;
             t1 = nxt;
             dt = t1 - t0;
         }
@@ -86,7 +100,7 @@ __device__ double norm_from_sums(const TdqCtrl &c, const double *sums, const int
     return nan ? CUDART_NAN : best;
 }
 
-__device__ void write_mailbox(TdqCtrl &c, double fin_t0, double fin_dt) {
+__device__ void write_mailbox(TdqCtrl &c, double fin_t0, double fin_dt, int jumped = 0) {
     c.seq += 1;
     tdq_mailbox *m = c.mbox;
     if (!m) return;
@@ -104,6 +118,7 @@ __device__ void write_mailbox(TdqCtrl &c, double fin_t0, double fin_dt) {
     m->att_dt = fin_dt;
     m->next_t0 = c.att_t0;
     m->next_dt = c.att_dt;
+    m->on_jump_t = jumped;
     __threadfence_system();
     m->seq = c.seq;
     __threadfence_system();
@@ -146,6 +161,10 @@ __device__ void controller(TdqCtrl &c, const double *norm_in, const int64_t *seg
         c.t1 = c.att_t1;
         c.n_accept += 1;
         if (c.on_step_t && c.next_step_index != c.n_step_t - 1) c.next_step_index += 1;
+        if (c.on_jump_t) {                                            // :346-351
+            if (c.next_jump_index != c.n_jump_t - 1) c.next_jump_index += 1;
+            store_T<T>(c.taux, 2, A::mul((T)c.t_sign, next_repr<T>((T)c.att_t1)));
+        }
         // constants _interp_fit needs from THIS attempt (rk_common.py:363-369)
         const T dtT = (T)c.att_dtT, sgn = (T)c.t_sign;
         c.fit_sdt = (double)A::mul(sgn, dtT);
@@ -192,8 +211,9 @@ __device__ void controller(TdqCtrl &c, const double *norm_in, const int64_t *seg
         c.halt = 1;
     }
     const double fin_t0 = c.att_t0, fin_dt = c.att_dt;
+    const int jumped = (accept && c.on_jump_t) ? 1 : 0;
     prepare_attempt<T>(c);
-    write_mailbox(c, fin_t0, fin_dt);
+    write_mailbox(c, fin_t0, fin_dt, jumped);
 }
 
 // misc.py:55-63: h0 from d0, d1.
@@ -346,6 +366,14 @@ __global__ void k_set_exchange(TdqCtrl *c, XPtrs xp, int rank, int world, unsign
     c->xepoch = epoch;
 }
 __global__ void k_reset_interval(TdqCtrl *c) { c->n_steps_interval = 0; }
+__global__ void k_set_jump_t(TdqCtrl *c, const double *jt, int n) {
+    c->jump_t = jt;
+    c->n_jump_t = n;
+    int idx = 0;                                                      // rk_common.py:241
+    while (idx < n && !(jt[idx] > c->t1)) ++idx;
+    c->next_jump_index = (idx < n - 1) ? idx : (n - 1);
+    if (n <= 0) c->next_jump_index = 0;
+}
 __global__ void k_set_step_t(TdqCtrl *c, const double *st, int n) {
     c->step_t = st;
     c->n_step_t = n;
@@ -444,6 +472,13 @@ int tdq_ctrl_init(void *ctrl_dev, const tdq_tableau *tab, const tdq_options *opt
 int tdq_ctrl_set_step_t(void *ctrl_dev, const double *step_t_dev, int32_t n, void *stream) {
     TDQ_REQUIRE(ctrl_dev, "null ctrl");
     k_set_step_t<<<1, 1, 0, (cudaStream_t)stream>>>((TdqCtrl *)ctrl_dev, step_t_dev, n);
+    TDQ_CHECK_CUDA(cudaGetLastError());
+    return TDQ_OK;
+}
+
+int tdq_ctrl_set_jump_t(void *ctrl_dev, const double *jump_t_dev, int32_t n, void *stream) {
+    TDQ_REQUIRE(ctrl_dev, "null ctrl");
+    k_set_jump_t<<<1, 1, 0, (cudaStream_t)stream>>>((TdqCtrl *)ctrl_dev, jump_t_dev, n);
     TDQ_CHECK_CUDA(cudaGetLastError());
     return TDQ_OK;
 }

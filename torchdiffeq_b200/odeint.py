@@ -215,17 +215,18 @@ def _make_adaptive_engine(p, method, rtol, atol, rtol_vec, atol_vec, options, fn
                           pieces=None, norm_fn=None, q_view=None, callbacks=None, solver_name=None):
     o = options
     _warn_unused(solver_name or method, o, _ADAPTIVE_OPTIONS)
-    if o.get("jump_t") is not None:
-        raise NotImplementedError("jump_t is not implemented on the B200 path yet (SURVEY.md section 8(f) item 2)")
     if o.get("dtype", torch.float64) != torch.float64:
         raise NotImplementedError("time dtype other than float64 (options['dtype']) is not implemented")
-    step_t = o.get("step_t")
-    if step_t is not None:
-        st = torch.as_tensor(step_t, dtype=torch.float64).to("cpu")
-        st = torch.sort(st[st >= p.t_cpu[0].double()]).values                          # rk_common.py:372-375
-        if (st.unique(return_counts=True)[1] > 1).any():                               # :234-236
-            raise ValueError("`step_t` and `jump_t` must not have any repeated elements between them.")
-        step_t = st.to(p.device)
+    def _tvals(v):                                                                     # rk_common.py:372-375
+        v = torch.as_tensor(v, dtype=torch.float64).to("cpu")
+        return torch.sort(v[v >= p.t_cpu[0].double()]).values
+    step_t, jump_t = o.get("step_t"), o.get("jump_t")
+    st = _tvals(step_t) if step_t is not None else torch.tensor([], dtype=torch.float64)
+    jt = _tvals(jump_t) if jump_t is not None else torch.tensor([], dtype=torch.float64)
+    if (torch.cat([st, jt]).unique(return_counts=True)[1] > 1).any():                  # :233-236
+        raise ValueError("`step_t` and `jump_t` must not have any repeated elements between them.")
+    step_t = st.to(p.device) if step_t is not None else None
+    jump_t = jt.to(p.device) if jump_t is not None else None
     reduce_fn, n_global, seg_counts_global, agree_fn, exchange = None, None, None, None, None
     pg = o.get("process_group")
     if pg is not None:
@@ -245,7 +246,7 @@ def _make_adaptive_engine(p, method, rtol, atol, rtol_vec, atol_vec, options, fn
         rtol=rtol, atol=atol, rtol_vec=rtol_vec, atol_vec=atol_vec,
         segs=segs, t_sign=p.t_sign, pieces=pieces,
         min_step=o.get("min_step", 0), max_step=o.get("max_step", float("inf")),
-        first_step=o.get("first_step"), step_t=step_t,
+        first_step=o.get("first_step"), step_t=step_t, jump_t=jump_t,
         safety=o.get("safety", 0.9), ifactor=o.get("ifactor", 10.0), dfactor=o.get("dfactor", 0.2),
         max_num_steps=o.get("max_num_steps", 2 ** 31 - 1),
         norm_fn=norm_fn, q_view=q_view, graph=o.get("graph", "auto"), run_ahead=o.get("run_ahead", 2),
