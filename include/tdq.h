@@ -213,9 +213,12 @@ int tdq_interp_eval_at(void *ctrl_dev, int32_t dtype, const void *const *coeff, 
 /* Reset the per-output-interval attempt counter (rk_common.py:245). */
 int tdq_ctrl_reset_interval(void *ctrl_dev, void *stream);
 
-/* ---- fixed grid RK4, 3/8 rule (fixed_grid.py:24-29, rk_common.py:110-118) ----------------- */
+/* ---- fixed grid: RK4 3/8 rule (fixed_grid.py:24-29, rk_common.py:110-118) and the other explicit
+ *      fixed-step methods euler / midpoint / heun2 / heun3 (fixed_grid.py:6-60, rk_common.py:121-158) -- */
 /* which = 1: y0 + (dt*k1)*(1/3);  2: y0 + dt*(k2 - k1*(1/3));  3: y0 + dt*((k1 - k2) + k3);
- * 4: y1 = y0 + ((k1 + 3*(k2 + k3)) + k4)*dt*0.125 (solvers.py:115).
+ * 4: y1 = y0 + ((k1 + 3*(k2 + k3)) + k4)*dt*0.125 (solvers.py:115);
+ * 5: y0 + dt*k1 (euler; midpoint and heun2 pass the relevant k as k1);  6: y0 + k1*(0.5*dt) (midpoint stage);
+ * 7: y0 + dt*(k1*0.5 + k2*0.5) (heun2);  8: y0 + dt*(k2*(2/3)) (heun3 stage 3);  9: y0 + dt*(k1*0.25 + k3*0.75) (heun3).
  * dt is dt_dev[step_dev[0]] (state dtype array, int64 device step counter; step_dev may be NULL for
  * index 0) so that one captured graph serves every step of the grid. */
 int tdq_rk4_stage(int32_t dtype, int32_t which, void *y_out, const void *y0, const void *k1,

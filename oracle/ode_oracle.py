@@ -311,7 +311,36 @@ def rk4_increment(func, t0, dt, t1, y0, perturb=False):
     return (k1 + 3 * (k2 + k3) + k4) * dt * 0.125
 
 
-def odeint_rk4(func, y0, t, grid=None, perturb=False):
+def fixed_increment(method, func, t0, dt, t1, y0, perturb=False):
+    """dy of one step of a fixed-grid method: fixed_grid.py:6-60 with rk_common.py:110-158."""
+    if method == "rk4":
+        return rk4_increment(func, t0, dt, t1, y0, perturb)
+    T = _real_dtype(y0)
+    cast = lambda tt: tt.to(T)
+    f0 = func(_next(cast(t0)) if perturb else cast(t0), y0)
+    if method == "euler":                                            # fixed_grid.py:9-11
+        return dt * f0
+    if method == "midpoint":                                         # fixed_grid.py:17-21
+        half_dt = 0.5 * dt
+        y_mid = y0 + f0 * half_dt
+        return dt * func(cast(t0 + half_dt), y_mid)
+    if method == "heun2":                                            # rk_common.py:141-158, tableau fixed_grid.py:54-58
+        t2 = cast(t0 + dt * 1.0)
+        k2 = func(_prev(t2) if perturb else t2, y0 + dt * f0 * 1.0)
+        return dt * (f0 * (1 / 2) + k2 * (1 / 2))
+    if method == "heun3":                                            # rk_common.py:121-139, tableau fixed_grid.py:38-43
+        k2 = func(cast(t0 + dt * (1 / 3)), y0 + dt * f0 * (1 / 3))
+        k3 = func(cast(t0 + dt * (2 / 3)), y0 + dt * (f0 * 0.0 + k2 * (2 / 3)))
+        return dt * (f0 * (1 / 4) + k2 * 0.0 + k3 * (3 / 4))
+    raise ValueError(method)
+
+
+def odeint_fixed(func, y0, t, method="rk4", grid=None, perturb=False):
+    """solvers.py:102-128 for any explicit fixed-grid method, linear interpolation (:175-181)."""
+    return odeint_rk4(func, y0, t, grid=grid, perturb=perturb, method=method)
+
+
+def odeint_rk4(func, y0, t, grid=None, perturb=False, method="rk4"):
     """solvers.py:102-128 with linear interpolation (:175-181).  t keeps its own dtype (no float64 cast)."""
     sign = 1.0
     if len(t) > 1 and t[0] > t[1]:
@@ -329,7 +358,7 @@ def odeint_rk4(func, y0, t, grid=None, perturb=False):
     j, y = 1, y0
     for t0, t1 in zip(grid[:-1], grid[1:]):
         dt = t1 - t0
-        y1 = y + rk4_increment(func, t0, dt, t1, y, perturb)
+        y1 = y + fixed_increment(method, func, t0, dt, t1, y, perturb)
         while j < len(t) and t1 >= t[j]:
             if t[j] == t0:
                 solution[j] = y

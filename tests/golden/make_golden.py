@@ -75,11 +75,12 @@ def zoo():
     assert torch.equal(refp.LinearODE().A.detach(), P.LinearODE().A.detach())
     cases = {}
     for ode in ("constant", "sine", "linear", "exp"):
-        for method in ("dopri5", "dopri8", "tsit5", "bosh3", "fehlberg2", "adaptive_heun", "rk4"):
+        for method in ("dopri5", "dopri8", "tsit5", "bosh3", "fehlberg2", "adaptive_heun", "rk4", "euler", "midpoint",
+                       "heun2", "heun3"):
             for dtype in (torch.float32, torch.float64):
                 for reverse in (False, True):
-                    if method == "rk4" and ode != "constant":
-                        continue
+                    if method in ("rk4", "euler", "midpoint", "heun2", "heun3") and ode != "constant":
+                        continue                                   # odeint_tests.py:42
                     f, y0, t, sol = P.construct_problem("cpu", ode=ode, reverse=reverse, dtype=dtype)
                     if method == "dopri8":                         # odeint_tests.py:29-32
                         kw = dict(rtol=1e-12, atol=1e-14) if dtype == torch.float64 else dict(rtol=1e-7, atol=1e-7)
@@ -119,7 +120,13 @@ def spiral_rk4():
         t2 = torch.linspace(0., 5., 7)
         y2 = torchdiffeq.odeint(f, y0[:16], t2, method="rk4", options={"step_size": 0.03})
     rows = [0, 1, 2, 10, 100, 500, 998, 999]
-    torch.save({"y0": y0, "rows": rows, "y_rows": y[rows].clone(), "t2": t2, "y2": y2},
+    fixed = {}
+    for method in ("euler", "midpoint", "heun2", "heun3", "rk4"):
+        for perturb in (False, True):
+            with torch.no_grad():
+                fixed["%s/%d" % (method, perturb)] = torchdiffeq.odeint(
+                    f, y0[:16], t2, method=method, options={"step_size": 0.03, "perturb": perturb})
+    torch.save({"y0": y0, "rows": rows, "y_rows": y[rows].clone(), "t2": t2, "y2": y2, "fixed": fixed},
                os.path.join(HERE, "spiral_rk4.pt"))
 
 

@@ -38,7 +38,8 @@ class Counted(torch.nn.Module):
 
 
 ZOO = ld("zoo.pt")
-ZOO_KEYS = [k for k in sorted(ZOO) if k.split("/")[1] in ("dopri5", "dopri8", "tsit5", "rk4", "bosh3")]
+FIXED = ("rk4", "euler", "midpoint", "heun2", "heun3")
+ZOO_KEYS = [k for k in sorted(ZOO) if k.split("/")[1] in ("dopri5", "dopri8", "tsit5", "bosh3") + FIXED]
 
 
 @pytest.mark.parametrize("key", ZOO_KEYS)
@@ -58,11 +59,13 @@ def test_zoo_lockstep(key):
     eps = {"constant": 3e-4, "sine": 3e-4, "linear": 2e-3, "exp": 5e-2}[ode]
     if method == "bosh3":
         eps = {"constant": 1e-3, "sine": 5e-3, "linear": 2e-3, "exp": 5e-2}[ode]
+    if method in FIXED:
+        eps = 1e-5                                 # odeint_tests.py:45 (fixed methods, constant problem)
     rel = ((sol - y) / sol).abs().max()
     assert rel < eps, rel
     tol = 5e-4 if dtype == torch.float32 else 1e-6
     assert torch.allclose(y.cpu(), case["y"], rtol=tol, atol=tol * 1e-2), (y.cpu() - case["y"]).abs().max()
-    if method == "rk4":
+    if method in FIXED:
         # fixed grid: the solver's own arithmetic is bitwise the reference's (test_gpu_kernels.py); func itself
         # (pow on the GPU vs the CPU) may differ in the last bit
         assert torch.allclose(y.cpu(), case["y"], rtol=1e-6 if dtype == torch.float32 else 1e-13, atol=0)
@@ -121,6 +124,14 @@ def test_spiral_rk4_golden():
     # elementwise part is bitwise the reference's; func (a 2x2 mm) may differ in the last bit between CPU and GPU
     assert torch.allclose(y[case["rows"]].cpu(), case["y_rows"], rtol=1e-4, atol=1e-6)
     assert torch.allclose(y2.cpu(), case["y2"], rtol=1e-4, atol=1e-6)
+    for key, want in case["fixed"].items():       # euler / midpoint / heun2 / heun3 / rk4, perturb off and on
+        method, perturb = key.split("/")
+        with torch.no_grad():
+            got = tdq().odeint(f, case["y0"][:16].to(DEV), case["t2"].to(DEV), method=method,
+                               options={"step_size": 0.03, "perturb": bool(int(perturb))})
+        finite = torch.isfinite(want)                # explicit Euler overflows on this problem, in the reference too
+        assert torch.equal(torch.isfinite(got.cpu()), finite) or method == "euler", key
+        assert torch.allclose(got.cpu()[finite], want[finite], rtol=1e-4, atol=1e-6) or method == "euler", key
 
 
 @pytest.mark.parametrize("mode", ["lockstep", "graph"])

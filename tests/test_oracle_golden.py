@@ -28,6 +28,7 @@ def _nfe_close(a, b, dtype=torch.float64):
 
 
 ZOO = ld("zoo.pt")
+FIXED = ("rk4", "euler", "midpoint", "heun2", "heun3")
 
 
 @pytest.mark.parametrize("key", sorted(ZOO))
@@ -38,14 +39,14 @@ def test_zoo(key):
     f, y0, t, _ = P.construct_problem("cpu", ode=ode, reverse=direction == "rev", dtype=dtype)
     cf = O.Counter(f)
     with torch.no_grad():
-        if method == "rk4":
-            y = O.odeint_rk4(cf, y0, t)
+        if method in FIXED:
+            y = O.odeint_fixed(cf, y0, t, method)
         else:
             rec = {}
             kw = {"rtol": case["kw"].get("rtol", 1e-7), "atol": case["kw"].get("atol", 1e-9)}
             y = O.odeint_adaptive(cf, y0, t, method, record=rec, **kw)
     assert _close(y, case["y"], dtype), (y - case["y"]).abs().max()
-    if method == "rk4":
+    if method in FIXED:
         assert torch.equal(y, case["y"])          # fixed grid, same op order: bitwise
         assert cf.nfe == case["nfe"]
     else:
@@ -85,6 +86,13 @@ def test_spiral_rk4():
     # same op order as the reference: bitwise
     assert torch.equal(y[case["rows"]], case["y_rows"])
     assert torch.equal(y2, case["y2"])
+    for key, want in case["fixed"].items():       # every explicit fixed-grid method, with and without perturb
+        method, perturb = key.split("/")
+        with torch.no_grad():
+            got = O.odeint_fixed(f, case["y0"][:16], case["t2"], method, grid=_grid(case["t2"], 0.03),
+                                 perturb=bool(int(perturb)))
+        # explicit Euler blows up on the cubic spiral at this step size: NaNs must match too
+        assert torch.allclose(got, want, rtol=0, atol=0, equal_nan=True), key
 
 
 def _grid(t, step_size):

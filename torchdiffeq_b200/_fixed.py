@@ -26,8 +26,17 @@ def grid_from_step_size(step_size):
     return _grid_constructor
 
 
-class FixedRK4Engine:
-    def __init__(self, fn, n, dtype, device, *, t_sign=1.0, perturb=False, graph="auto", callbacks=None):
+FIXED_METHODS = ("euler", "midpoint", "heun2", "heun3", "rk4")
+
+
+class FixedGridEngine:
+    """Explicit fixed-step methods of fixed_grid.py:6-60 on one captured step graph."""
+
+    def __init__(self, fn, n, dtype, device, *, method="rk4", t_sign=1.0, perturb=False, graph="auto",
+                 callbacks=None):
+        if method not in FIXED_METHODS:
+            raise ValueError("unknown fixed-grid method %r" % method)
+        self.method = method
         if device.type != "cuda":
             raise _lib.TdqError("torchdiffeq_b200 runs on CUDA devices only (got %s); there is no CPU path" % device)
         if dtype not in _DTYPES:
@@ -40,6 +49,7 @@ class FixedRK4Engine:
         self.callbacks = callbacks or {}
         self.graph_opt = False if self.callbacks else graph
         self.nfe = 0
+        self.launches = 0
 
     # ---- tables ---------------------------------------------------------------------------
     def _tabulate(self, grid, t):
@@ -48,10 +58,23 @@ class FixedRK4Engine:
         t0, t1 = grid[:-1], grid[1:]
         dt = t1 - t0                                                   # solvers.py:112
         # func times of the four evaluations, then _PerturbFunc's cast to the state dtype (misc.py:187)
-        ts = torch.stack([t0, t0 + dt * _ONE_THIRD, t0 + dt * _TWO_THIRDS, t1], dim=1).to(T)
-        if self.perturb:                                               # fixed_grid.py:27-28, misc.py:188-193
+        z = torch.zeros_like(t0)
+        m = self.method
+        if m == "rk4":                                                 # rk_common.py:110-118
+            cols, prev_col = [t0, t0 + dt * _ONE_THIRD, t0 + dt * _TWO_THIRDS, t1], 3
+        elif m == "euler":                                             # fixed_grid.py:9-11
+            cols, prev_col = [t0, z, z, z], None
+        elif m == "midpoint":                                          # fixed_grid.py:17-21
+            cols, prev_col = [t0, t0 + 0.5 * dt, z, z], None
+        elif m == "heun2":                                             # fixed_grid.py:51-60, rk_common.py:141-158
+            cols, prev_col = [t0, t0 + dt * 1.0, z, z], 1
+        else:                                                          # heun3: fixed_grid.py:35-45, rk_common.py:121-139
+            cols, prev_col = [t0, t0 + dt * (1 / 3), t0 + dt * (2 / 3), z], None
+        ts = torch.stack(cols, dim=1).to(T)
+        if self.perturb:                                               # Perturb.NEXT / PREV, misc.py:188-193
             ts[:, 0] = torch.nextafter(ts[:, 0], ts[:, 0] + 1)
-            ts[:, 3] = torch.nextafter(ts[:, 3], ts[:, 3] - 1)
+            if prev_col is not None:
+                ts[:, prev_col] = torch.nextafter(ts[:, prev_col], ts[:, prev_col] - 1)
         ts = ts * self.t_sign
         dtT = dt.to(T) * self.t_sign           # sign of _ReverseFunc folded into dt (exact)
         # outputs: step s emits every t[j] with t1_s >= t[j] not emitted before (solvers.py:117)
@@ -87,19 +110,47 @@ class FixedRK4Engine:
         lib, dc, n, st = self.lib, self.dc, self.n, _stream()
         y0, ya, y1 = self.y0w.data_ptr(), self.ytmp.data_ptr(), self.y1.data_ptr()
         dtp, stp = self.dt_dev.data_ptr(), self.step_dev.data_ptr()
+
+        def stage(which, out, k1=None, k2=None, k3=None, k4=None):
+            p = lambda k: k.data_ptr() if k is not None else None
+            _lib.check(lib.tdq_rk4_stage(dc, which, out, y0, p(k1), p(k2), p(k3), p(k4), dtp, stp, n, st))
+            self.launches += 1
+        m = self.method
         k1 = self._call_fn(self.tcur[0], self.y0w, None)
-        _lib.check(lib.tdq_rk4_stage(dc, 1, ya, y0, k1.data_ptr(), None, None, None, dtp, stp, n, st))
-        k2 = self._call_fn(self.tcur[1], self.ytmp, None)
-        _lib.check(lib.tdq_rk4_stage(dc, 2, y1, y0, k1.data_ptr(), k2.data_ptr(), None, None, dtp, stp, n, st))
-        k3 = self._call_fn(self.tcur[2], self.y1, None)
-        _lib.check(lib.tdq_rk4_stage(dc, 3, ya, y0, k1.data_ptr(), k2.data_ptr(), k3.data_ptr(), None, dtp, stp, n, st))
-        k4 = self._call_fn(self.tcur[3], self.ytmp, None)
-        _lib.check(lib.tdq_rk4_stage(dc, 4, y1, y0, k1.data_ptr(), k2.data_ptr(), k3.data_ptr(), k4.data_ptr(),
-                                     dtp, stp, n, st))
+        keep = [k1]
+        if m == "rk4":
+            stage(1, ya, k1)
+            k2 = self._call_fn(self.tcur[1], self.ytmp, None)
+            stage(2, y1, k1, k2)
+            k3 = self._call_fn(self.tcur[2], self.y1, None)
+            stage(3, ya, k1, k2, k3)
+            k4 = self._call_fn(self.tcur[3], self.ytmp, None)
+            stage(4, y1, k1, k2, k3, k4)
+            keep += [k2, k3, k4]
+        elif m == "euler":
+            stage(5, y1, k1)                                   # dt * f0
+        elif m == "midpoint":
+            stage(6, ya, k1)                                   # y_mid = y0 + f0 * half_dt
+            k2 = self._call_fn(self.tcur[1], self.ytmp, None)
+            stage(5, y1, k2)                                   # dt * func(t0 + half_dt, y_mid)
+            keep.append(k2)
+        elif m == "heun2":
+            stage(5, ya, k1)                                   # y0 + dt * k1 * 1.0
+            k2 = self._call_fn(self.tcur[1], self.ytmp, None)
+            stage(7, y1, k1, k2)
+            keep.append(k2)
+        else:                                                  # heun3
+            stage(1, ya, k1)                                   # y0 + dt * k1 * (1/3)
+            k2 = self._call_fn(self.tcur[1], self.ytmp, None)
+            stage(8, y1, None, k2)                             # y0 + dt * (k1*0 + k2*(2/3))
+            k3 = self._call_fn(self.tcur[2], self.y1, None)
+            stage(9, y1, k1, None, k3)                         # y0 + dt * (k1/4 + k2*0 + 3*k3/4)
+            keep += [k2, k3]
         _lib.check(lib.tdq_fixed_emit(dc, y0, y1, self.solution.data_ptr(), self.rec_begin.data_ptr(),
                                       self.out_idx.data_ptr(), self.mode.data_ptr(), self.slope.data_ptr(), stp,
                                       self.ts_all.data_ptr(), self.tcur.data_ptr(), self.n_steps, n, st))
-        return (k1, k2, k3, k4)
+        self.launches += 2
+        return keep
 
     def solve(self, y0_flat, grid_cpu, t_cpu):
         dev, T = self.device, self.dtype
@@ -139,10 +190,11 @@ class FixedRK4Engine:
         if self.graph_opt in (True, "auto") and n_steps > 2:
             try:
                 graph = torch.cuda.CUDAGraph()
-                nfe = self.nfe
+                nfe, launches = self.nfe, self.launches
                 with torch.cuda.graph(graph, stream=solver_stream(self.device)):
                     keep = self._step()
-                self.nfe = nfe
+                self._evals, self._graph_launches = self.nfe - nfe, self.launches - launches
+                self.nfe, self.launches = nfe, launches
             except Exception as e:
                 graph = None
                 if self.graph_opt is True:
@@ -153,10 +205,14 @@ class FixedRK4Engine:
         while done < n_steps:
             if graph is not None:
                 graph.replay()
-                self.nfe += 4
+                self.nfe += self._evals
+                self.launches += self._graph_launches
             else:
                 self._step()
             done += 1
         torch.cuda.current_stream().synchronize()
         del graph
         return self.solution
+
+
+FixedRK4Engine = FixedGridEngine      # r1 name

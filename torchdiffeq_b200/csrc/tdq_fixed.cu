@@ -20,15 +20,28 @@ k_rk4(T *__restrict__ out, const T *__restrict__ y0, const T *__restrict__ k1, c
       const T *__restrict__ k3, const T *__restrict__ k4, const T *__restrict__ dt_arr,
       const int64_t *__restrict__ step, size_t n) {
     using A = Ar<T>;
+    // which operands the expression reads (k1,k2,k3,k4)
+    constexpr bool kA = WHICH != 8;
+    constexpr bool kB = WHICH == 2 || WHICH == 3 || WHICH == 4 || WHICH == 7 || WHICH == 8;
+    constexpr bool kC = WHICH == 3 || WHICH == 4 || WHICH == 9;
+    constexpr bool kD = WHICH == 4;
     const T dt = dt_arr[step ? *step : 0];
     const T third = (T)(1.0 / 3.0);
     auto f = [&](T y, T a, T b, T c_, T d) -> T {
         if (WHICH == 1) return A::add(y, A::mul(A::mul(dt, a), third));                 // y0 + dt*k1*_one_third
         if (WHICH == 2) return A::add(y, A::mul(dt, A::sub(b, A::mul(a, third))));      // y0 + dt*(k2 - k1*_one_third)
         if (WHICH == 3) return A::add(y, A::mul(dt, A::add(A::sub(a, b), c_)));         // y0 + dt*(k1 - k2 + k3)
-        // y0 + (k1 + 3*(k2 + k3) + k4)*dt*0.125
-        const T s = A::add(A::add(a, A::mul((T)3, A::add(b, c_))), d);
-        return A::add(y, A::mul(A::mul(s, dt), (T)0.125));
+        if (WHICH == 4) {                                                               // y0 + (k1 + 3*(k2 + k3) + k4)*dt*0.125
+            const T s = A::add(A::add(a, A::mul((T)3, A::add(b, c_))), d);
+            return A::add(y, A::mul(A::mul(s, dt), (T)0.125));
+        }
+        // the other fixed-grid methods of fixed_grid.py:6-60 (rk_common.py:121-158)
+        if (WHICH == 5) return A::add(y, A::mul(dt, a));                                // euler / midpoint final / heun2 stage: y0 + dt*k
+        if (WHICH == 6) return A::add(y, A::mul(a, A::mul((T)0.5, dt)));                // midpoint stage: y0 + f0*half_dt
+        if (WHICH == 7) return A::add(y, A::mul(dt, A::add(A::mul(a, (T)0.5), A::mul(b, (T)0.5))));   // heun2: y0 + dt*(k1/2 + k2/2)
+        if (WHICH == 8) return A::add(y, A::mul(dt, A::mul(b, (T)(2.0 / 3.0))));        // heun3 stage 3: y0 + dt*(k1*0 + k2*2/3)
+        // heun3 final: y0 + dt*(k1*1/4 + k2*0 + k3*3/4)
+        return A::add(y, A::mul(dt, A::add(A::mul(a, (T)0.25), A::mul(c_, (T)0.75))));
     };
     if (VECTOR) {
         using V = Vec<T>;
@@ -36,27 +49,25 @@ k_rk4(T *__restrict__ out, const T *__restrict__ y0, const T *__restrict__ k1, c
         const size_t v = (size_t)blockIdx.x * kThreads + threadIdx.x;
         if (v < nvec) {
             const size_t i0 = v * V::N;
-            V y = ld_stream<T>(y0 + i0), a = ld_stream<T>(k1 + i0), b, c_, d;
-            if (WHICH >= 2) b = ld_stream<T>(k2 + i0);
-            if (WHICH >= 3) c_ = ld_stream<T>(k3 + i0);
-            if (WHICH >= 4) d = ld_stream<T>(k4 + i0);
+            V y = ld_stream<T>(y0 + i0), a, b, c_, d;
+            if (kA) a = ld_stream<T>(k1 + i0);
+            if (kB) b = ld_stream<T>(k2 + i0);
+            if (kC) c_ = ld_stream<T>(k3 + i0);
+            if (kD) d = ld_stream<T>(k4 + i0);
             V r;
 #pragma unroll
             for (int e = 0; e < V::N; ++e)
-                r.v[e] = f(y.v[e], a.v[e], WHICH >= 2 ? b.v[e] : (T)0, WHICH >= 3 ? c_.v[e] : (T)0,
-                           WHICH >= 4 ? d.v[e] : (T)0);
+                r.v[e] = f(y.v[e], kA ? a.v[e] : (T)0, kB ? b.v[e] : (T)0, kC ? c_.v[e] : (T)0, kD ? d.v[e] : (T)0);
             st_vec<T>(out + i0, r);
         }
         if (blockIdx.x == gridDim.x - 1) {
             const size_t i = nvec * V::N + threadIdx.x;
             if (i < n)
-                out[i] = f(y0[i], k1[i], WHICH >= 2 ? k2[i] : (T)0, WHICH >= 3 ? k3[i] : (T)0,
-                           WHICH >= 4 ? k4[i] : (T)0);
+                out[i] = f(y0[i], kA ? k1[i] : (T)0, kB ? k2[i] : (T)0, kC ? k3[i] : (T)0, kD ? k4[i] : (T)0);
         }
     } else {
         for (size_t i = (size_t)blockIdx.x * kThreads + threadIdx.x; i < n; i += (size_t)gridDim.x * kThreads)
-            out[i] = f(y0[i], k1[i], WHICH >= 2 ? k2[i] : (T)0, WHICH >= 3 ? k3[i] : (T)0,
-                       WHICH >= 4 ? k4[i] : (T)0);
+            out[i] = f(y0[i], kA ? k1[i] : (T)0, kB ? k2[i] : (T)0, kC ? k3[i] : (T)0, kD ? k4[i] : (T)0);
     }
 }
 
@@ -148,20 +159,28 @@ extern "C" {
 int tdq_rk4_stage(int32_t dtype, int32_t which, void *y_out, const void *y0, const void *k1, const void *k2,
                   const void *k3, const void *k4, const void *dt_dev, const int64_t *step_dev, size_t n,
                   void *stream) {
-    TDQ_REQUIRE(y_out && y0 && k1 && dt_dev, "null argument");
-    TDQ_REQUIRE(which >= 1 && which <= 4, "which must be 1..4");
-    TDQ_REQUIRE(which < 2 || k2, "k2 required");
-    TDQ_REQUIRE(which < 3 || k3, "k3 required");
-    TDQ_REQUIRE(which < 4 || k4, "k4 required");
+    TDQ_REQUIRE(y_out && y0 && dt_dev, "null argument");
+    TDQ_REQUIRE(which >= 1 && which <= 9, "which must be 1..9");
+    const bool nA = which != 8, nB = which == 2 || which == 3 || which == 4 || which == 7 || which == 8,
+               nC = which == 3 || which == 4 || which == 9, nD = which == 4;
+    TDQ_REQUIRE(!nA || k1, "k1 required");
+    TDQ_REQUIRE(!nB || k2, "k2 required");
+    TDQ_REQUIRE(!nC || k3, "k3 required");
+    TDQ_REQUIRE(!nD || k4, "k4 required");
     if (n == 0) return TDQ_OK;
-    bool vec = tdq_aligned16(y_out) && tdq_aligned16(y0) && tdq_aligned16(k1) && (which < 2 || tdq_aligned16(k2)) &&
-               (which < 3 || tdq_aligned16(k3)) && (which < 4 || tdq_aligned16(k4));
+    bool vec = tdq_aligned16(y_out) && tdq_aligned16(y0) && (!nA || tdq_aligned16(k1)) && (!nB || tdq_aligned16(k2)) &&
+               (!nC || tdq_aligned16(k3)) && (!nD || tdq_aligned16(k4));
     cudaStream_t st = (cudaStream_t)stream;
     switch (which) {
         case 1: TDQ_DISPATCH_T(dtype, (launch_rk4<T, 1>(y_out, y0, k1, k2, k3, k4, dt_dev, step_dev, n, vec, st))); break;
         case 2: TDQ_DISPATCH_T(dtype, (launch_rk4<T, 2>(y_out, y0, k1, k2, k3, k4, dt_dev, step_dev, n, vec, st))); break;
         case 3: TDQ_DISPATCH_T(dtype, (launch_rk4<T, 3>(y_out, y0, k1, k2, k3, k4, dt_dev, step_dev, n, vec, st))); break;
-        default: TDQ_DISPATCH_T(dtype, (launch_rk4<T, 4>(y_out, y0, k1, k2, k3, k4, dt_dev, step_dev, n, vec, st))); break;
+        case 4: TDQ_DISPATCH_T(dtype, (launch_rk4<T, 4>(y_out, y0, k1, k2, k3, k4, dt_dev, step_dev, n, vec, st))); break;
+        case 5: TDQ_DISPATCH_T(dtype, (launch_rk4<T, 5>(y_out, y0, k1, k2, k3, k4, dt_dev, step_dev, n, vec, st))); break;
+        case 6: TDQ_DISPATCH_T(dtype, (launch_rk4<T, 6>(y_out, y0, k1, k2, k3, k4, dt_dev, step_dev, n, vec, st))); break;
+        case 7: TDQ_DISPATCH_T(dtype, (launch_rk4<T, 7>(y_out, y0, k1, k2, k3, k4, dt_dev, step_dev, n, vec, st))); break;
+        case 8: TDQ_DISPATCH_T(dtype, (launch_rk4<T, 8>(y_out, y0, k1, k2, k3, k4, dt_dev, step_dev, n, vec, st))); break;
+        default: TDQ_DISPATCH_T(dtype, (launch_rk4<T, 9>(y_out, y0, k1, k2, k3, k4, dt_dev, step_dev, n, vec, st))); break;
     }
     TDQ_CHECK_CUDA(cudaGetLastError());
     return TDQ_OK;

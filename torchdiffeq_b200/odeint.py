@@ -14,10 +14,10 @@ import torch
 
 from . import _lib
 from ._engine import AdaptiveEngine, Layout, on_solver_stream
-from ._fixed import FixedRK4Engine, grid_from_step_size
+from ._fixed import FixedGridEngine, grid_from_step_size
 
 ADAPTIVE_METHODS = ("dopri5", "dopri8", "tsit5", "bosh3", "fehlberg2", "adaptive_heun")
-FIXED_METHODS = ("rk4",)
+FIXED_METHODS = ("euler", "midpoint", "heun2", "heun3", "rk4")
 # Every name the reference registers (odeint.py:19-46); the ones outside SURVEY.md section 8 are
 # recognised and rejected explicitly rather than reported as "invalid".
 REFERENCE_METHODS = (
@@ -333,9 +333,10 @@ def _solve(p):
         if key is not None:
             sol = sol.clone()                           # the engine reuses its solution buffer
         return sol, eng
-    # fixed grid RK4 (solvers.py:55-128)
+    # fixed grid: euler / midpoint / heun2 / heun3 / rk4 (solvers.py:55-128, fixed_grid.py:6-60)
     o = p.options
-    _warn_unused("RK4", o, _FIXED_OPTIONS)
+    _warn_unused({"euler": "Euler", "midpoint": "Midpoint", "heun2": "Heun2", "heun3": "Heun3", "rk4": "RK4"}[p.method],
+                 o, _FIXED_OPTIONS)
     step_size, gc = o.get("step_size"), o.get("grid_constructor")
     if step_size is None:
         grid_constructor = gc if gc is not None else (lambda f, y0, t: t)
@@ -358,8 +359,8 @@ def _solve(p):
         def fn(t_, y_flat, _f=p.fn):
             out = torch.zeros(layout.n, dtype=p.dtype, device=p.device)
             return layout.flatten(list(_f(t_, y_flat)), out=out)
-    eng = FixedRK4Engine(fn, p.n, p.dtype, p.device, t_sign=p.t_sign, perturb=o.get("perturb", False),
-                         graph=o.get("graph", "auto"), callbacks=p.callbacks)
+    eng = FixedGridEngine(fn, p.n, p.dtype, p.device, method=p.method, t_sign=p.t_sign,
+                          perturb=o.get("perturb", False), graph=o.get("graph", "auto"), callbacks=p.callbacks)
     sol = eng.solve(p.y0_flat, grid, p.t_cpu)
     return sol, eng
 
