@@ -334,7 +334,6 @@ class AdaptiveEngine:
             self._reduce(self.norm_out)
         self._launch(lib.tdq_controller(ctrl, dc, self.norm_out.data_ptr(), self.seg_counts.data_ptr(), self.n_seg,
                                       ratio_ptr, st))
-        self._k_last = (k, kp, keep)
         return k, kp, keep
 
     def _attempt_back(self, kp):

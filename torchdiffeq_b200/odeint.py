@@ -282,8 +282,6 @@ def _cache_key(p, extra=()):
     o = p.options
     if o.get("cache", True) is False or p.callbacks or p.norm_fn is not None or p.rtol_vec is not None:
         return None
-    if o.get("graph", "auto") is False and False:
-        return None
     items = []
     for k, v in sorted(o.items()):
         if k == "process_group":
