@@ -69,28 +69,45 @@ class PeerExchange:
         self.lib = _lib.load()
         pg = None if process_group is True else process_group
         self.rank, self.world = dist.get_rank(pg), dist.get_world_size(pg)
-        if self.world > _lib.TDQ_MAX_RANKS:
-            raise _lib.TdqError("peer exchange supports at most %d ranks" % _lib.TDQ_MAX_RANKS)
-        own = C.c_void_p()
-        h = _lib.IpcHandle()
-        _lib.check(self.lib.tdq_xchg_create(C.byref(own), C.byref(h)))
-        self.own = own.value
-        handles = [None] * self.world
-        dist.all_gather_object(handles, bytes(h.bytes), group=pg)
-        self.peers, self._opened = [], []
-        for r, hb in enumerate(handles):
-            if r == self.rank:
-                self.peers.append(self.own)
-                continue
-            ph = _lib.IpcHandle()
-            C.memmove(ph.bytes, hb, 64)
-            ptr = C.c_void_p()
-            _lib.check(self.lib.tdq_xchg_open(C.byref(ph), C.byref(ptr)))
-            self.peers.append(ptr.value)
-            self._opened.append(ptr.value)
+        self.own, self.peers, self._opened = None, [], []
+        # Every step below is collective and every rank takes part in all of them, whatever happened locally,
+        # so that a failure anywhere (IPC not permitted, too many ranks) makes ALL ranks fall back together.
+        err, hbytes = None, None
+        try:
+            if self.world > _lib.TDQ_MAX_RANKS:
+                raise _lib.TdqError("peer exchange supports at most %d ranks" % _lib.TDQ_MAX_RANKS)
+            own = C.c_void_p()
+            h = _lib.IpcHandle()
+            _lib.check(self.lib.tdq_xchg_create(C.byref(own), C.byref(h)))
+            self.own = own.value
+            hbytes = bytes(h.bytes)
+        except Exception as e:
+            err = "%s: %s" % (type(e).__name__, e)
+        gathered = [None] * self.world
+        dist.all_gather_object(gathered, (err, hbytes), group=pg)
+        errs = [g[0] for g in gathered if g[0] is not None]
+        if not errs:
+            try:
+                for r, (_, hb) in enumerate(gathered):
+                    if r == self.rank:
+                        self.peers.append(self.own)
+                        continue
+                    ph = _lib.IpcHandle()
+                    C.memmove(ph.bytes, hb, 64)
+                    ptr = C.c_void_p()
+                    _lib.check(self.lib.tdq_xchg_open(C.byref(ph), C.byref(ptr)))
+                    self.peers.append(ptr.value)
+                    self._opened.append(ptr.value)
+            except Exception as e:
+                err = "%s: %s" % (type(e).__name__, e)
+            gathered = [None] * self.world
+            dist.all_gather_object(gathered, err, group=pg)       # doubles as the "everybody has mapped everybody" barrier
+            errs = [g for g in gathered if g is not None]
+        if errs:
+            self.close()
+            raise _lib.TdqError("peer exchange unavailable on at least one rank: %s" % errs[0])
         self.ptrs = _lib.ptr_array(self.peers)
         self.epoch = 0
-        dist.barrier(group=pg)                 # everybody has mapped everybody before the first use
 
     def arm(self, ctrl_ptr, stream):
         """Call after tdq_ctrl_init of every solve (solves are collective, so epochs agree)."""
