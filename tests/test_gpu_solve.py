@@ -337,3 +337,27 @@ def test_jump_t_golden(key):
     with pytest.raises(ValueError):
         tdq().odeint(f, x0, tj, method=method, options={"jump_t": torch.tensor([0.5], device=DEV),
                                                           "step_t": torch.tensor([0.5], device=DEV)})
+
+
+def test_plain_odeint_with_grad_routes_to_adjoint():
+    """gradient_tests.py style: gradients requested through plain odeint on an nn.Module are served by the
+    adjoint method (with a warning); they must agree with odeint_adjoint's."""
+    f = P.MLPField(dim=8, hidden=16, seed=0, dtype=torch.float64).to(DEV)
+    y0 = torch.randn(16, 8, generator=torch.Generator().manual_seed(1), dtype=torch.float64).to(DEV)
+    t = torch.tensor([0., 0.5, 1.], dtype=torch.float64, device=DEV)
+    grads = []
+    for api in ("odeint", "odeint_adjoint"):
+        f.zero_grad()
+        yy = y0.clone().requires_grad_(True)
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            y = getattr(tdq(), api)(f, yy, t, method="dopri5", rtol=1e-8, atol=1e-10)
+        y[-1].pow(2).sum().backward()
+        grads.append([yy.grad.clone()] + [q.grad.clone() for q in f.parameters()])
+    for a, b in zip(*grads):
+        assert torch.equal(a, b)
+    with pytest.raises(NotImplementedError):
+        yy = y0.clone().requires_grad_(True)
+        tdq().odeint(lambda t_, y_: -y_, yy, t)
+    with pytest.raises(NotImplementedError):
+        tdq().odeint_event(f, y0, t[0], event_fn=lambda t_, y_: y_[0, 0])

@@ -375,6 +375,19 @@ def _func_requires_grad(func):
     return False
 
 
+_WARNED_ADJOINT_ROUTE = False
+
+
+def odeint_event(func, y0, t0, *, event_fn, reverse_time=False, odeint_interface=None, **kwargs):
+    """odeint.py:160-194.  Event handling is outside the B200 hot path."""
+    raise NotImplementedError("odeint_event / event_fn are not implemented on the B200 path (SURVEY.md section 8(f))")
+
+
+def odeint_dense(func, y0, t0, t1, *, rtol=1e-7, atol=1e-9, method=None, options=None):
+    """odeint.py:111-157.  Dense-output closures are outside the B200 hot path."""
+    raise NotImplementedError("odeint_dense is not implemented on the B200 path (SURVEY.md section 8(f))")
+
+
 def odeint(func, y0, t, *, rtol=1e-7, atol=1e-9, method=None, options=None, event_fn=None, _stats=None):
     """Integrate dy/dt = func(t, y), y(t[0]) = y0 and return y at every t (odeint.py:49-108).
 
@@ -386,14 +399,24 @@ def odeint(func, y0, t, *, rtol=1e-7, atol=1e-9, method=None, options=None, even
     p = normalise(func, y0, t, rtol, atol, method, options, event_fn)
     if torch.is_grad_enabled():
         y_req = any(y_.requires_grad for y_ in y0) if p.is_tuple else y0.requires_grad
-        if y_req or t.requires_grad:
+        if y_req or t.requires_grad or _func_requires_grad(func):
+            # The reference backpropagates through the solver's own ops here.  That discretise-then-
+            # differentiate path is not part of the B200 hot path; for an
+            # nn.Module the adjoint method yields the same gradients up to the solver tolerance, so it is used
+            # instead (loudly).  A plain callable's parameters cannot be discovered, hence the error.
+            if isinstance(func, torch.nn.Module):
+                global _WARNED_ADJOINT_ROUTE
+                if not _WARNED_ADJOINT_ROUTE:
+                    _WARNED_ADJOINT_ROUTE = True
+                    warnings.warn("torchdiffeq_b200.odeint: gradients are computed with the adjoint method "
+                                  "(odeint_adjoint); backpropagation through the solver internals is not implemented",
+                                  stacklevel=2)
+                from .adjoint import odeint_adjoint
+                return odeint_adjoint(func, y0, t, rtol=rtol, atol=atol, method=method, options=options)
             raise NotImplementedError(
                 "backpropagation through the solver's internals is not part of the B200 hot path "
-                "(SURVEY.md section 8(f) item 4); use odeint_adjoint for gradients or call odeint under "
-                "torch.no_grad()")
-        if _func_requires_grad(func):
-            warnings.warn("torchdiffeq_b200.odeint returns a tensor without autograd history; use "
-                          "odeint_adjoint to train func's parameters", stacklevel=2)
+                "(SURVEY.md section 8(f) item 4); use odeint_adjoint(..., adjoint_params=...) for gradients or call "
+                "odeint under torch.no_grad()")
     with torch.no_grad(), on_solver_stream(p.device) as ss:
         sol, eng = _solve(p)
         ss.publish(sol)
