@@ -270,12 +270,36 @@ def clear_cache():
     _ENGINE_CACHE.clear()
 
 
+def _tensor_sig(x):
+    return (x.data_ptr(), tuple(x.shape), x.dtype, x.requires_grad)
+
+
 def _func_signature(func):
+    """Identity of everything a captured step graph bakes in about func: the object itself plus the storage
+    of every tensor it can reach without running it -- module parameters and buffers (recursively), tensor
+    attributes of the object, tensors in a plain function's closure cells.  Rebinding any of them to a new
+    tensor changes the key, so a stale graph is never replayed for them."""
+    sig = [id(func)]
     if isinstance(func, torch.nn.Module):
-        ps = tuple((q.data_ptr(), tuple(q.shape), q.dtype, q.requires_grad) for q in func.parameters())
-        bs = tuple((b.data_ptr(), tuple(b.shape), b.dtype) for b in func.buffers())
-        return (id(func), func.training, ps, bs)
-    return (id(func),)
+        sig.append(func.training)
+        sig.extend(_tensor_sig(q) for q in func.parameters())
+        sig.extend(_tensor_sig(b) for b in func.buffers())
+        for m in func.modules():
+            sig.extend((k,) + _tensor_sig(v) for k, v in vars(m).items() if isinstance(v, torch.Tensor))
+    else:
+        owner = getattr(func, "__self__", func)
+        if hasattr(owner, "__dict__"):
+            sig.extend((k,) + _tensor_sig(v) for k, v in vars(owner).items() if isinstance(v, torch.Tensor))
+        for cell in getattr(func, "__closure__", None) or ():
+            try:
+                v = cell.cell_contents
+            except ValueError:
+                continue
+            if isinstance(v, torch.Tensor):
+                sig.append(_tensor_sig(v))
+            elif isinstance(v, torch.nn.Module):
+                sig.append(_func_signature(v))
+    return tuple(sig)
 
 
 def _cache_key(p, extra=()):
