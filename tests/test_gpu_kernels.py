@@ -209,3 +209,34 @@ def test_pack_segments(dtype):
     for s, off, l, sc in zip(srcs, offs, lens, scales):
         want = torch.zeros(l, dtype=dtype) if s is None else s * sc
         assert torch.equal(got[off:off + l], want)
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.float64])
+def test_interp_eval_at_bitwise(dtype):
+    """tdq_interp_eval_at: the interpolant at an arbitrary time (interp.py:25-48), as event handling would use it."""
+    n, dt, t0 = 1027, 0.25, 1.0
+    eng, _lib, _stream = _engine("dopri5", dtype, n, dt, t0)
+    coeffs = [_rand(n, dtype, 40 + i) for i in range(5)]
+    for dst, src in zip(eng.coeff, coeffs):
+        dst.copy_(src)
+    # make [t0, t1] the current interval: one accepted attempt with zero error
+    zeros = [torch.zeros(n, dtype=dtype, device="cuda") for _ in range(7)]
+    y0d = torch.ones(n, dtype=dtype, device="cuda")
+    kp = _lib.ptr_array([z.data_ptr() for z in zeros])
+    _lib.check(eng.lib.tdq_error_norm(eng.ctrl.data_ptr(), C.byref(eng.tab), eng.dt_code, y0d.data_ptr(), y0d.data_ptr(),
+                                      kp, None, None, eng.seg_off, eng.seg_len, 1, n, eng.partials.data_ptr(),
+                                      eng.norm_out.data_ptr(), None, _stream()))
+    _lib.check(eng.lib.tdq_controller(eng.ctrl.data_ptr(), eng.dt_code, eng.norm_out.data_ptr(),
+                                      eng.seg_counts.data_ptr(), 1, None, _stream()))
+    torch.cuda.synchronize()
+    mb = eng.mbox_host.contents
+    assert mb.accept == 1 and mb.t0 == t0 and mb.t1 == t0 + dt
+    assert mb.dt == dt * 10.0                                     # ratio == 0 -> dt * ifactor (misc.py:87-88)
+    out = torch.empty(n, dtype=dtype, device="cuda")
+    for tq in (t0, t0 + 0.3 * dt, t0 + dt):
+        tdev = torch.tensor(tq, dtype=torch.float64, device="cuda")
+        _lib.check(eng.lib.tdq_interp_eval_at(eng.ctrl.data_ptr(), eng.dt_code, eng.coeff_ptrs, tdev.data_ptr(),
+                                              out.data_ptr(), n, _stream()))
+        want = O.interp_eval(coeffs, torch.tensor(t0, dtype=torch.float64), torch.tensor(t0 + dt, dtype=torch.float64),
+                             torch.tensor(tq, dtype=torch.float64))
+        assert torch.equal(out.cpu(), want)

@@ -1,0 +1,123 @@
+"""CPU tests of the host-side logic that needs no GPU: state layout, tolerance vectors, the fixed-grid
+step tables (checked against the reference's loop semantics, solvers.py:102-128), the engine-cache key."""
+import pytest
+import torch
+
+from torchdiffeq_b200._engine import Layout
+from torchdiffeq_b200._fixed import FixedGridEngine, grid_from_step_size
+from torchdiffeq_b200.odeint import _func_signature, _tol_vector
+
+
+def test_layout_alignment_and_views():
+    lay = Layout([(5, 6), (3,), (), (2, 2)], torch.float32)
+    assert all(o % 4 == 0 for o in lay.offsets)                   # 16-byte aligned float32 pieces
+    assert lay.lens == [30, 3, 1, 4] and lay.n == 32 + 4 + 4 + 4
+    parts = [torch.arange(30.).view(5, 6), torch.tensor([1., 2., 3.]), torch.tensor(7.), torch.ones(2, 2)]
+    flat = lay.flatten(parts)
+    back = lay.views(flat)
+    for a, b in zip(parts, back):
+        assert torch.equal(a, b)
+    pad = torch.ones(lay.n, dtype=torch.bool)
+    for o, l in zip(lay.offsets, lay.lens):
+        pad[o:o + l] = False
+    assert (flat[pad] == 0).all()                                  # padding is zero
+    sol = flat.repeat(3, 1)
+    assert lay.views(sol, (3,))[0].shape == (3, 5, 6)              # misc.py:126-134 with a leading time dimension
+    lay64 = Layout([(3,), (3,)], torch.float64)
+    assert lay64.offsets == [0, 4]                                 # 16 bytes = 2 doubles
+
+
+def test_tol_vector():
+    lay = Layout([(2, 3), (3,)], torch.float64)
+    s, v = _tol_vector("rtol", 1e-6, lay, None, torch.device("cpu"))
+    assert s == 1e-6 and v is None
+    s, v = _tol_vector("rtol", (1e-6, 1e-4), lay, None, torch.device("cpu"))
+    assert s is None and v.dtype == torch.float64 and v.numel() == lay.n
+    # the reference builds these through float32 (torch.as_tensor of a Python float), misc.py:122
+    assert v[0] == float(torch.tensor(1e-6)) and v[lay.offsets[1]] == float(torch.tensor(1e-4))
+    with pytest.raises(AssertionError):
+        _tol_vector("rtol", (1e-6,), lay, None, torch.device("cpu"))
+    s, v = _tol_vector("atol", torch.tensor([1e-3, 1e-6]), None, (4, 2), torch.device("cpu"))
+    assert v.shape == (8,) and v[1] == float(torch.tensor(1e-6))   # float32 tensor -> float64, like rk_common.py:186
+
+
+def _reference_fixed_loop(grid, t):
+    """solvers.py:108-126 as written: which output index is produced in which step, and how."""
+    recs, j = [], 1
+    for s, (t0, t1) in enumerate(zip(grid[:-1], grid[1:])):
+        while j < len(t) and t1 >= t[j]:
+            if t[j] == t0:
+                recs.append((s, j, 0, 0.0))
+            elif t[j] == t1:
+                recs.append((s, j, 1, 0.0))
+            else:
+                recs.append((s, j, 2, float((t[j] - t0) / (t1 - t0))))
+            j += 1
+    return recs
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.float64])
+@pytest.mark.parametrize("case", ["grid_is_t", "step_size", "coarse_t"])
+def test_fixed_grid_tables(case, dtype):
+    if case == "grid_is_t":
+        t = torch.linspace(0., 25., 50, dtype=dtype)
+        grid = t
+    elif case == "step_size":
+        t = torch.linspace(0., 5., 7, dtype=dtype)
+        grid = grid_from_step_size(0.03)(None, None, t)
+    else:
+        t = torch.tensor([0., 0.3, 0.31, 2.0], dtype=dtype)
+        grid = torch.linspace(0., 2., 5, dtype=dtype)
+    eng = FixedGridEngine.__new__(FixedGridEngine)
+    eng.dtype, eng.perturb, eng.t_sign, eng.method = torch.float32, False, 1.0, "rk4"
+    ts, dtT, rec_begin, out_idx, mode, slope, n_steps = eng._tabulate(grid, t)
+    want = _reference_fixed_loop(grid, t)
+    got = []
+    for s in range(n_steps):
+        for r in range(int(rec_begin[s]), int(rec_begin[s + 1])):
+            got.append((s, int(out_idx[r]), int(mode[r]), float(slope[r]) if int(mode[r]) == 2 else 0.0))
+    assert [g[:3] for g in got] == [w[:3] for w in want]
+    for g, w in zip(got, want):
+        assert g[3] == pytest.approx(float(torch.tensor(w[3], dtype=dtype).to(torch.float32)), abs=0)
+    assert torch.equal(dtT, (grid[1:] - grid[:-1]).to(torch.float32))
+    assert torch.equal(ts[:, 0], grid[:-1].to(torch.float32)) and torch.equal(ts[:, 3], grid[1:].to(torch.float32))
+    # perturb: first time moved up one ulp, last time down (misc.py:188-193)
+    eng.perturb = True
+    tsp = eng._tabulate(grid, t)[0]
+    assert (tsp[:, 0] > ts[:, 0]).all() and (tsp[:, 3] < ts[:, 3]).all()
+    # reverse time: sign folded into the func times and into dt
+    eng.perturb, eng.t_sign = False, -1.0
+    tsr, dtr = eng._tabulate(grid, t)[:2]
+    assert torch.equal(tsr, -ts) and torch.equal(dtr, -dtT)
+
+
+def test_cache_signature_tracks_reachable_tensors():
+    def make():
+        A = torch.randn(3, 3)
+        return (lambda t, y: y @ A), A
+    f, _ = make()
+    g, _ = make()
+    assert _func_signature(f) == _func_signature(f) and _func_signature(f) != _func_signature(g)
+
+    class M(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.lin = torch.nn.Linear(2, 2)
+            self.c = torch.ones(2)
+
+        def forward(self, t, y):
+            return self.lin(y) * self.c
+    m = M()
+    k = _func_signature(m)
+    m.c = torch.ones(2)                      # plain tensor attribute rebound
+    assert _func_signature(m) != k
+    k = _func_signature(m)
+    m.eval()
+    assert _func_signature(m) != k
+    k = _func_signature(m)
+    with torch.no_grad():
+        m.lin.weight.add_(1.0)               # in-place update keeps the storage: same key
+    assert _func_signature(m) == k
+    m.lin.weight = torch.nn.Parameter(torch.zeros(2, 2))
+    assert _func_signature(m) != k
+    hash(_func_signature(m))
