@@ -3,6 +3,7 @@ C ABI) against (a) the CPU oracle on the same seeded inputs and (b) the committe
 produced by the unmodified reference.  Tolerances are the north_star's: 1e-4/1e-6 float32,
 1e-5/1e-7 float64 (rtol/atol) on solutions, 1e-4 relative on adjoint gradients; the reference's own
 acceptance thresholds against exact solutions (tests/odeint_tests.py:45-58) are asserted as well."""
+import math
 import os
 import warnings
 
@@ -361,3 +362,92 @@ def test_plain_odeint_with_grad_routes_to_adjoint():
         tdq().odeint(lambda t_, y_: -y_, yy, t)
     with pytest.raises(NotImplementedError):
         tdq().odeint_event(f, y0, t[0], event_fn=lambda t_, y_: y_[0, 0])
+
+
+def test_adjoint_time_gradients_analytic():
+    """gradient_tests.py:25-32 checks d/dt through odeint_adjoint; here against the closed form of y' = a*y:
+    L = sum(y(t1)) => dL/dt1 = a*L, dL/dt0 = -a*L, dL/dy0 = exp(a*(t1-t0)), dL/da = (t1-t0)*L."""
+    class Lin(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.a = torch.nn.Parameter(torch.tensor(-0.7, dtype=torch.float64))
+
+        def forward(self, t, y):
+            return self.a * y
+    f = Lin().to(DEV)
+    y0 = torch.tensor([1.0, 2.0, -0.5], dtype=torch.float64, device=DEV, requires_grad=True)
+    t = torch.tensor([0.2, 1.5], dtype=torch.float64, device=DEV, requires_grad=True)
+    for mode in ("lockstep", "graph"):
+        f.zero_grad()
+        y0.grad = t.grad = None
+        y = tdq().odeint_adjoint(f, y0, t, method="dopri5", rtol=1e-10, atol=1e-12, options=dict(MODES[mode]))
+        L = y[-1].sum()
+        L.backward()
+        a, span = float(f.a), 1.3
+        Lv = float(L)
+        assert abs(Lv - float(y0.detach().sum()) * math.exp(a * span)) < 1e-8
+        assert abs(float(t.grad[1]) - a * Lv) < 1e-7 and abs(float(t.grad[0]) + a * Lv) < 1e-7
+        assert torch.allclose(y0.grad, torch.full_like(y0, math.exp(a * span)), rtol=1e-8, atol=0)
+        assert abs(float(f.a.grad) - span * Lv) < 1e-7
+
+
+def test_adjoint_tuple_state_matches_tensor_state():
+    """api_tests.py:12-39 style: a tuple state (a, b) and the same system written on one tensor give the same
+    solution and the same gradients."""
+    A = P.skew_matrix(6, torch.float64).to(DEV)
+
+    class Tup(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.w = torch.nn.Parameter(torch.tensor(0.3, dtype=torch.float64))
+
+        def forward(self, t, state):
+            a, b = state
+            return (a @ A.t() * self.w, -0.5 * b + a[:, :3].sum(0))
+
+    class Flat(torch.nn.Module):
+        def __init__(self, tup):
+            super().__init__()
+            self.tup = tup
+
+        def forward(self, t, y):
+            da, db = self.tup(t, (y[:30].view(5, 6), y[30:]))
+            return torch.cat([da.reshape(-1), db])
+    g = torch.Generator().manual_seed(3)
+    ya = torch.randn(5, 6, generator=g, dtype=torch.float64).to(DEV)
+    yb = torch.randn(3, generator=g, dtype=torch.float64).to(DEV)
+    t = torch.linspace(0, 1.5, 4, dtype=torch.float64, device=DEV)
+    tup = Tup().to(DEV)
+    a1, b1 = ya.clone().requires_grad_(True), yb.clone().requires_grad_(True)
+    sa, sb = tdq().odeint_adjoint(tup, (a1, b1), t, method="dopri5", rtol=1e-9, atol=1e-11)
+    (sa[-1].pow(2).sum() + sb[2].sum()).backward()
+    gw_t = tup.w.grad.clone()
+    tup.zero_grad()
+    yf = torch.cat([ya.reshape(-1), yb]).requires_grad_(True)
+    sf = tdq().odeint_adjoint(Flat(tup), yf, t, method="dopri5", rtol=1e-9, atol=1e-11)
+    (sf[-1][:30].pow(2).sum() + sf[2][30:].sum()).backward()
+    assert torch.allclose(sa.reshape(4, -1), sf[:, :30], rtol=1e-7, atol=1e-9)
+    assert torch.allclose(sb, sf[:, 30:], rtol=1e-7, atol=1e-9)
+    assert torch.allclose(a1.grad.reshape(-1), yf.grad[:30], rtol=1e-6, atol=1e-8)
+    assert torch.allclose(b1.grad, yf.grad[30:], rtol=1e-6, atol=1e-8)
+    assert torch.allclose(gw_t, tup.w.grad, rtol=1e-6, atol=1e-8)
+
+
+def test_custom_norm_callable():
+    """norm_tests.py: a user norm (here the max norm) replaces the RMS norm in the step control; the CUDA path
+    materialises err/tol for it.  Checked against the oracle driven by the same norm."""
+    f = P.BatchedLinear(16, torch.float64)
+    y0 = torch.randn(8, 16, generator=torch.Generator().manual_seed(1), dtype=torch.float64)
+    t = torch.linspace(0., 2., 4, dtype=torch.float64)
+    linf = lambda x: x.abs().max()
+    rec = {}
+    co = O.Counter(f)
+    with torch.no_grad():
+        want = O.odeint_adaptive(co, y0, t, "dopri5", rtol=1e-6, atol=1e-8, norm=linf, record=rec)
+        st = {}
+        got = tdq().odeint(f.to(DEV), y0.to(DEV), t.to(DEV), method="dopri5", rtol=1e-6, atol=1e-8,
+                           options={"norm": linf, "run_ahead": 0, "graph": False}, _stats=st)
+        got_g = tdq().odeint(f, y0.to(DEV), t.to(DEV), method="dopri5", rtol=1e-6, atol=1e-8, options={"norm": linf})
+    assert torch.allclose(got.cpu(), want, rtol=1e-9, atol=1e-11)
+    assert (st["n_accept"], st["n_reject"]) == (rec["n_accept"], rec["n_reject"])
+    assert torch.allclose(got_g, got, rtol=1e-12, atol=0)
