@@ -120,8 +120,7 @@ __device__ void write_mailbox(TdqCtrl &c, double fin_t0, double fin_dt, int jump
     m->next_dt = c.att_dt;
     m->on_jump_t = jumped;
     __threadfence_system();
-    m->seq = c.seq;
-    __threadfence_system();
+    m->seq = c.seq;                  // kernel completion flushes this last store; no second fence needed
 }
 
 // rk_common.py:323-361 + misc.py:85-95, then the next attempt's constants.
