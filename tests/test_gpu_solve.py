@@ -451,3 +451,102 @@ def test_custom_norm_callable():
     assert torch.allclose(got.cpu(), want, rtol=1e-9, atol=1e-11)
     assert (st["n_accept"], st["n_reject"]) == (rec["n_accept"], rec["n_reject"])
     assert torch.allclose(got_g, got, rtol=1e-12, atol=0)
+
+
+@pytest.mark.parametrize("adjoint", [False, True])
+def test_grid_constructor(adjoint):
+    """TestGridConstructor (odeint_tests.py:210-248): a user grid for the forward solve and, flipped, for the
+    adjoint pass; Euler on x' = x with 10 steps gives x0 * 1.1**10 and d x1 / d x0 = 1.1**10 exactly."""
+    def f(t, x):
+        return x
+    x0 = torch.tensor(1., device=DEV, requires_grad=True)
+    t = torch.tensor([0., 1.], device=DEV)
+    seen = []
+
+    def grid_constructor(f_, y0_, t_):
+        assert t_.shape == (2,)
+        seen.append((float(t_[0]), float(t_[1])))
+        if len(seen) == 1:
+            return torch.linspace(0, 1, 11)
+        return torch.linspace(1, 0, 11)                   # adjoint pass: decreasing times
+    if adjoint:
+        xs = tdq().odeint_adjoint(f, x0, t, method="euler", options=dict(grid_constructor=grid_constructor),
+                                  adjoint_params=())
+    else:
+        with torch.no_grad():
+            xs = tdq().odeint(f, x0, t, method="euler", options=dict(grid_constructor=grid_constructor))
+    assert (xs[1] - 1.1 ** 10).abs().max() < 1e-6
+    assert seen[0] == (0.0, 1.0)
+    if adjoint:
+        xs[1].backward()
+        assert seen[1] == (1.0, 0.0)
+        assert (x0.grad - 1.1 ** 10).abs().max() < 1e-6
+
+
+@pytest.mark.parametrize("method", ["euler", "midpoint", "rk4", "dopri5", "bosh3"])
+def test_callback_steps_forward_and_adjoint(method):
+    """TestCallbacks.test_steps (odeint_tests.py:310-386): callback counts of the forward and the adjoint pass."""
+    class NeuralF(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            torch.manual_seed(0)
+            self.linears = torch.nn.Sequential(torch.nn.Linear(2, 10), torch.nn.Tanh(), torch.nn.Linear(10, 2),
+                                               torch.nn.Tanh())
+            self.n = {k: 0 for k in ("step", "accept", "reject", "step_adj", "accept_adj", "reject_adj")}
+
+        def forward(self, t, x):
+            return self.linears(x)
+
+        def callback_step(self, t0, y0, dt):
+            self.n["step"] += 1
+
+        def callback_accept_step(self, t0, y0, dt):
+            self.n["accept"] += 1
+
+        def callback_reject_step(self, t0, y0, dt):
+            self.n["reject"] += 1
+
+        def callback_step_adjoint(self, t0, y0, dt):
+            self.n["step_adj"] += 1
+            assert isinstance(y0, tuple) and y0[1].shape == (2,)     # (vjp_t, y, adj_y, *adj_params)
+
+        def callback_accept_step_adjoint(self, t0, y0, dt):
+            self.n["accept_adj"] += 1
+
+        def callback_reject_step_adjoint(self, t0, y0, dt):
+            self.n["reject_adj"] += 1
+    fixed = method in ("euler", "midpoint", "rk4")
+    f = NeuralF().to(DEV)
+    x0 = torch.tensor([1.0, 2.0], device=DEV, requires_grad=True)
+    t = torch.tensor([0., 1.0], device=DEV)
+    kwargs = dict(options=dict(step_size=0.1)) if fixed else {}
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")               # fixed solvers warn about accept/reject callbacks (misc.py:341-343)
+        xs = tdq().odeint_adjoint(f, x0, t, method=method, **kwargs)
+        if fixed:
+            assert f.n["step"] == 10 and f.n["accept"] == 0
+        else:
+            assert f.n["step"] > 0 and f.n["accept"] + f.n["reject"] == f.n["step"]
+        xs.sum().backward()
+    if fixed:
+        assert f.n["step_adj"] == 10
+    else:
+        assert f.n["step_adj"] > 0 and f.n["accept_adj"] + f.n["reject_adj"] == f.n["step_adj"]
+    assert torch.isfinite(x0.grad).all()
+
+
+def test_seminorm_needs_no_more_evaluations():
+    """norm_tests.py:272-306: the adjoint seminorm ignores the parameter block in the step control, so the
+    backward pass needs at most as many evaluations as with the default norm."""
+    nfe = {}
+    for name, ao in (("default", {}), ("seminorm", {"norm": "seminorm"})):
+        f = P.MLPField(dim=8, hidden=16, seed=0, dtype=torch.float64).to(DEV)
+        cf = Counted(f)
+        y0 = torch.randn(32, 8, generator=torch.Generator().manual_seed(1), dtype=torch.float64).to(DEV).requires_grad_(True)
+        t = torch.tensor([0., 1.], dtype=torch.float64, device=DEV)
+        y = tdq().odeint_adjoint(cf, y0, t, method="dopri5", rtol=1e-6, atol=1e-8,
+                                 options={"run_ahead": 0, "graph": False}, adjoint_options=dict(ao, run_ahead=0, graph=False))
+        cf.nfe = 0
+        y[-1].pow(2).mean().backward()
+        nfe[name] = cf.nfe
+    assert 0 < nfe["seminorm"] <= nfe["default"]

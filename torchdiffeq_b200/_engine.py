@@ -115,6 +115,35 @@ class Layout:
         return tuple(flat[..., o:o + l].view((*lead, *s)) for o, l, s in zip(self.offsets, self.lens, self.shapes))
 
 
+def pack_pieces(lib, dt_code, dtype, buf, f, pieces):
+    """Write the pieces func returned (a tuple; None = zeros) into the flat buffer `buf` at their offsets with
+    their scales: one tdq_pack_segments launch per 64 pieces (misc.py:145 torch.cat, misc.py:165 the reverse-
+    time factor, adjoint.py:96 the unary minus).  Returns the number of launches."""
+    offs, lens, scales = pieces
+    srcs, keep = [], []
+    for p_, l in zip(f, lens):
+        if p_ is None:
+            srcs.append(None)
+            continue
+        if p_.dtype != dtype:
+            p_ = p_.to(dtype)
+        p_ = p_.reshape(-1)
+        if not p_.is_contiguous():
+            p_ = p_.contiguous()
+        if p_.numel() != l:
+            raise ValueError("func returned a piece of %d elements, expected %d" % (p_.numel(), l))
+        keep.append(p_)
+        srcs.append(p_.data_ptr())
+    n_launch = 0
+    for lo in range(0, len(srcs), _lib.TDQ_MAX_SEGS):
+        hi = min(lo + _lib.TDQ_MAX_SEGS, len(srcs))
+        _lib.check(lib.tdq_pack_segments(
+            dt_code, buf.data_ptr(), _lib.ptr_array(srcs[lo:hi]), _lib.i64_array(offs[lo:hi]),
+            _lib.i64_array(lens[lo:hi]), _lib.dbl_array(scales[lo:hi]), hi - lo, _stream()))
+        n_launch += 1
+    return n_launch
+
+
 class AdaptiveEngine:
     """One adaptive explicit-RK solve on a flat state vector, all state on the device.
 
@@ -246,30 +275,9 @@ class AdaptiveEngine:
                 buf.copy_(f)
                 f = buf
             return f
-        # tuple of pieces -> one pack launch into an engine-owned slot (misc.py:145 torch.cat,
-        # misc.py:165 mul, adjoint.py:96 unary minus folded into `scales`)
-        offs, lens, scales = self.pieces
+        # tuple of pieces -> one pack launch into an engine-owned slot
         buf = self._slot(slot)
-        srcs = []
-        keep = []
-        for p, l in zip(f, lens):
-            if p is None:
-                srcs.append(None)
-                continue
-            if p.dtype != self.dtype:
-                p = p.to(self.dtype)
-            p = p.reshape(-1)
-            if not p.is_contiguous():
-                p = p.contiguous()
-            if p.numel() != l:
-                raise ValueError("func returned a piece of %d elements, expected %d" % (p.numel(), l))
-            keep.append(p)
-            srcs.append(p.data_ptr())
-        for lo in range(0, len(srcs), _lib.TDQ_MAX_SEGS):
-            hi = min(lo + _lib.TDQ_MAX_SEGS, len(srcs))
-            self._launch(self.lib.tdq_pack_segments(
-                self.dt_code, buf.data_ptr(), _lib.ptr_array(srcs[lo:hi]), _lib.i64_array(offs[lo:hi]),
-                _lib.i64_array(lens[lo:hi]), _lib.dbl_array(scales[lo:hi]), hi - lo, _stream()))
+        self.launches += pack_pieces(self.lib, self.dt_code, self.dtype, buf, f, self.pieces)
         return buf
 
     def _launch(self, rc):

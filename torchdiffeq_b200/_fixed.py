@@ -8,7 +8,7 @@ grid interval, indexed by a device step counter."""
 import torch
 
 from . import _lib
-from ._engine import _DTYPES, _stream, solver_stream
+from ._engine import _DTYPES, _stream, pack_pieces, solver_stream
 
 _ONE_THIRD = 1 / 3      # rk_common.py:94-96
 _TWO_THIRDS = 2 / 3
@@ -33,7 +33,7 @@ class FixedGridEngine:
     """Explicit fixed-step methods of fixed_grid.py:6-60 on one captured step graph."""
 
     def __init__(self, fn, n, dtype, device, *, method="rk4", t_sign=1.0, perturb=False, graph="auto",
-                 callbacks=None):
+                 callbacks=None, pieces=None):
         if method not in FIXED_METHODS:
             raise ValueError("unknown fixed-grid method %r" % method)
         self.method = method
@@ -48,6 +48,7 @@ class FixedGridEngine:
         self.perturb = bool(perturb)
         self.callbacks = callbacks or {}
         self.graph_opt = False if self.callbacks else graph
+        self.pieces = pieces            # fn returns a tuple of pieces (tuple states, the adjoint's augmented state)
         self.nfe = 0
         self.launches = 0
 
@@ -55,6 +56,9 @@ class FixedGridEngine:
     def _tabulate(self, grid, t):
         """grid, t: ascending CPU tensors of t's dtype.  Returns per-step and per-output tables."""
         T = self.dtype
+        if grid.dtype != t.dtype:                  # a grid_constructor may return another float dtype: compare in
+            common = torch.promote_types(grid.dtype, t.dtype)      # the promoted one, like the reference's mixed ops
+            t = t.to(common)
         t0, t1 = grid[:-1], grid[1:]
         dt = t1 - t0                                                   # solvers.py:112
         # func times of the four evaluations, then _PerturbFunc's cast to the state dtype (misc.py:187)
@@ -79,7 +83,7 @@ class FixedGridEngine:
         dtT = dt.to(T) * self.t_sign           # sign of _ReverseFunc folded into dt (exact)
         # outputs: step s emits every t[j] with t1_s >= t[j] not emitted before (solvers.py:117)
         n_steps = grid.numel() - 1
-        step_of = torch.searchsorted(t1.contiguous(), t[1:].contiguous(), right=False)
+        step_of = torch.searchsorted(t1.to(t.dtype).contiguous(), t[1:].contiguous(), right=False)
         if step_of.numel() and int(step_of.max()) >= n_steps:
             raise AssertionError("output time beyond the end of the grid")
         g0, g1, tj = t0[step_of], t1[step_of], t[1:]
@@ -97,6 +101,10 @@ class FixedGridEngine:
     def _call_fn(self, t, y, own):
         self.nfe += 1
         f = self.fn(t, y)
+        if not isinstance(f, torch.Tensor):
+            buf = torch.zeros(self.n, dtype=self.dtype, device=self.device)
+            self.launches += pack_pieces(self.lib, self.dc, self.dtype, buf, f, self.pieces)
+            return buf
         if f.dtype != self.dtype:
             f = f.to(self.dtype)
         f = f.reshape(-1)

@@ -21,8 +21,10 @@ import torch.nn as nn
 
 from . import _lib
 from ._engine import Layout, on_solver_stream
-from .odeint import (ADAPTIVE_METHODS, _ADJOINT_CALLBACK_NAMES, _CALLBACK_NAMES, _cache_get, _cache_key, _cache_put,
-                     _make_adaptive_engine, _mixed_norm, _rms_norm, _solve, _unflatten, normalise, Problem)
+from ._fixed import FixedGridEngine
+from .odeint import (ADAPTIVE_METHODS, FIXED_METHODS, _ADJOINT_CALLBACK_NAMES, _CALLBACK_NAMES, _cache_get, _cache_key,
+                     _cache_put, _make_adaptive_engine, _mixed_norm, _rms_norm, _solve, _unflatten, fixed_grid,
+                     normalise, Problem)
 
 
 def find_parameters(module):
@@ -156,6 +158,20 @@ class _BackwardSolver:
         bp = Problem()                       # the backward problem as the engine factory sees it
         bp.t_sign, bp.device, bp.dtype, bp.n, bp.fn = self.bsign, dev, T, lay.n, aug_fn
         bp.t_cpu = (p.t_cpu.to(torch.float64) * fwd_sign * self.bsign).flip(0)
+        self.fixed = adjoint_method in FIXED_METHODS
+        if self.fixed:
+            # fixed-grid backward (adjoint.py:134-138 with a FixedGridODESolver): the same step kernels; the grid of
+            # every interval comes from adjoint_options (step_size / grid_constructor), solvers.py:85-104
+            self.fixed_opts = {k: v for k, v in opts.items() if k not in ("graph", "run_ahead", "cache", "exchange",
+                                                                           "process_group")}
+            self.aug_fn = aug_fn
+            valid = {k: v for k, v in callbacks.items() if k == "callback_step"}
+            if set(callbacks) - set(valid):
+                warnings.warn("Solver '{}' does not support callbacks {}".format(adjoint_method, set(callbacks) - set(valid)))
+            # never capture inside autograd's backward (see AdaptiveEngine.prime): eager launches
+            self.eng = FixedGridEngine(aug_fn, lay.n, T, dev, method=adjoint_method, t_sign=self.bsign,
+                                       perturb=opts.get("perturb", False), graph=False, callbacks=valid, pieces=pieces)
+            return
         rtol_s, rtol_v = _adj_tol(adjoint_rtol, lay, dev)
         atol_s, atol_v = _adj_tol(adjoint_atol, lay, dev)
         if (rtol_v is None) != (atol_v is None):
@@ -171,6 +187,8 @@ class _BackwardSolver:
 
     def prime(self, t, y_last):
         """Capture the backward step graph now (forward call, main thread) on stand-in data."""
+        if self.fixed:
+            return False
         lay, n = self.lay, self.p.n
         aug = torch.zeros(lay.n, dtype=self.p.dtype, device=self.p.device)
         aug[self.o_y:self.o_y + n] = y_last
@@ -196,8 +214,17 @@ class _BackwardSolver:
                 dLd_cur_t = fe.reshape(-1).dot(grad_sol[i].reshape(-1))
                 aug[o_t] -= dLd_cur_t
                 time_vjps[i] = dLd_cur_t
-            pair = torch.stack([t64[i], t64[i - 1]]) * self.bsign        # ascending for the engine
-            sol = eng.solve(aug, pair)
+            if self.fixed:
+                pair = (t[i - 1:i + 1].detach().flip(0) * self.bsign).to("cpu")      # ascending engine time, t's own dtype
+                opts = dict(self.fixed_opts)
+                if "grid_constructor" in opts:                       # the user sees the true times (misc.py:283-289)
+                    gc, sgn = opts["grid_constructor"], self.bsign
+                    opts["grid_constructor"] = lambda f_, y_, t_: sgn * gc(f_, y_, sgn * t_)
+                grid = fixed_grid(eng.method, opts, self.aug_fn, aug, pair)
+                sol = eng.solve(aug, grid, pair)
+            else:
+                pair = torch.stack([t64[i], t64[i - 1]]) * self.bsign    # ascending for the engine
+                sol = eng.solve(aug, pair)
             aug.copy_(sol[1])
             aug[o_y:o_y + n] = y[i - 1]                               # adjoint.py:140
             aug[o_a:o_a + n] += grad_sol[i - 1]                       # adjoint.py:141
@@ -324,9 +351,9 @@ def odeint_adjoint(func, y0, t, *, rtol=1e-7, atol=1e-9, method=None, options=No
     p = normalise(func, y0, t, rtol, atol, method, options, event_fn)
     if adjoint_method is None:
         adjoint_method = 'dopri5'
-    if adjoint_method not in ADAPTIVE_METHODS:
-        raise NotImplementedError('adjoint_method "{}" is not implemented on the B200 path; adaptive methods: {}'
-                                  .format(adjoint_method, ADAPTIVE_METHODS))
+    if adjoint_method not in ADAPTIVE_METHODS + FIXED_METHODS:
+        raise NotImplementedError('adjoint_method "{}" is not implemented on the B200 path; implemented: {}'
+                                  .format(adjoint_method, ADAPTIVE_METHODS + FIXED_METHODS))
     if p.is_tuple:
         y0_flat = p.layout.flatten(list(y0))          # differentiable wrt every piece (copy_ into zeros)
     else:

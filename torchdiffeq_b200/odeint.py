@@ -357,8 +357,22 @@ def _solve(p):
         return sol, eng
     # fixed grid: euler / midpoint / heun2 / heun3 / rk4 (solvers.py:55-128, fixed_grid.py:6-60)
     o = p.options
-    _warn_unused({"euler": "Euler", "midpoint": "Midpoint", "heun2": "Heun2", "heun3": "Heun3", "rk4": "RK4"}[p.method],
-                 o, _FIXED_OPTIONS)
+    y0_view = p.layout.views(p.y0_flat) if p.is_tuple else p.y0_flat.view(p.shape)
+    grid = fixed_grid(p.method, o, p.original_func, y0_view, p.t_cpu)
+    eng = FixedGridEngine(p.fn, p.n, p.dtype, p.device, method=p.method, t_sign=p.t_sign,
+                          perturb=o.get("perturb", False), graph=o.get("graph", "auto"), callbacks=p.callbacks,
+                          pieces=p.pieces)
+    sol = eng.solve(p.y0_flat, grid, p.t_cpu)
+    return sol, eng
+
+
+_FIXED_NAMES = {"euler": "Euler", "midpoint": "Midpoint", "heun2": "Heun2", "heun3": "Heun3", "rk4": "RK4"}
+
+
+def fixed_grid(method, o, func, y0_view, t_cpu):
+    """Option handling and time grid of FixedGridODESolver (solvers.py:55-79, :85-96, :103-104) for an
+    ascending CPU `t_cpu`; the caller has already wrapped a user grid_constructor for reversed time."""
+    _warn_unused(_FIXED_NAMES[method], o, _FIXED_OPTIONS)
     step_size, gc = o.get("step_size"), o.get("grid_constructor")
     if step_size is None:
         grid_constructor = gc if gc is not None else (lambda f, y0, t: t)
@@ -371,20 +385,9 @@ def _solve(p):
         raise NotImplementedError("interp='cubic' is not implemented on the B200 path yet")
     if interp != "linear":
         raise ValueError(f"Unknown interpolation method {interp}")
-    y0_view = p.layout.views(p.y0_flat) if p.is_tuple else p.y0_flat.view(p.shape)
-    grid = grid_constructor(p.original_func, y0_view, p.t_cpu)
-    grid = grid.detach().to("cpu")
-    assert grid[0] == p.t_cpu[0] and grid[-1] == p.t_cpu[-1]                           # solvers.py:104
-    fn = p.fn
-    if p.is_tuple:
-        layout = p.layout
-        def fn(t_, y_flat, _f=p.fn):
-            out = torch.zeros(layout.n, dtype=p.dtype, device=p.device)
-            return layout.flatten(list(_f(t_, y_flat)), out=out)
-    eng = FixedGridEngine(fn, p.n, p.dtype, p.device, method=p.method, t_sign=p.t_sign,
-                          perturb=o.get("perturb", False), graph=o.get("graph", "auto"), callbacks=p.callbacks)
-    sol = eng.solve(p.y0_flat, grid, p.t_cpu)
-    return sol, eng
+    grid = grid_constructor(func, y0_view, t_cpu).detach().to("cpu")
+    assert grid[0] == t_cpu[0] and grid[-1] == t_cpu[-1]                               # solvers.py:104
+    return grid
 
 
 def _unflatten(p, sol):
