@@ -192,10 +192,11 @@ def interp_eval(coeffs, t0, t1, t):
 # ------------------------------------------------------------------------------------------------
 def odeint_adaptive(func, y0, t, method="dopri5", rtol=1e-7, atol=1e-9, norm=rms, min_step=0.,
                     max_step=float("inf"), first_step=None, step_t=None, jump_t=None, safety=0.9, ifactor=10.0,
-                    dfactor=0.2, max_num_steps=2 ** 31 - 1, record=None):
+                    dfactor=0.2, max_num_steps=2 ** 31 - 1, record=None, event_fn=None):
     """solvers.py:28-35 + rk_common.py:213-361 for a flat or shaped tensor state and ascending or
     descending t.  Returns solution [len(t), *y0.shape].  `record`, if a dict, receives
-    n_accept, n_reject, dts (attempted step sizes), accepted (flags)."""
+    n_accept, n_reject, dts (attempted step sizes), accepted (flags).  With event_fn(t, y) (scalar valued) only
+    t[0] and the direction of t matter and the result is (event_t, [y0, y(event_t)])."""
     f64 = torch.float64
     tab = tableau(method)
     ct = _cast_tableau(tab, y0.dtype)
@@ -234,61 +235,93 @@ def odeint_adaptive(func, y0, t, method="dopri5", rtol=1e-7, atol=1e-9, norm=rms
     import bisect
     next_step = min(bisect.bisect(step_t.tolist(), t[0]), len(step_t) - 1)   # :240
     next_jump = min(bisect.bisect(jump_t.tolist(), t[0]), len(jump_t) - 1)   # :241
-    y, f, t_lo, t_hi = y0, f0, t[0], t[0]
-    coeffs = [y0] * 5
+    st = {"y": y0, "f": f0, "t_lo": t[0], "t_hi": t[0], "dt": dt, "coeffs": [y0] * 5, "next_step": next_step,
+          "next_jump": next_jump}
     stats = {"n_accept": 0, "n_reject": 0, "dts": [], "accepted": []}
+
+    def attempt():
+        """rk_common.py:266-361."""
+        dt = st["dt"]
+        if not torch.isfinite(dt):
+            dt = min_step
+        dt = dt.clamp(min_step, max_step)
+        y, f = st["y"], st["f"]
+        a0 = st["t_hi"]
+        a1 = a0 + dt
+        assert a0 + dt > a0, 'underflow in dt {}'.format(dt.item())
+        assert torch.isfinite(y).all(), 'non-finite values in state `y`: {}'.format(y)
+        on_step_t = False
+        if len(step_t):
+            nxt = step_t[st["next_step"]]
+            on_step_t = bool(a0 < nxt < a0 + dt)
+            if on_step_t:
+                a1 = nxt
+                dt = a1 - a0
+        on_jump_t = False
+        if len(jump_t):                                             # :302-308
+            nxt = jump_t[st["next_jump"]]
+            on_jump_t = bool(a0 < nxt < a0 + dt)
+            if on_jump_t:
+                on_step_t = False
+                a1 = nxt
+                dt = a1 - a0
+        y1, f1, err, ks = rk_attempt(func, y, f, a0, dt, a1, ct)
+        ratio = error_ratio(err, rtol, atol, y, y1, norm)
+        accept = bool(ratio <= 1)
+        if dt > max_step:
+            accept = False
+        if dt <= min_step:
+            accept = True
+        stats["dts"].append(float(dt))
+        stats["accepted"].append(accept)
+        if accept:
+            st["coeffs"] = interp_fit(y, y1, ks, dt, ct)
+            if on_step_t and st["next_step"] != len(step_t) - 1:
+                st["next_step"] += 1
+            if on_jump_t:                                           # :346-351
+                if st["next_jump"] != len(jump_t) - 1:
+                    st["next_jump"] += 1
+                f1 = func(_next(a1.to(T)), y1)
+            st["y"], st["f"], st["t_lo"], st["t_hi"] = y1, f1, a0, a1
+            stats["n_accept"] += 1
+        else:
+            st["t_lo"], st["t_hi"] = a0, a0
+            stats["n_reject"] += 1
+        st["dt"] = optimal_step(dt, ratio, safety, ifactor, dfactor, tab["order"]).clamp(min_step, max_step)
+
+    if event_fn is not None:
+        # solvers.py:41-49 + rk_common.py:252-264 + event_handling.py:5-20
+        ev = (lambda tt, yy: event_fn(-tt, yy)) if sign < 0 else event_fn    # misc.py:281-282
+        if ev(st["t_hi"], st["y"]) == 0:
+            event_t, y_ev = st["t_hi"], st["y"]
+        else:
+            n_steps = 0
+            sign0 = torch.sign(ev(st["t_hi"], st["y"]))
+            while sign0 == torch.sign(ev(st["t_hi"], st["y"])):
+                assert n_steps < max_num_steps, 'max_num_steps exceeded ({}>={})'.format(n_steps, max_num_steps)
+                attempt()
+                n_steps += 1
+            lo, hi = st["t_lo"], st["t_hi"]
+            interp = lambda tq: interp_eval(st["coeffs"], st["t_lo"], st["t_hi"], tq)
+            nitrs = torch.ceil(torch.log((hi - lo) / atol) / math.log(2.0))
+            for _ in range(int(nitrs.long())):
+                mid = (hi + lo) / 2.0
+                same = bool(sign0 == torch.sign(ev(mid, interp(mid))))
+                lo = torch.where(torch.tensor(same), mid, lo)
+                hi = torch.where(torch.tensor(same), hi, mid)
+            event_t = (lo + hi) / 2.0
+            y_ev = interp(event_t)
+        if record is not None:
+            record.update(stats)
+        return event_t * sign, torch.stack([y0, y_ev], dim=0)
+
     for i in range(1, len(t)):
         n_steps = 0
-        while t[i] > t_hi:                                          # rk_common.py:246
+        while t[i] > st["t_hi"]:                                    # rk_common.py:246
             assert n_steps < max_num_steps, 'max_num_steps exceeded ({}>={})'.format(n_steps, max_num_steps)
-            # ---- rk_common.py:266-361 ----
-            if not torch.isfinite(dt):
-                dt = min_step
-            dt = dt.clamp(min_step, max_step)
-            a0 = t_hi
-            a1 = a0 + dt
-            assert a0 + dt > a0, 'underflow in dt {}'.format(dt.item())
-            assert torch.isfinite(y).all(), 'non-finite values in state `y`: {}'.format(y)
-            on_step_t = False
-            if len(step_t):
-                nxt = step_t[next_step]
-                on_step_t = bool(a0 < nxt < a0 + dt)
-                if on_step_t:
-                    a1 = nxt
-                    dt = a1 - a0
-            on_jump_t = False
-            if len(jump_t):                                         # :302-308
-                nxt = jump_t[next_jump]
-                on_jump_t = bool(a0 < nxt < a0 + dt)
-                if on_jump_t:
-                    on_step_t = False
-                    a1 = nxt
-                    dt = a1 - a0
-            y1, f1, err, ks = rk_attempt(func, y, f, a0, dt, a1, ct)
-            ratio = error_ratio(err, rtol, atol, y, y1, norm)
-            accept = bool(ratio <= 1)
-            if dt > max_step:
-                accept = False
-            if dt <= min_step:
-                accept = True
-            stats["dts"].append(float(dt))
-            stats["accepted"].append(accept)
-            if accept:
-                coeffs = interp_fit(y, y1, ks, dt, ct)
-                if on_step_t and next_step != len(step_t) - 1:
-                    next_step += 1
-                if on_jump_t:                                       # :346-351
-                    if next_jump != len(jump_t) - 1:
-                        next_jump += 1
-                    f1 = func(_next(a1.to(T)), y1)
-                y, f, t_lo, t_hi = y1, f1, a0, a1
-                stats["n_accept"] += 1
-            else:
-                t_lo, t_hi = a0, a0
-                stats["n_reject"] += 1
-            dt = optimal_step(dt, ratio, safety, ifactor, dfactor, tab["order"]).clamp(min_step, max_step)
+            attempt()
             n_steps += 1
-        solution[i] = interp_eval(coeffs, t_lo, t_hi, t[i])         # rk_common.py:250
+        solution[i] = interp_eval(st["coeffs"], st["t_lo"], st["t_hi"], t[i])   # rk_common.py:250
     if record is not None:
         record.update(stats)
     return solution

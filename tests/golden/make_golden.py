@@ -203,6 +203,47 @@ def options_cases():
     torch.save(out, os.path.join(HERE, "options.pt"))
 
 
+def events():
+    """event_tests.py:14-49 (forward) and :51-64 (adjoint)."""
+    out = {}
+    for ode in ("constant", "sine"):
+        for method in ("dopri5", "dopri8", "tsit5", "bosh3"):
+            for dtype in (torch.float32, torch.float64):
+                for reverse in (False, True):
+                    f, y0, t, sol = P.construct_problem("cpu", ode=ode, reverse=reverse, dtype=dtype)
+                    target = sol[2]
+                    rec = Rec(f)
+                    with torch.no_grad():
+                        et, ys = torchdiffeq.odeint(rec, y0, t[0:2], event_fn=lambda t_, y_: torch.sum(y_ - target).real,
+                                                    method=method)
+                    out["%s/%s/%s/%s" % (ode, method, str(dtype).split(".")[1], "rev" if reverse else "fwd")] = {
+                        "event_t": et, "y": ys, "nfe": rec.nfe, "t2": t[2], "target": target}
+    f, y0, t, sol = P.construct_problem("cpu", ode="constant")
+    y0 = y0.requires_grad_(True)
+    target = sol[-1]
+    et, ys = torchdiffeq.odeint_adjoint(f, y0, t[0:2], event_fn=lambda t_, y_: torch.sum(y_ - target), method="dopri5")
+    ys[-1].sum().backward()
+    out["adjoint/constant"] = {"event_t": et.detach(), "y": ys.detach(), "gy0": y0.grad.clone(),
+                               "gp": [q.grad.clone() for q in f.parameters()], "t_last": t[-1]}
+    # odeint_event with the implicit-function gradient (odeint.py:160-231): time at which y' = -y + b hits a level
+    class Decay(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.b = torch.nn.Parameter(torch.tensor(0.3, dtype=torch.float64))
+
+        def forward(self, t_, y_):
+            return -y_ + self.b
+    fd = Decay()
+    yd = torch.tensor([2.0, 3.0], dtype=torch.float64, requires_grad=True)
+    t0 = torch.tensor(0.5, dtype=torch.float64, requires_grad=True)
+    et, ys = torchdiffeq.odeint_event(fd, yd, t0, event_fn=lambda t_, y_: y_[0] - 1.0, odeint_interface=torchdiffeq.odeint_adjoint,
+                                      method="dopri5", rtol=1e-9, atol=1e-11)
+    (et + ys[-1].sum()).backward()
+    out["odeint_event/decay"] = {"event_t": et.detach(), "y": ys.detach(), "gy0": yd.grad.clone(), "gt0": t0.grad.clone(),
+                                 "gb": fd.b.grad.clone()}
+    torch.save(out, os.path.join(HERE, "events.pt"))
+
+
 if __name__ == "__main__":
     only = sys.argv[1:]
     if only:
@@ -216,5 +257,6 @@ if __name__ == "__main__":
     adjoint_mlp()
     detest()
     options_cases()
+    events()
     for fn in sorted(os.listdir(HERE)):
         print(fn, os.path.getsize(os.path.join(HERE, fn)))

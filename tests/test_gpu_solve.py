@@ -360,8 +360,6 @@ def test_plain_odeint_with_grad_routes_to_adjoint():
     with pytest.raises(NotImplementedError):
         yy = y0.clone().requires_grad_(True)
         tdq().odeint(lambda t_, y_: -y_, yy, t)
-    with pytest.raises(NotImplementedError):
-        tdq().odeint_event(f, y0, t[0], event_fn=lambda t_, y_: y_[0, 0])
 
 
 def test_adjoint_time_gradients_analytic():
@@ -550,3 +548,63 @@ def test_seminorm_needs_no_more_evaluations():
         y[-1].pow(2).mean().backward()
         nfe[name] = cf.nfe
     assert 0 < nfe["seminorm"] <= nfe["default"]
+
+
+EV = ld("events.pt")
+
+
+@pytest.mark.parametrize("key", sorted(k for k in EV if k.count("/") == 3))
+def test_event_handling_golden(key):
+    """TestEventHandling.test_odeint (event_tests.py:14-49) on the CUDA path, and against the reference's values."""
+    ode, method, dt, direction = key.split("/")
+    dtype = getattr(torch, dt)
+    case = EV[key]
+    f, y0, t, sol = P.construct_problem(DEV, ode=ode, reverse=direction == "rev", dtype=dtype)
+    target = case["target"].to(DEV)
+    with torch.no_grad():
+        et, ys = tdq().odeint(f, y0, t[0:2], event_fn=lambda t_, y_: torch.sum(y_ - target).real, method=method)
+    assert et.dtype == t.dtype and ys.shape == (2, *y0.shape)
+    tol = 1e-4
+    assert ((case["t2"] - et.cpu()) / case["t2"]).abs() < tol
+    assert ((target - ys[-1]) / target).abs().max() < tol
+    close = 1e-4 if dtype == torch.float32 else 1e-7
+    assert abs(float(et) - float(case["event_t"])) <= close * abs(float(case["event_t"]))
+    assert torch.allclose(ys.cpu(), case["y"], rtol=close, atol=close)
+
+
+def test_event_adjoint_and_implicit_gradient():
+    """event_tests.py:51-64 (odeint_adjoint with event_fn) and odeint.py:160-231 (odeint_event gradient rerouting)."""
+    case = EV["adjoint/constant"]
+    f, y0, t, sol = P.construct_problem(DEV, ode="constant")
+    y0 = y0.requires_grad_(True)
+    target = sol[-1]
+    et, ys = tdq().odeint_adjoint(f, y0, t[0:2], event_fn=lambda t_, y_: torch.sum(y_ - target), method="dopri5")
+    assert ((sol[-1] - ys[-1]) / sol[-1]).abs().max() < 1e-4 and ((t[-1] - et) / t[-1]).abs() < 1e-4
+    et.backward(retain_graph=True)
+    f.zero_grad()
+    y0.grad = None
+    ys[-1].sum().backward()
+    assert torch.allclose(y0.grad.cpu(), case["gy0"], rtol=1e-4, atol=1e-8)
+    for q, want in zip(f.parameters(), case["gp"]):
+        assert torch.allclose(q.grad.cpu(), want, rtol=1e-4, atol=1e-6)
+
+    case = EV["odeint_event/decay"]
+
+    class Decay(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.b = torch.nn.Parameter(torch.tensor(0.3, dtype=torch.float64))
+
+        def forward(self, t_, y_):
+            return -y_ + self.b
+    fd = Decay().to(DEV)
+    yd = torch.tensor([2.0, 3.0], dtype=torch.float64, device=DEV, requires_grad=True)
+    t0 = torch.tensor(0.5, dtype=torch.float64, device=DEV, requires_grad=True)
+    et, ys = tdq().odeint_event(fd, yd, t0, event_fn=lambda t_, y_: y_[0] - 1.0, odeint_interface=tdq().odeint_adjoint,
+                                method="dopri5", rtol=1e-9, atol=1e-11)
+    (et + ys[-1].sum()).backward()
+    assert abs(float(et) - float(case["event_t"])) < 1e-7
+    assert torch.allclose(ys.detach().cpu(), case["y"], rtol=1e-7, atol=1e-9)
+    assert torch.allclose(yd.grad.cpu(), case["gy0"], rtol=1e-5, atol=1e-8)
+    assert torch.allclose(t0.grad.cpu(), case["gt0"], rtol=1e-5, atol=1e-8)
+    assert torch.allclose(fd.b.grad.cpu(), case["gb"], rtol=1e-5, atol=1e-8)

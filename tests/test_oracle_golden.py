@@ -177,3 +177,26 @@ def test_jump_t(key):
     assert f.nfe == case["nfe_jump"] if dtype == torch.float64 else abs(f.nfe - case["nfe_jump"]) <= 24
     assert f.nfe < case["nfe_plain"]
     assert torch.allclose(y, case["y_jump"], rtol=1e-5 if dtype == torch.float32 else 1e-9, atol=1e-6)
+
+
+EV = ld("events.pt")
+
+
+@pytest.mark.parametrize("key", sorted(k for k in EV if k.count("/") == 3))
+def test_events(key):
+    """solvers.py:41-49 + rk_common.py:252-264 + event_handling.py:5-20 against the reference (event_tests.py:14-49)."""
+    ode, method, dt, direction = key.split("/")
+    dtype = getattr(torch, dt)
+    case = EV[key]
+    f, y0, t, sol = P.construct_problem("cpu", ode=ode, reverse=direction == "rev", dtype=dtype)
+    target = case["target"]
+    cf = O.Counter(f)
+    with torch.no_grad():
+        et, ys = O.odeint_adaptive(cf, y0, t[0:2], method, event_fn=lambda t_, y_: torch.sum(y_ - target).real)
+    tol = 1e-4                                                     # event_tests.py:33
+    assert ((case["t2"] - et) / case["t2"]).abs() < tol and ((target - ys[-1]) / target).abs().max() < tol
+    close = 1e-4 if dtype == torch.float32 else 1e-7
+    assert abs(float(et) - float(case["event_t"])) <= close * abs(float(case["event_t"]))
+    assert torch.allclose(ys, case["y"], rtol=close, atol=close)
+    if dtype == torch.float64 and method != "dopri8":
+        assert cf.nfe == case["nfe"]

@@ -473,34 +473,82 @@ class AdaptiveEngine:
         return n_out
 
     # ---- lock step: the reference's exact call sequence --------------------------------------
+    def _lockstep_attempt(self, issued, mb):
+        """One attempt in the reference's exact call order (rk_common.py:266-361): callbacks, stages, the
+        accept decision read from the mailbox, accepted-step work, the f re-evaluation after a jump."""
+        cb = self.callbacks
+        if cb.get("callback_step") is not None:             # rk_common.py:272
+            cb["callback_step"](*self._with_y(mb.next_t0, mb.next_dt))
+        k, kp, keep = self._attempt_front()
+        issued += 1
+        mb = self._wait_seq(issued)
+        self._raise_if_failed(mb)
+        if cb:
+            name = "callback_accept_step" if mb.accept else "callback_reject_step"   # :339, :354
+            if cb.get(name) is not None:
+                cb[name](*self._with_y(mb.att_t0, mb.att_dt))
+        jumped = bool(mb.accept) and bool(mb.on_jump_t)
+        self._attempt_back(kp)
+        del k, kp, keep
+        if jumped:                                          # rk_common.py:346-351: f on the far side of the jump
+            f = self._call_fn(self.taux[2], self.y0w, 0)
+            if f.data_ptr() != self.k0.data_ptr():
+                self.k0.copy_(f)
+            del f
+        return issued, mb
+
     def _loop_lockstep(self):
         issued = 0
-        cb = self.callbacks
         torch.cuda.current_stream().synchronize()          # first attempt's (t0, dt) and status are in the mailbox
         mb = self.mbox_host.contents
         self._raise_if_failed(mb)
         while True:
-            if cb.get("callback_step") is not None:         # rk_common.py:272
-                cb["callback_step"](*self._with_y(mb.next_t0, mb.next_dt))
-            k, kp, keep = self._attempt_front()
-            issued += 1
-            mb = self._wait_seq(issued)
-            self._raise_if_failed(mb)
-            if cb:
-                name = "callback_accept_step" if mb.accept else "callback_reject_step"   # :339, :354
-                if cb.get(name) is not None:
-                    cb[name](*self._with_y(mb.att_t0, mb.att_dt))
-            jumped = bool(mb.accept) and bool(mb.on_jump_t)
-            self._attempt_back(kp)
-            del k, kp, keep
-            if jumped:                                      # rk_common.py:346-351: f on the far side of the jump
-                f = self._call_fn(self.taux[2], self.y0w, 0)
-                if f.data_ptr() != self.k0.data_ptr():
-                    self.k0.copy_(f)
-                del f
+            issued, mb = self._lockstep_attempt(issued, mb)
             if mb.done:
                 break
         torch.cuda.current_stream().synchronize()
+
+    # ---- event handling (solvers.py:38-49, rk_common.py:252-264, event_handling.py:5-20) ----------------
+    def solve_until_event(self, y0_flat, t0, event_fn, tol):
+        """Integrate from t0 until event_fn(t, y) changes sign, then bisect on the dense output of the last
+        step.  event_fn takes a 0-dim float64 device tensor (ascending solver time) and the flat state.
+        Host driven by nature (a sign test per step); returns (event_t as float, y(event_t) tensor)."""
+        t64 = torch.tensor([float(t0), float("inf")], dtype=torch.float64, device=self.device)
+        self._begin(y0_flat, t64, float(t0))
+        torch.cuda.current_stream().synchronize()
+        mb = self.mbox_host.contents
+        self._raise_if_failed(mb)
+        tt = lambda v: torch.tensor(v, dtype=torch.float64, device=self.device)
+        t_cur = float(t0)
+        if bool(event_fn(tt(t_cur), self.y0w) == 0):                         # rk_common.py:254-255
+            return t_cur, self.y0w.clone()
+        sign0 = torch.sign(event_fn(tt(t_cur), self.y0w))
+        issued = 0
+        while bool(sign0 == torch.sign(event_fn(tt(t_cur), self.y0w))):      # :259
+            issued, mb = self._lockstep_attempt(issued, mb)
+            t_cur = mb.t1
+        torch.cuda.current_stream().synchronize()
+        self.n_accept, self.n_reject = int(mb.n_accept), int(mb.n_reject)
+        self.n_attempts = self.n_accept + self.n_reject
+        # find_event (event_handling.py:5-20): bisection on [t0, t1] of the last accepted step
+        lo, hi = float(mb.t0), float(mb.t1)
+        import math
+        nitrs = int(math.ceil(math.log((hi - lo) / float(tol)) / math.log(2.0)))
+        y_mid = torch.empty(self.n, dtype=self.dtype, device=self.device)
+
+        def interp(t_eval):
+            self._launch(self.lib.tdq_interp_eval_at(self.ctrl.data_ptr(), self.dt_code, self.coeff_ptrs,
+                                                     tt(t_eval).data_ptr(), y_mid.data_ptr(), self.n, _stream()))
+            return y_mid
+        for _ in range(max(nitrs, 0)):
+            t_mid = (hi + lo) / 2.0
+            same = bool(sign0 == torch.sign(event_fn(tt(t_mid), interp(t_mid))))
+            if same:
+                lo = t_mid
+            else:
+                hi = t_mid
+        event_t = (lo + hi) / 2.0
+        return event_t, interp(event_t).clone()
 
     def _with_y(self, t0, dt):
         t0, dt = self._scalars(t0, dt)

@@ -23,8 +23,8 @@ from . import _lib
 from ._engine import Layout, on_solver_stream
 from ._fixed import FixedGridEngine
 from .odeint import (ADAPTIVE_METHODS, FIXED_METHODS, _ADJOINT_CALLBACK_NAMES, _CALLBACK_NAMES, _cache_get, _cache_key,
-                     _cache_put, _make_adaptive_engine, _mixed_norm, _rms_norm, _solve, _unflatten, fixed_grid,
-                     normalise, Problem)
+                     _cache_put, _make_adaptive_engine, _mixed_norm, _rms_norm, _solve, _solve_event, _unflatten,
+                     fixed_grid, normalise, Problem)
 
 
 def find_parameters(module):
@@ -263,7 +263,13 @@ class _AdjointFunction(torch.autograd.Function):
         ctx.p = p
         ctx.bargs = (adjoint_rtol, adjoint_atol, adjoint_method, adjoint_options, t_requires_grad)
         ctx.bsolver = None
+        ctx.event_mode = p.event_fn is not None                          # adjoint.py:21
         with torch.no_grad():
+            if ctx.event_mode:                                           # adjoint.py:30-31
+                ev, sol, _ = _solve_event(p)
+                event_t = torch.tensor(ev, dtype=t.dtype, device=t.device)
+                ctx.save_for_backward(t, sol, event_t, *adjoint_params)
+                return event_t, sol
             sol, _ = _solve(p)                                          # adjoint.py:23-24
             graph_opt = adjoint_options.get("graph", "auto")
             if any(ctx.needs_input_grad) and len(t) > 1 and graph_opt in (True, "auto") \
@@ -287,15 +293,24 @@ class _AdjointFunction(torch.autograd.Function):
         return sol
 
     @staticmethod
-    def backward(ctx, grad_sol):
+    def backward(ctx, *grads):
         p = ctx.p
-        t, y, *adjoint_params = ctx.saved_tensors
+        if ctx.event_mode:
+            # backprop as if integrating up to the event time; not through the event time itself (adjoint.py:46-53)
+            t_all, y, event_t, *adjoint_params = ctx.saved_tensors
+            t = torch.cat([t_all[0].reshape(-1), event_t.reshape(-1).to(t_all)])
+            grad_sol = grads[1]
+        else:
+            t, y, *adjoint_params = ctx.saved_tensors
+            grad_sol = grads[0]
         grad_sol = grad_sol.contiguous()
         with torch.no_grad():
             bs = ctx.bsolver
             if bs is None:
                 bs = _BackwardSolver(p, adjoint_params, *ctx.bargs)
             time_vjps, adj_y, adj_params = bs.run(t, y, grad_sol)
+            if ctx.event_mode and time_vjps is not None:                 # adjoint.py:146-148
+                time_vjps = torch.cat([time_vjps[0].reshape(-1), torch.zeros_like(t_all[1:])])
         ctx.bsolver = None
         return (None, None, None, None, None, None, time_vjps, adj_y, *adj_params)
 
@@ -361,7 +376,12 @@ def odeint_adjoint(func, y0, t, *, rtol=1e-7, atol=1e-9, method=None, options=No
     # The autograd node is created on the solver stream, so that its backward -- and every gradient edge
     # into the parameters -- lives on the stream the backward step graph is captured and replayed on.
     with on_solver_stream(p.device) as ss:
-        sol = _AdjointFunction.apply(p, adjoint_rtol, adjoint_atol, adjoint_method, adjoint_options, t.requires_grad,
+        ans = _AdjointFunction.apply(p, adjoint_rtol, adjoint_atol, adjoint_method, adjoint_options, t.requires_grad,
                                      t, y0_flat, *adjoint_params)
+        if p.event_fn is not None:                                                     # adjoint.py:209-223
+            event_t, sol = ans
+            ss.publish(sol, event_t)
+            return event_t, _unflatten(p, sol)
+        sol = ans
         ss.publish(sol)
     return _unflatten(p, sol)

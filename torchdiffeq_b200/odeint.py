@@ -50,6 +50,17 @@ class Problem:
     pass
 
 
+def _combine_event_functions(event_fn, t0, y0):
+    """event_handling.py:23-35: make every component initially positive and take the minimum."""
+    with torch.no_grad():
+        initial_signs = torch.sign(event_fn(t0, y0))
+
+    def combined_event_fn(t, y):
+        c = event_fn(t, y)
+        return torch.min(c * initial_signs)
+    return combined_event_fn
+
+
 def _check_timelike(name, timelike, can_grad):                                         # misc.py:367-374
     assert isinstance(timelike, torch.Tensor), '{} must be a torch.Tensor'.format(name)
     if not torch.is_floating_point(timelike):                                          # misc.py:110-112
@@ -92,8 +103,7 @@ def normalise(func, y0, t, rtol, atol, method, options, event_fn, adjoint=False)
     if event_fn is not None:
         if len(t) != 2:                                                                # misc.py:203-204
             raise ValueError(f"We require len(t) == 2 when in event handling mode, but got len(t)={len(t)}.")
-        raise NotImplementedError("event handling (odeint_event / event_fn) is outside the B200 hot path "
-                                  "(SURVEY.md section 8(f) item 3)")
+        event_fn = _combine_event_functions(event_fn, t[0], y0)                        # misc.py:207
     p = Problem()
     p.original_func = func
     p.is_tuple = not isinstance(y0, torch.Tensor)
@@ -191,6 +201,15 @@ def normalise(func, y0, t, rtol, atol, method, options, event_fn, adjoint=False)
         p.fn = lambda t_, y_flat: func(t_, y_flat.view(shape))
         p.pieces = None
         p.segs = None
+
+    # event function on the flat state, in the solver's ascending time (misc.py:224-225, :281-282)
+    p.event_fn = None
+    if event_fn is not None:
+        if method not in ADAPTIVE_METHODS:
+            raise NotImplementedError("event handling is implemented for the adaptive methods only")
+        unflat = (lambda yf: p.layout.views(yf)) if p.is_tuple else (lambda yf: yf.view(p.shape))
+        sign_ = p.t_sign
+        p.event_fn = lambda t_, y_flat: event_fn(t_ * sign_, unflat(y_flat))
 
     # norm (misc.py:237-266): the defaults stay fused; a user callable takes the compatibility path
     p.norm_fn = None
@@ -390,6 +409,17 @@ def fixed_grid(method, o, func, y0_view, t_cpu):
     return grid
 
 
+def _solve_event(p):
+    """odeint.py:97-100 + solvers.py:41-49: integrate until the event; returns (event_t tensor like t, [2, n])."""
+    eng = _make_adaptive_engine(p, p.method, p.rtol, p.atol, p.rtol_vec, p.atol_vec,
+                                dict(p.options, run_ahead=0, graph=False), segs=p.segs, pieces=p.pieces,
+                                norm_fn=p.norm_fn, q_view=p.q_view, callbacks=p.callbacks)
+    tol = p.atol if p.atol is not None else float(p.atol_vec.min())
+    event_t, y_event = eng.solve_until_event(p.y0_flat, float(p.t_cpu[0]), p.event_fn, tol)
+    sol = torch.stack([p.y0_flat.to(p.dtype), y_event], dim=0)                         # solvers.py:48
+    return event_t * p.t_sign, sol, eng                                                # odeint.py:99-100
+
+
 def _unflatten(p, sol):
     if p.is_tuple:
         return p.layout.views(sol, (sol.shape[0],))                                    # odeint.py:102-103
@@ -405,9 +435,65 @@ def _func_requires_grad(func):
 _WARNED_ADJOINT_ROUTE = False
 
 
+class _ImplicitFnGradientRerouting(torch.autograd.Function):
+    """odeint.py:197-231: gradient of the event time and of the state at the event through the implicit function
+    theorem, event_fn(t*, y(t*)) = 0  =>  dt*/dy = -(dc/dy) / (dc/dt + dc/dy . f)."""
+
+    @staticmethod
+    def forward(ctx, func, event_fn, event_t, state_t):
+        ctx.func, ctx.event_fn = func, event_fn
+        ctx.save_for_backward(event_t, state_t)
+        return event_t.detach(), state_t.detach()
+
+    @staticmethod
+    def backward(ctx, grad_t, grad_state):
+        func, event_fn = ctx.func, ctx.event_fn
+        event_t, state_t = ctx.saved_tensors
+        event_t = event_t.detach().clone().requires_grad_(True)
+        state_t = state_t.detach().clone().requires_grad_(True)
+        f_val = func(event_t, state_t)
+        with torch.enable_grad():
+            c, (par_dt, dstate) = torch.autograd.functional.vjp(event_fn, (event_t, state_t))
+        dcdt = par_dt + torch.sum(dstate * f_val)                  # total derivative of the event function along the flow
+        grad_t = grad_t + torch.sum(grad_state * f_val)
+        dstate = dstate * (-grad_t / (dcdt + 1e-12)).reshape_as(c)
+        return None, None, None, grad_state + dstate
+
+
 def odeint_event(func, y0, t0, *, event_fn, reverse_time=False, odeint_interface=None, **kwargs):
-    """odeint.py:160-194.  Event handling is outside the B200 hot path."""
-    raise NotImplementedError("odeint_event / event_fn are not implemented on the B200 path (SURVEY.md section 8(f))")
+    """odeint.py:160-194: solve until event_fn crosses zero and link up the gradient of the event time.
+    Pass odeint_interface=odeint_adjoint for gradients with respect to func's parameters and y0."""
+    if odeint_interface is None:
+        odeint_interface = odeint
+    if reverse_time:
+        t = torch.cat([t0.reshape(-1), t0.reshape(-1).detach() - 1.0])
+    else:
+        t = torch.cat([t0.reshape(-1), t0.reshape(-1).detach() + 1.0])
+    event_t, solution = odeint_interface(func, y0, t, event_fn=event_fn, **kwargs)
+    p = normalise(func, y0, t, 0.0, 0.0, kwargs.get("method"), None, event_fn)        # flat func / event_fn, :172
+    sign_ = p.t_sign
+    flat_func = lambda t_, y_flat: _as_flat(p, p.fn(t_ * sign_, y_flat)) * sign_       # ascending-time dynamics
+    if p.is_tuple:
+        state_t = p.layout.flatten([s_[-1] for s_ in solution])
+    else:
+        state_t = solution[-1].reshape(-1)
+    if reverse_time:
+        event_t = -event_t
+    event_t, state_t = _ImplicitFnGradientRerouting.apply(flat_func, p.event_fn, event_t, state_t)
+    if reverse_time:
+        event_t = -event_t
+    if p.is_tuple:
+        pieces = p.layout.views(state_t)
+        solution = tuple(torch.cat([s_[:-1], s_t[None]], dim=0) for s_, s_t in zip(solution, pieces))
+    else:
+        solution = torch.cat([solution[:-1], state_t.view(p.shape)[None]], dim=0)
+    return event_t, solution
+
+
+def _as_flat(p, f):
+    if isinstance(f, tuple):
+        return p.layout.flatten(list(f))
+    return f.reshape(-1)
 
 
 def odeint_dense(func, y0, t0, t1, *, rtol=1e-7, atol=1e-9, method=None, options=None):
@@ -439,12 +525,17 @@ def odeint(func, y0, t, *, rtol=1e-7, atol=1e-9, method=None, options=None, even
                                   "(odeint_adjoint); backpropagation through the solver internals is not implemented",
                                   stacklevel=2)
                 from .adjoint import odeint_adjoint
-                return odeint_adjoint(func, y0, t, rtol=rtol, atol=atol, method=method, options=options)
+                return odeint_adjoint(func, y0, t, rtol=rtol, atol=atol, method=method, options=options,
+                                      event_fn=event_fn)
             raise NotImplementedError(
                 "backpropagation through the solver's internals is not part of the B200 hot path "
                 "(SURVEY.md section 8(f) item 4); use odeint_adjoint(..., adjoint_params=...) for gradients or call "
                 "odeint under torch.no_grad()")
     with torch.no_grad(), on_solver_stream(p.device) as ss:
+        if p.event_fn is not None:
+            event_t, sol, eng = _solve_event(p)
+            ss.publish(sol)
+            return torch.tensor(event_t, dtype=t.dtype, device=t.device), _unflatten(p, sol)     # odeint.py:98, :105-108
         sol, eng = _solve(p)
         ss.publish(sol)
     if _stats is not None:               # private: solver counters for bench.py and the tests
