@@ -210,6 +210,9 @@ int tdq_interp_eval(void *ctrl_dev, int32_t dtype, const void *const *coeff, voi
 /* Evaluate the current interpolant at one time (device float64 scalar) into out[n] (interp.py:25-48). */
 int tdq_interp_eval_at(void *ctrl_dev, int32_t dtype, const void *const *coeff, const double *t_dev, void *out,
                        size_t n, void *stream);
+/* out = c0 + x*c1 + x^2*c2 + x^3*c3 + x^4*c4 with x = T(x64) (interp.py:39-46) for coefficient sets the caller keeps
+ * itself, e.g. one per accepted step for a dense-output closure (odeint.py:111-157). */
+int tdq_poly_eval(int32_t dtype, const void *const *coeff, double x, void *out, size_t n, void *stream);
 /* Reset the per-output-interval attempt counter (rk_common.py:245). */
 int tdq_ctrl_reset_interval(void *ctrl_dev, void *stream);
 

@@ -244,6 +244,19 @@ def events():
     torch.save(out, os.path.join(HERE, "events.pt"))
 
 
+def dense():
+    """odeint_dense (odeint.py:111-157): the dense-output closure of a dopri5 solve."""
+    out = {}
+    for ode in ("constant", "sine", "linear"):
+        for dtype in (torch.float32, torch.float64):
+            f, y0, t, sol = P.construct_problem("cpu", ode=ode, dtype=dtype)
+            with torch.no_grad():
+                fn = torchdiffeq.odeint_dense(f, y0, t[0], t[-1], rtol=1e-6, atol=1e-8)
+                qs = torch.linspace(1.0, 7.99, 23, dtype=torch.float64)
+                out["%s/%s" % (ode, str(dtype).split(".")[1])] = {"q": qs, "y": torch.stack([fn(q) for q in qs])}
+    torch.save(out, os.path.join(HERE, "dense.pt"))
+
+
 if __name__ == "__main__":
     only = sys.argv[1:]
     if only:
@@ -258,5 +271,6 @@ if __name__ == "__main__":
     detest()
     options_cases()
     events()
+    dense()
     for fn in sorted(os.listdir(HERE)):
         print(fn, os.path.getsize(os.path.join(HERE, fn)))

@@ -608,3 +608,21 @@ def test_event_adjoint_and_implicit_gradient():
     assert torch.allclose(yd.grad.cpu(), case["gy0"], rtol=1e-5, atol=1e-8)
     assert torch.allclose(t0.grad.cpu(), case["gt0"], rtol=1e-5, atol=1e-8)
     assert torch.allclose(fd.b.grad.cpu(), case["gb"], rtol=1e-5, atol=1e-8)
+
+
+@pytest.mark.parametrize("key", sorted(ld("dense.pt")))
+def test_odeint_dense_golden(key):
+    """odeint_dense (odeint.py:111-157): the closure evaluates the per-step quartic interpolants; compared with the
+    reference's closure at 23 times and with odeint's own interpolated outputs."""
+    case = ld("dense.pt")[key]
+    ode, dt = key.split("/")
+    dtype = getattr(torch, dt)
+    f, y0, t, sol = P.construct_problem(DEV, ode=ode, dtype=dtype)
+    with torch.no_grad():
+        fn = tdq().odeint_dense(f, y0, t[0], t[-1], rtol=1e-6, atol=1e-8)
+        got = torch.stack([fn(q) for q in case["q"]])
+        direct = tdq().odeint(f, y0, torch.cat([t[0:1], case["q"][1:].to(DEV)]), method="dopri5", rtol=1e-6, atol=1e-8,
+                              options={"run_ahead": 0, "graph": False})
+    tol = 2e-4 if dtype == torch.float32 else 1e-6
+    assert torch.allclose(got.cpu(), case["y"], rtol=tol, atol=tol * 1e-2), (got.cpu() - case["y"]).abs().max()
+    assert torch.equal(got[1:], direct[1:])                # same interpolants, same arithmetic: bitwise

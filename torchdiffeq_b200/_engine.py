@@ -508,6 +508,25 @@ class AdaptiveEngine:
                 break
         torch.cuda.current_stream().synchronize()
 
+    # ---- dense output (odeint.py:111-157) ------------------------------------------------------------
+    def solve_dense(self, y0_flat, t64):
+        """Lock-step solve that keeps the interpolant of EVERY accepted step: returns (solution, times, coeffs)
+        with times[i], times[i+1] bounding accepted step i and coeffs[i] its five coefficient arrays."""
+        n_out = self._begin(y0_flat, t64)
+        torch.cuda.current_stream().synchronize()
+        mb = self.mbox_host.contents
+        self._raise_if_failed(mb)
+        times, coeffs, issued = [float(t64[0])], [], 0
+        while n_out > 1:
+            issued, mb = self._lockstep_attempt(issued, mb)
+            if mb.accept:                                                   # odeint.py:141-145
+                times.append(float(mb.t1))
+                coeffs.append([c.clone() for c in self.coeff])
+            if mb.done:
+                break
+        torch.cuda.current_stream().synchronize()
+        return self.solution, times, coeffs
+
     # ---- event handling (solvers.py:38-49, rk_common.py:252-264, event_handling.py:5-20) ----------------
     def solve_until_event(self, y0_flat, t0, event_fn, tol):
         """Integrate from t0 until event_fn(t, y) changes sign, then bisect on the dense output of the last

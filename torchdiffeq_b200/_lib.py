@@ -90,6 +90,7 @@ _SIGNATURES = {
     "tdq_interp_fit_commit": (C.c_int, [_vp, _ptab, _i32, _vp, _vp, _pp, _pp, _sz, _vp]),
     "tdq_interp_eval": (C.c_int, [_vp, _i32, _pp, _vp, _sz, _vp]),
     "tdq_interp_eval_at": (C.c_int, [_vp, _i32, _pp, _vp, _vp, _sz, _vp]),
+    "tdq_poly_eval": (C.c_int, [_i32, _pp, _dbl, _vp, _sz, _vp]),
     "tdq_ctrl_reset_interval": (C.c_int, [_vp, _vp]),
     "tdq_rk4_stage": (C.c_int, [_i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "tdq_fixed_emit": (C.c_int, [_i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _sz, _vp]),

@@ -486,6 +486,17 @@ template <typename T> __device__ __forceinline__ T eval_poly(T e, T d, T cq, T b
     return total;
 }
 
+// p(x) for a caller-supplied abscissa x (float64, cast to T like interp.py:39-40); used by dense-output
+// closures that keep their own (t0, t1, coefficients) per accepted step (odeint.py:111-157).
+template <typename T>
+__global__ void __launch_bounds__(kThreads)
+k_poly_eval(const T *__restrict__ ce, const T *__restrict__ cd, const T *__restrict__ cc, const T *__restrict__ cb,
+            const T *__restrict__ ca, T *__restrict__ out, double x64, size_t n) {
+    const T x = (T)x64;
+    for (size_t i = (size_t)blockIdx.x * kThreads + threadIdx.x; i < n; i += (size_t)gridDim.x * kThreads)
+        out[i] = eval_poly<T>(ce[i], cd[i], cc[i], cb[i], ca[i], x);
+}
+
 template <typename T, bool VECTOR, bool AT>
 __global__ void __launch_bounds__(kThreads)
 k_interp_eval(const TdqCtrl *__restrict__ c, const T *__restrict__ ce, const T *__restrict__ cd,
@@ -785,6 +796,19 @@ int tdq_interp_eval(void *ctrl_dev, int32_t dtype, const void *const *coeff, voi
     if (n == 0) return TDQ_OK;
     TDQ_DISPATCH_T(dtype, (launch_eval<T, false>((const TdqCtrl *)ctrl_dev, coeff, solution, nullptr, n, vec,
                                                  (cudaStream_t)stream)));
+    TDQ_CHECK_CUDA(cudaGetLastError());
+    return TDQ_OK;
+}
+
+int tdq_poly_eval(int32_t dtype, const void *const *coeff, double x, void *out, size_t n, void *stream) {
+    TDQ_REQUIRE(coeff && out, "null argument");
+    for (int i = 0; i < 5; ++i) TDQ_REQUIRE(coeff[i] != nullptr, "five coefficient buffers are required");
+    if (n == 0) return TDQ_OK;
+    size_t blocks = (n + kThreads - 1) / kThreads;
+    if (blocks > (size_t)sm_count() * 8) blocks = (size_t)sm_count() * 8;
+    TDQ_DISPATCH_T(dtype, (k_poly_eval<T><<<(unsigned)blocks, kThreads, 0, (cudaStream_t)stream>>>(
+                               (const T *)coeff[0], (const T *)coeff[1], (const T *)coeff[2], (const T *)coeff[3],
+                               (const T *)coeff[4], (T *)out, x, n)));
     TDQ_CHECK_CUDA(cudaGetLastError());
     return TDQ_OK;
 }

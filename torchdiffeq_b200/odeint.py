@@ -497,8 +497,38 @@ def _as_flat(p, f):
 
 
 def odeint_dense(func, y0, t0, t1, *, rtol=1e-7, atol=1e-9, method=None, options=None):
-    """odeint.py:111-157.  Dense-output closures are outside the B200 hot path."""
-    raise NotImplementedError("odeint_dense is not implemented on the B200 path (SURVEY.md section 8(f))")
+    """odeint.py:111-157: solve from t0 to t1 with dopri5 and return a function that evaluates the solution at any
+    time in between from the stored per-step interpolants (on the device, tdq_poly_eval)."""
+    import bisect
+    import ctypes as C
+    from ._engine import _stream
+    assert torch.is_tensor(y0)
+    t0_, t1_ = torch.as_tensor(t0), torch.as_tensor(t1)
+    t = torch.stack([t0_.reshape(()), t1_.reshape(()).to(t0_)]).to(t0_)
+    p = normalise(func, y0, t, rtol, atol, method, options, None)
+    assert p.method == "dopri5"                                                        # odeint.py:119
+    with torch.no_grad(), on_solver_stream(p.device) as ss:
+        eng = _make_adaptive_engine(p, p.method, p.rtol, p.atol, p.rtol_vec, p.atol_vec,
+                                    dict(p.options, run_ahead=0, graph=False), segs=p.segs, pieces=p.pieces,
+                                    norm_fn=p.norm_fn, q_view=p.q_view, callbacks=p.callbacks)
+        t64 = p.t_cpu.to(torch.float64).to(p.device)
+        _, times, coeffs = eng.solve_dense(p.y0_flat, t64)
+    lib, dc, n, sign_, shape, dtype, dev = eng.lib, eng.dt_code, p.n, p.t_sign, p.shape, p.dtype, p.device
+    ptrs = [_lib.ptr_array([c.data_ptr() for c in cs]) for cs in coeffs]
+
+    def dense_output_fn(t_eval):
+        te = float(t_eval) * sign_                                                     # solver (ascending) time
+        idx = bisect.bisect_right(times, te)                                           # searchsorted(..., side="right")
+        idx = min(max(idx, 1), len(times) - 1)
+        lo, hi = times[idx - 1], times[idx]
+        assert lo <= te <= hi, 'invalid interpolation, fails `t0 <= t <= t1`: {}, {}, {}'.format(lo, te, hi)
+        out = torch.empty(n, dtype=dtype, device=dev)
+        with on_solver_stream(dev) as ss2:
+            _lib.check(lib.tdq_poly_eval(dc, ptrs[idx - 1], (te - lo) / (hi - lo), out.data_ptr(), n, _stream()))
+            ss2.publish(out)
+        return out.view(shape)
+    dense_output_fn._keep = (coeffs, ptrs)
+    return dense_output_fn
 
 
 def odeint(func, y0, t, *, rtol=1e-7, atol=1e-9, method=None, options=None, event_fn=None, _stats=None):
