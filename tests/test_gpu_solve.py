@@ -626,3 +626,24 @@ def test_odeint_dense_golden(key):
     tol = 2e-4 if dtype == torch.float32 else 1e-6
     assert torch.allclose(got.cpu(), case["y"], rtol=tol, atol=tol * 1e-2), (got.cpu() - case["y"]).abs().max()
     assert torch.equal(got[1:], direct[1:])                # same interpolants, same arithmetic: bitwise
+
+
+@pytest.mark.parametrize("mode", sorted(MODES))
+def test_func_outputs_that_alias(mode):
+    """The reference copies f into its k tensor (rk_common.py:81), so a func may return its own input or one
+    reused buffer; the CUDA path keeps func outputs in place and must therefore detect both."""
+    y0 = torch.tensor([1.0, -2.0, 0.5, 3.0], dtype=torch.float64, device=DEV)
+    t = torch.tensor([0., 1.], dtype=torch.float64, device=DEV)
+    want = y0 * math.exp(1.0)
+    buf = torch.empty_like(y0)
+
+    def reuse(t_, y_):
+        buf.copy_(y_)
+        return buf
+    with torch.no_grad():
+        for f in (lambda t_, y_: y_, reuse):
+            for method in ("dopri5", "rk4"):
+                opts = dict(MODES[mode]) if method == "dopri5" else {"step_size": 0.01}
+                y = tdq().odeint(f, y0, t, method=method, rtol=1e-10, atol=1e-12, options=opts)
+                assert torch.allclose(y[-1], want, rtol=1e-8, atol=0), (method, (y[-1] - want).abs().max())
+    assert torch.equal(y0, torch.tensor([1.0, -2.0, 0.5, 3.0], dtype=torch.float64, device=DEV))   # input untouched

@@ -259,9 +259,11 @@ class AdaptiveEngine:
             pass
 
     # ---------------------------------------------------------------------------------------
-    def _call_fn(self, t, y, slot):
+    def _call_fn(self, t, y, slot, taken=()):
         """Evaluate func and return a tensor holding the flat result that is safe to keep as stage
-        slot `slot` (rk_common.py:80-81 writes it into k[..., slot])."""
+        slot `slot` (rk_common.py:80-81 writes it into k[..., slot]): the reference COPIES f into k, so an
+        output that aliases the solver's buffers, func's input, or an earlier stage's output (a func that
+        returns y itself, or reuses one result buffer) must be copied here too."""
         self.nfe += 1
         f = self.fn(t, y)
         if isinstance(f, torch.Tensor):
@@ -270,7 +272,7 @@ class AdaptiveEngine:
             f = f.reshape(-1)
             if f.numel() != self.n:
                 raise ValueError("func returned %d elements for a state of %d" % (f.numel(), self.n))
-            if not f.is_contiguous() or (f.data_ptr() % 16) != 0 or self._aliases(f):
+            if not f.is_contiguous() or (f.data_ptr() % 16) != 0 or self._aliases(f) or f.data_ptr() in taken:
                 buf = self._slot(slot)
                 buf.copy_(f)
                 f = buf
@@ -319,7 +321,7 @@ class AdaptiveEngine:
             out = self.y1 if (i == S - 1 and self.fsal) else self.ytmp
             self._launch(lib.tdq_stage_combine(ctrl, tab, dc, i, out.data_ptr(), self.y0w.data_ptr(),
                                              _lib.ptr_array(k), self.n, st))
-            f = self._call_fn(self.tstage[i], out, i + 1)
+            f = self._call_fn(self.tstage[i], out, i + 1, taken=k)
             keep.append(f)
             k[i + 1] = f.data_ptr()
         if not self.fsal:

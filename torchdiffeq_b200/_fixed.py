@@ -110,8 +110,9 @@ class FixedGridEngine:
         f = f.reshape(-1)
         if f.numel() != self.n:
             raise ValueError("func returned %d elements for a state of %d" % (f.numel(), self.n))
-        if (not f.is_contiguous()) or f.untyped_storage().data_ptr() in self._own:
+        if (not f.is_contiguous()) or f.untyped_storage().data_ptr() in self._own or f.data_ptr() in self._taken:
             f = f.clone(memory_format=torch.contiguous_format)
+        self._taken.add(f.data_ptr())
         return f
 
     def _step(self):
@@ -124,6 +125,7 @@ class FixedGridEngine:
             _lib.check(lib.tdq_rk4_stage(dc, which, out, y0, p(k1), p(k2), p(k3), p(k4), dtp, stp, n, st))
             self.launches += 1
         m = self.method
+        self._taken = set()                                # stage outputs of this step (a func may reuse one buffer)
         k1 = self._call_fn(self.tcur[0], self.y0w, None)
         keep = [k1]
         if m == "rk4":
