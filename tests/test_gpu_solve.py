@@ -645,9 +645,9 @@ def test_func_outputs_that_alias(mode):
         buf.copy_(y_)
         return buf
     with torch.no_grad():
-        for f in (lambda t_, y_: y_, reuse):
+        for name, f in (("identity", lambda t_, y_: y_), ("reused-buffer", reuse)):
             for method in ("dopri5", "rk4"):
                 opts = dict(MODES[mode]) if method == "dopri5" else {"step_size": 0.01}
                 y = tdq().odeint(f, y0, t, method=method, rtol=1e-10, atol=1e-12, options=opts)
-                assert torch.allclose(y[-1].cpu(), want[method], rtol=1e-8, atol=0), (method, (y[-1].cpu() - want[method]).abs().max())
+                assert torch.allclose(y[-1].cpu(), want[method], rtol=1e-8, atol=0), (name, method, (y[-1].cpu() - want[method]).abs().max())
     assert torch.equal(y0, torch.tensor([1.0, -2.0, 0.5, 3.0], dtype=torch.float64, device=DEV))   # input untouched

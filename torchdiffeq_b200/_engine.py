@@ -79,6 +79,10 @@ class on_solver_stream:
                     t.record_stream(self.cur)
 
 
+class _RetryWithCopies(Exception):
+    """func handed back a buffer it had already returned for an earlier stage of the same attempt."""
+
+
 class SolverFailure(AssertionError):
     """Raised for the reference's in-loop assertions (rk_common.py:247, :286, :287)."""
 
@@ -241,6 +245,7 @@ class AdaptiveEngine:
         self._graph = None
         self._graph_failed = False
         self._graph_keep = None
+        self._always_copy = False        # set when func is seen to reuse its output buffer (see _call_fn)
         self.capture_in_solve = True     # False: only a prime()d graph is used (solves run inside autograd backward)
         self.n_attempts = 0              # attempts that did work (from the mailbox counters)
         self.nfe = 0                     # func evaluations issued by the host
@@ -272,7 +277,13 @@ class AdaptiveEngine:
             f = f.reshape(-1)
             if f.numel() != self.n:
                 raise ValueError("func returned %d elements for a state of %d" % (f.numel(), self.n))
-            if not f.is_contiguous() or (f.data_ptr() % 16) != 0 or self._aliases(f) or f.data_ptr() in taken:
+            if f.data_ptr() in taken and not self._always_copy:
+                # func reuses ONE output buffer: the earlier stage's values are already gone.  Nothing of this
+                # attempt has been committed yet, so switch to copying every output and redo the attempt.
+                self._always_copy = True
+                raise _RetryWithCopies()
+            if (self._always_copy or not f.is_contiguous() or (f.data_ptr() % 16) != 0 or self._aliases(f)
+                    or f.data_ptr() in taken):
                 buf = self._slot(slot)
                 buf.copy_(f)
                 f = buf
@@ -313,6 +324,12 @@ class AdaptiveEngine:
     # ---------------------------------------------------------------------------------------
     def _attempt_front(self):
         """Stages, error norm, controller: everything up to the accept decision."""
+        try:
+            return self._attempt_front_once()
+        except _RetryWithCopies:
+            return self._attempt_front_once()
+
+    def _attempt_front_once(self):
         lib, ctrl, tab, dc, st = self.lib, self.ctrl.data_ptr(), C.byref(self.tab), self.dt_code, _stream()
         S = self.S
         k = [self.k0.data_ptr()] + [None] * S

@@ -8,7 +8,7 @@ grid interval, indexed by a device step counter."""
 import torch
 
 from . import _lib
-from ._engine import _DTYPES, _stream, pack_pieces, solver_stream
+from ._engine import _DTYPES, _RetryWithCopies, _stream, pack_pieces, solver_stream
 
 _ONE_THIRD = 1 / 3      # rk_common.py:94-96
 _TWO_THIRDS = 2 / 3
@@ -48,6 +48,7 @@ class FixedGridEngine:
         self.perturb = bool(perturb)
         self.callbacks = callbacks or {}
         self.graph_opt = False if self.callbacks else graph
+        self._always_copy = False
         self.pieces = pieces            # fn returns a tuple of pieces (tuple states, the adjoint's augmented state)
         self.nfe = 0
         self.launches = 0
@@ -110,12 +111,22 @@ class FixedGridEngine:
         f = f.reshape(-1)
         if f.numel() != self.n:
             raise ValueError("func returned %d elements for a state of %d" % (f.numel(), self.n))
-        if (not f.is_contiguous()) or f.untyped_storage().data_ptr() in self._own or f.data_ptr() in self._taken:
+        if f.data_ptr() in self._taken and not self._always_copy:
+            self._always_copy = True                       # func reuses one output buffer: redo the step with copies
+            raise _RetryWithCopies()
+        if (self._always_copy or (not f.is_contiguous()) or f.untyped_storage().data_ptr() in self._own
+                or f.data_ptr() in self._taken):
             f = f.clone(memory_format=torch.contiguous_format)
         self._taken.add(f.data_ptr())
         return f
 
     def _step(self):
+        try:
+            return self._step_once()
+        except _RetryWithCopies:                           # nothing of the step has been committed yet
+            return self._step_once()
+
+    def _step_once(self):
         lib, dc, n, st = self.lib, self.dc, self.n, _stream()
         y0, ya, y1 = self.y0w.data_ptr(), self.ytmp.data_ptr(), self.y1.data_ptr()
         dtp, stp = self.dt_dev.data_ptr(), self.step_dev.data_ptr()
