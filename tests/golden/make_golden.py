@@ -90,7 +90,7 @@ def zoo():
                     with torch.no_grad():
                         y = torchdiffeq.odeint(rec, y0, t, method=method, **kw)
                     key = "%s/%s/%s/%s" % (ode, method, str(dtype).split(".")[1], "rev" if reverse else "fwd")
-                    cases[key] = {"y": y, "nfe": rec.nfe, "dts": rec.dts, "acc": rec.acc, "kw": kw, "exact": sol}
+                    cases[key] = {"y": y, "nfe": rec.nfe, "kw": kw, "exact": sol}
     torch.save(cases, os.path.join(HERE, "zoo.pt"))
 
 
