@@ -21,7 +21,7 @@ def log(*a):
 
 def main():
     import faulthandler
-    faulthandler.dump_traceback_later(int(os.environ.get("DIST_CHECK_DUMP_AFTER", "90")), exit=True)
+    faulthandler.dump_traceback_later(int(os.environ.get("DIST_CHECK_DUMP_AFTER", "300")), exit=True)
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
