@@ -170,20 +170,27 @@ def roofline_probe(dev, n_elems, reps=20):
     _lib.check(lib.tdq_ctrl_init(eng.ctrl.data_ptr(), C.byref(eng.tab), C.byref(eng.opt), eng.t_out.data_ptr(), 0.0, 2,
                                  eng.mbox_dev, _stream()))
     _lib.check(lib.tdq_set_first_step(eng.ctrl.data_ptr(), 0.05, _stream()))
-    _lib.check(lib.tdq_prepare_attempt(eng.ctrl.data_ptr(), eng.dt_code, _stream()))
+    _lib.check(lib.tdq_prepare_attempt(eng.ctrl.data_ptr(), eng.dt_code, None, _stream()))
     ks = [torch.randn(n_elems, device=dev) * 1e-3 for _ in range(7)]
     y0 = torch.randn(n_elems, device=dev)
     outs = [torch.empty(n_elems, device=dev) for _ in range(2)]
     kp = _lib.ptr_array([k.data_ptr() for k in ks])
     ctrl, tab, dc = eng.ctrl.data_ptr(), C.byref(eng.tab), eng.dt_code
 
-    def combine(row):
-        _lib.check(lib.tdq_stage_combine(ctrl, tab, dc, row, outs[row & 1].data_ptr(), y0.data_ptr(), kp, n_elems, _stream()))
+    errp = torch.empty(n_elems, device=dev)
 
-    def norm():
-        _lib.check(lib.tdq_error_norm(ctrl, tab, dc, y0.data_ptr(), outs[1].data_ptr(), kp, None, None, eng.seg_off,
-                                      eng.seg_len, 1, n_elems, eng.partials.data_ptr(), eng.norm_out.data_ptr(), None,
-                                      _stream()))
+    def combine(row):
+        if row == 5:       # the row that yields y1, fused with the prefix of the error estimate (one extra N*s write)
+            _lib.check(lib.tdq_stage_combine_final(ctrl, tab, dc, outs[1].data_ptr(), errp.data_ptr(), y0.data_ptr(), kp,
+                                                   n_elems, _stream()))
+        else:
+            _lib.check(lib.tdq_stage_combine(ctrl, tab, dc, row, outs[row & 1].data_ptr(), y0.data_ptr(), kp, n_elems,
+                                             _stream()))
+
+    def norm():            # error ratio + candidate commit (y1, k_S -> the other pair of the pointer table)
+        _lib.check(lib.tdq_error_norm_commit(ctrl, dc, errp.data_ptr(), ks[6].data_ptr(), y0.data_ptr(),
+                                             outs[1].data_ptr(), None, None, None, 0, 0, 1, n_elems,
+                                             eng.partials.data_ptr(), eng.norm_out.data_ptr(), None, _stream()))
     rows = [lambda r=r: combine(r) for r in range(6)]
 
     def timed(fns, reps):

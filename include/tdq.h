@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define TDQ_ABI_VERSION 1
+#define TDQ_ABI_VERSION 2
 
 #define TDQ_MAX_STAGES 16            /* func evaluations per attempt, excluding f0 (dopri8: 13)   */
 #define TDQ_MAX_K      (TDQ_MAX_STAGES + 1) /* stage slots k_0 .. k_S                              */
@@ -78,6 +78,18 @@ typedef struct {
                                       /* every coefficient instead of a pass over f.                */
     int64_t max_num_steps;            /* per output interval (rk_common.py:247)                     */
     int64_t n_global;                 /* element count the RMS mean divides by (all ranks)          */
+    /* State pointer table.  The accepted state y0 and its derivative f0 = k_0 live in ybuf[par]/kbuf[par]  */
+    /* (par = 0 when a solve starts: the caller puts y(t[0]) into ybuf[0] and f(t[0], y0) into kbuf[0]).     */
+    /* tdq_error_norm_commit writes every attempt's candidate (y1, k_S) into the other pair and             */
+    /* tdq_controller accepts by flipping par -- rk_common.py:341,:352 without a copy.  Four caller-owned    */
+    /* device buffers of n elements, 16-byte aligned; all NULL = no table (every launcher then needs y0 and  */
+    /* k[0] explicitly and nothing is committed).                                                           */
+    void *ybuf[2];
+    void *kbuf[2];
+    int32_t always_fit;               /* 1: fit the interpolant on EVERY accepted step (dense output, events) */
+    int32_t reserved;
+    uint64_t loop_handle;             /* tdq_loop_create's handle when attempts run inside the device-side   */
+                                      /* while loop, else 0                                                  */
 } tdq_options;
 
 /* Mapped-host mailbox the controller kernel writes after every attempt; the host polls `seq`
@@ -95,7 +107,7 @@ typedef struct {
     volatile double next_t0, next_dt; /* the same for the attempt prepared next (callback_step)     */
     volatile int32_t on_jump_t;       /* the accepted attempt ended on a jump_t point: the host must */
                                       /* re-evaluate f at taux[2] = next(T(t1)) (rk_common.py:346-351) */
-    volatile int32_t reserved;
+    volatile int32_t par;             /* which pair of the pointer table holds the accepted state now */
 } tdq_mailbox;
 
 /* ---- library ------------------------------------------------------------------------------ */
@@ -139,24 +151,37 @@ int tdq_ctrl_set_step_t(void *ctrl_dev, const double *step_t_dev, int32_t n, voi
 int tdq_ctrl_set_jump_t(void *ctrl_dev, const double *jump_t_dev, int32_t n, void *stream);
 
 /* ---- norms: deterministic segmented sum of squares ---------------------------------------- */
-/* Doubles the caller must provide (zero-initialised ONCE) as `partials` for the two reductions
- * below, given the longest segment length and the segment count. */
-size_t tdq_norm_partials_len(size_t n_max_seg_len, int32_t n_seg);
+/* A norm is max over SEGMENTS of rms(segment) (misc.py:22-23, :30-33, adjoint.py:247-271).  One segment
+ * covering [0,n) needs no table.  Anything else -- tuple states, the adjoint's augmented state with one
+ * segment per parameter tensor, any number of them -- is described by a CHUNK TABLE in device memory:
+ * tdq_norm_table_fill() writes it into a HOST buffer of int64 words that the caller uploads once per solver
+ * (the library owns no memory).  Segments must be ascending and disjoint; elements outside every segment
+ * (padding, the parameter block under 'seminorm') are still committed and still checked for non-finite
+ * values, they just enter no norm.  Returns the number of words needed (call with table_host == NULL to
+ * size the buffer), or -1.  table_host[1] = number of chunks, table_host[3] = 1 when every segment starts
+ * on a 16-byte boundary (pass both to the launchers below). */
+int64_t tdq_norm_table_fill(const int64_t *seg_offsets, const int64_t *seg_lens, int32_t n_seg, int64_t n,
+                            int32_t dtype, int64_t *table_host, int64_t capacity_words);
+/* Doubles the caller must provide (zero-initialised ONCE) as `partials` for the reductions below;
+ * n_chunks = 0 without a table. */
+size_t tdq_norm_partials_len(size_t n, int64_t n_chunks);
 
 /* ---- initial step (misc.py:36-77 _select_initial_step) ------------------------------------ */
 /* out[s] = sum over segment s of (x/scale)^2 (or ((x - x2)/scale)^2 when x2 != NULL),
- * scale = atol + |y0|*rtol (misc.py:55-58, :69); out[n_seg] unused (0).  seg_offsets/seg_lens are
- * HOST arrays (NULL: one segment [0,n)).  rtol_vec/atol_vec: optional per-element float64. */
+ * scale = atol + |y0|*rtol (misc.py:55-58, :69); without x2, out[n_seg] = number of non-finite y0
+ * elements (the pass over y0 doubles as the check of rk_common.py:287 for the first attempt).
+ * y0 == NULL: the control block's current y0.  table_dev/n_chunks/table_aligned: chunk table or
+ * NULL/0/0 with n_seg == 1.  rtol_vec/atol_vec: optional per-element float64. */
 int tdq_scaled_sumsq(void *ctrl_dev, int32_t dtype, const void *x, const void *x2, const void *y0,
-                     const double *rtol_vec, const double *atol_vec, const int64_t *seg_offsets,
-                     const int64_t *seg_lens, int32_t n_seg, size_t n, double *partials, double *out,
-                     void *stream);
+                     const double *rtol_vec, const double *atol_vec, const int64_t *table_dev, int64_t n_chunks,
+                     int32_t table_aligned, int32_t n_seg, size_t n, double *partials, double *out, void *stream);
 /* h0 from d0 = norm(y0/scale), d1 = norm(f0/scale) given as (all-reduced) segment sums; also sets
  * taux[1] = probe time t0 + h0 (misc.py:60-67).  seg_counts_dev: GLOBAL element count per segment
  * (device int64) or NULL for a single segment of options.n_global elements. */
 int tdq_initial_step_h0(void *ctrl_dev, int32_t dtype, const double *d0_sumsq, const double *d1_sumsq,
                         const int64_t *seg_counts_dev, int32_t n_seg, void *stream);
-/* y_probe = y0 + h0*f0 (misc.py:66); f0 is the RAW func output (t_sign applied inside). */
+/* y_probe = y0 + h0*f0 (misc.py:66); f0 is the RAW func output (t_sign applied inside).  NULL y0 / f0: the
+ * control block's current pair. */
 int tdq_initial_step_probe(void *ctrl_dev, int32_t dtype, void *y_probe, const void *y0, const void *f0,
                            size_t n, void *stream);
 /* dt = min(100*h0, h1) from d2 = norm((f1 - f0)/scale)/h0 (misc.py:69-77). */
@@ -170,43 +195,56 @@ int tdq_set_first_step(void *ctrl_dev, double first_step, void *stream);
  * max_num_steps assertions, stage times t_i = T(t0) + alpha_i*T(dt) (or prev(T(t1)) when
  * alpha_i == 1) and coefficients fl_T(beta_ij*T(dt)); rk_common.py:246-247, :269-308, :61-79, :89.
  * tdq_controller already does this for attempt n+1, so the host calls it once per solve. */
-int tdq_prepare_attempt(void *ctrl_dev, int32_t dtype, void *stream);
+/* y0_nonfinite_count_dev: optional device double (tdq_scaled_sumsq's out[n_seg] for x = y0); when it is
+ * positive the first attempt fails with TDQ_RUN_NONFINITE exactly where the reference asserts (:287, after
+ * the underflow check :286). */
+int tdq_prepare_attempt(void *ctrl_dev, int32_t dtype, const double *y0_nonfinite_count_dev, void *stream);
 
 /* y_out = y0 + sum_j k_j * coef[row][j] over the non-zero tableau entries (rk_common.py:79, :85).
  * row in [0, S): stage rows; row == S: the c_sol row of a non-FSAL tableau.  k[j] is stage slot j
  * (RAW func output), NULL allowed where the tableau entry is zero.  `tab` only selects the
- * sparsity pattern; coefficients come from the control block.  No-op once the solve has halted. */
+ * sparsity pattern; coefficients come from the control block.  No-op once the solve has halted.
+ * y0 == NULL and k[0] == NULL select the control block's current pair (pointer table). */
 int tdq_stage_combine(void *ctrl_dev, const tdq_tableau *tab, int32_t dtype, int32_t row, void *y_out,
                       const void *y0, const void *const *k, size_t n, void *stream);
 
-/* Embedded error + scaled squared norm (rk_common.py:89 + misc.py:80-82 + misc.py:22-23), fused:
- * err = sum_j k_j*fl_T(dt*e_j); tol = atol + rtol*max(|y0|,|y1|); out[s] = sum over segment s of
- * (err/tol)^2, out[n_seg] = number of non-finite y1 elements.  Segments (HOST arrays; NULL = one
- * segment [0,n)) express the max-of-RMS norms of misc.py:30-33 and adjoint.py:247-271.
- * err_over_tol_out, if non-NULL, receives err/tol (state dtype; float64 with vector tolerances)
- * for callers with a custom norm callable. */
-int tdq_error_norm(void *ctrl_dev, const tdq_tableau *tab, int32_t dtype, const void *y0, const void *y1,
-                   const void *const *k, const double *rtol_vec, const double *atol_vec,
-                   const int64_t *seg_offsets, const int64_t *seg_lens, int32_t n_seg, size_t n,
-                   double *partials, double *out, void *err_over_tol_out, void *stream);
+/* The LAST combine of an attempt -- the row that yields y1: stage row S-1 for FSAL tableaus
+ * (rk_common.py:83-87), the c_sol row otherwise (:85) -- fused with the part of the embedded error
+ * estimate (:89) whose stage slots exist at that point:
+ *     y1_out  = y0 + sum_j k_j*fl(dt*c_sol_j)
+ *     err_out = sum_{j <= avail} k_j*fl(dt*e_j)       ascending j; avail = S-1 (FSAL) or S
+ * One pass over k_0..k_avail instead of two.  Same NULL conventions as tdq_stage_combine. */
+int tdq_stage_combine_final(void *ctrl_dev, const tdq_tableau *tab, int32_t dtype, void *y1_out, void *err_out,
+                            const void *y0, const void *const *k, size_t n, void *stream);
+
+/* Error ratio + candidate commit (rk_common.py:89 tail + misc.py:80-82 + :22-23/:30-33; rk_common.py:338-352):
+ *     err = err_pre (+ k_last*fl(dt*e_S) when the tableau is FSAL and e_S != 0; k_last = k_S)
+ *     tol = atol + rtol*max(|y0|,|y1|);  out[s] = sum over segment s of (err/tol)^2
+ *     out[n_seg] = number of non-finite y1 elements
+ * and, in the same pass, y1 -> ybuf[par^1], k_last -> kbuf[par^1] (the candidate the controller accepts by
+ * flipping par).  err_over_tol_out, if non-NULL, receives err/tol (state dtype; float64 with vector
+ * tolerances) for callers with a custom norm callable.  Chunk table as for tdq_scaled_sumsq. */
+int tdq_error_norm_commit(void *ctrl_dev, int32_t dtype, const void *err_pre, const void *k_last, const void *y0,
+                          const void *y1, const double *rtol_vec, const double *atol_vec, const int64_t *table_dev,
+                          int64_t n_chunks, int32_t table_aligned, int32_t n_seg, size_t n, double *partials,
+                          double *out, void *err_over_tol_out, void *stream);
+/* The candidate commit alone: y1 -> ybuf[par^1], k_last -> kbuf[par^1]. */
+int tdq_commit_candidates(void *ctrl_dev, int32_t dtype, const void *y1, const void *k_last, size_t n, void *stream);
 
 /* Accept/reject, I-controller, bookkeeping, output cursor, the NEXT attempt's constants, mailbox
  * (rk_common.py:323-361, misc.py:85-95, solvers.py:33-34, then :269-308 for the next attempt).
- * norm_in: the (all-reduced) output of tdq_error_norm.  If ratio_dev != NULL (state dtype scalar,
+ * norm_in: the (all-reduced) output of tdq_error_norm_commit.  If ratio_dev != NULL (state dtype scalar,
  * float64 when options.ratio_f64) the ratio is read from there instead (custom norm callable). */
 int tdq_controller(void *ctrl_dev, int32_t dtype, const double *norm_in, const int64_t *seg_counts_dev,
                    int32_t n_seg, const void *ratio_dev, void *stream);
 
-/* On accept: y_mid and the quartic coefficients (rk_common.py:363-369, interp.py:1-22) and the
- * state commit y0 <- y1, k[0] <- k[S] (rk_common.py:338-352), one pass.  No-op on reject.
- * coeff[0..4] = e,d,c,b,a (state dtype). */
-int tdq_interp_fit_commit(void *ctrl_dev, const tdq_tableau *tab, int32_t dtype, void *y0, const void *y1,
-                          void *const *k, void *const *coeff, size_t n, void *stream);
-
-/* On accept: solution[j] for every requested t_j in (t0, t1] not yet emitted (interp.py:25-48 via
- * rk_common.py:243-250 / solvers.py:28-35).  solution is [n_out, n] in the state dtype. */
-int tdq_interp_eval(void *ctrl_dev, int32_t dtype, const void *const *coeff, void *solution, size_t n,
-                    void *stream);
+/* Lazy dense output of the attempt the controller just accepted (rk_common.py:363-369, interp.py:1-48 via
+ * rk_common.py:243-250 / solvers.py:28-35).  Does something only when an output time t_j fell into (t0, t1]
+ * or options.always_fit is set: forms y_mid and the quartic's coefficients from (y0, y1, k_0, k_S, the
+ * mid-point slots) -- y0/k_0 are the pair the accepted step started from -- writes solution[j] for every such
+ * t_j (solution is [n_out, n] in the state dtype) and, when coeff != NULL, stores coeff[0..4] = e,d,c,b,a. */
+int tdq_interp_fit_eval(void *ctrl_dev, const tdq_tableau *tab, int32_t dtype, const void *y1, const void *const *k,
+                        void *const *coeff, void *solution, size_t n, void *stream);
 /* Evaluate the current interpolant at one time (device float64 scalar) into out[n] (interp.py:25-48). */
 int tdq_interp_eval_at(void *ctrl_dev, int32_t dtype, const void *const *coeff, const double *t_dev, void *out,
                        size_t n, void *stream);
@@ -215,6 +253,20 @@ int tdq_interp_eval_at(void *ctrl_dev, int32_t dtype, const void *const *coeff, 
 int tdq_poly_eval(int32_t dtype, const void *const *coeff, double x, void *out, size_t n, void *stream);
 /* Reset the per-output-interval attempt counter (rk_common.py:245). */
 int tdq_ctrl_reset_interval(void *ctrl_dev, void *stream);
+
+/* ---- the adaptive loop itself on the device (solvers.py:28-35, rk_common.py:243-250) ----------- */
+/* The reference's `while next_t > t1: _adaptive_step()` is a host loop with a dozen syncs per iteration.
+ * Here one attempt is a CUDA graph (captured by the caller: stage combines, func, norm, controller, fit) and
+ * the loop is a conditional WHILE node around it: tdq_controller, the last decision of every attempt, calls
+ * cudaGraphSetConditional(handle, !halt) from the device, so a whole solve is ONE graph launch with no host
+ * in the loop and no attempt executed after the end.
+ * tdq_loop_create clones `body_graph` (a cudaGraph_t; it may be destroyed afterwards) into the body of a new
+ * executable graph; *handle_out goes into tdq_options.loop_handle (or tdq_ctrl_set_loop) of every solve that
+ * is launched with tdq_loop_launch, and must be 0 for attempts launched any other way. */
+int tdq_loop_create(void *body_graph, void **loop_out, uint64_t *handle_out);
+int tdq_loop_launch(void *loop, void *stream);
+int tdq_loop_destroy(void *loop);
+int tdq_ctrl_set_loop(void *ctrl_dev, uint64_t loop_handle, void *stream);
 
 /* ---- fixed grid: RK4 3/8 rule (fixed_grid.py:24-29, rk_common.py:110-118) and the other explicit
  *      fixed-step methods euler / midpoint / heun2 / heun3 (fixed_grid.py:6-60, rk_common.py:121-158) -- */

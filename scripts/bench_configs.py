@@ -64,7 +64,7 @@ def c3():
 def c4():
     for name in ("B1", "B5"):
         f, y0, t0 = P.detest(name)
-        yb = torch.tensor(y0, dtype=torch.float64).unsqueeze(-1).repeat(1, 4096).to(DEV)
+        yb = y0.unsqueeze(-1).repeat(*([1] * y0.dim()), 4096).to(DEV)
         t = torch.tensor([t0, 20.0], dtype=torch.float64, device=DEV)
         for tol in (1e-3, 1e-6, 1e-9):
             st = {}
@@ -85,18 +85,23 @@ def dopri8_roofline():
     _lib.check(lib.tdq_ctrl_init(eng.ctrl.data_ptr(), C.byref(eng.tab), C.byref(eng.opt), eng.t_out.data_ptr(), 0.0, 2,
                                  eng.mbox_dev, _stream()))
     _lib.check(lib.tdq_set_first_step(eng.ctrl.data_ptr(), 0.05, _stream()))
-    _lib.check(lib.tdq_prepare_attempt(eng.ctrl.data_ptr(), eng.dt_code, _stream()))
+    _lib.check(lib.tdq_prepare_attempt(eng.ctrl.data_ptr(), eng.dt_code, None, _stream()))
     ks = [torch.randn(n, device=DEV, dtype=torch.float64) * 1e-3 for _ in range(14)]
     y0 = torch.randn(n, device=DEV, dtype=torch.float64)
     outs = [torch.empty(n, device=DEV, dtype=torch.float64) for _ in range(2)]
     kp = _lib.ptr_array([k.data_ptr() for k in ks])
     ctrl, tab, dc = eng.ctrl.data_ptr(), C.byref(eng.tab), eng.dt_code
 
+    errp = torch.empty(n, device=DEV, dtype=torch.float64)
+
     def attempt():
-        for row in range(13):
+        for row in range(12):
             _lib.check(lib.tdq_stage_combine(ctrl, tab, dc, row, outs[row & 1].data_ptr(), y0.data_ptr(), kp, n, _stream()))
-        _lib.check(lib.tdq_error_norm(ctrl, tab, dc, y0.data_ptr(), outs[1].data_ptr(), kp, None, None, eng.seg_off,
-                                      eng.seg_len, 1, n, eng.partials.data_ptr(), eng.norm_out.data_ptr(), None, _stream()))
+        _lib.check(lib.tdq_stage_combine_final(ctrl, tab, dc, outs[1].data_ptr(), errp.data_ptr(), y0.data_ptr(), kp, n,
+                                               _stream()))
+        _lib.check(lib.tdq_error_norm_commit(ctrl, dc, errp.data_ptr(), ks[13].data_ptr(), y0.data_ptr(), outs[1].data_ptr(),
+                                             None, None, None, 0, 0, 1, n, eng.partials.data_ptr(),
+                                             eng.norm_out.data_ptr(), None, _stream()))
     ms = timed(lambda: [attempt() for _ in range(10)], reps=3, warm=1) / 10
     nbytes = 105 * n * 8                                     # 94 + 11 N*s
     peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"] if os.path.exists(

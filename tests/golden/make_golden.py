@@ -11,7 +11,8 @@ Outputs (committed):
     linear_batch.pt       C2-shaped batched linear ODE at a small batch: solution, dt sequence, accept flags
     spiral_rk4.pt         C1: rk4 on the cubic spiral, B=1024, selected output rows
     adjoint_mlp.pt        odeint_adjoint gradients for a small MLP field
-    detest.pt             DETEST classes A/B: NFE and end states at rtol=atol in {1e-3, 1e-6, 1e-9}
+    detest.pt             all 25 DETEST problems: NFE, end states and RMS error vs dopri5@1e-12 for dopri5/dopri8 at
+                          rtol=atol in {1e-3, 1e-6, 1e-9} (+ dopri8 at 1e-12)
     options.pt            step_t / min_step / max_step / first_step / tuple-state / vector-tol cases
 """
 import json
@@ -151,19 +152,39 @@ def adjoint_mlp():
 
 
 def detest():
-    out = {}
-    for name in P.DETEST_NAMES:
-        f, y0, t0 = P.detest(name)
-        y0 = torch.tensor(y0, dtype=torch.float64)
-        if name.startswith("A"):
-            y0 = y0[0]
-        t = torch.tensor([t0, 20.0], dtype=torch.float64)
-        for method in ("dopri5", "dopri8"):
-            for tol in (1e-3, 1e-6, 1e-9):
-                rec = Rec(f)
-                with torch.no_grad():
-                    y = torchdiffeq.odeint(rec, y0, t, method=method, rtol=tol, atol=tol)
-                out["%s/%s/%g" % (name, method, tol)] = {"y": y[-1].clone(), "nfe": rec.nfe}
+    """All 25 DETEST problems (tests/DETEST/detest.py:8-315) through the UNMODIFIED reference, using the reference's OWN
+    problem definitions (so the goldens also pin tests/problems.py's restatement of them): NFE and end state for dopri5
+    and dopri8 at rtol = atol in {1e-3, 1e-6, 1e-9}, dopri8 at 1e-12, and the dopri5 @ 1e-12 solution run.py:37-41 uses as
+    ground truth with the RMS error run.py:47 reports against it."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("ref_detest", "/root/reference/tests/DETEST/detest.py")
+    rd = importlib.util.module_from_spec(spec)
+    old = torch.get_default_dtype()
+    torch.set_default_dtype(torch.float64)                       # run.py:8
+    try:
+        spec.loader.exec_module(rd)
+        out = {}
+        for name in P.DETEST_NAMES:
+            f, init, _ = getattr(rd, name)()
+            t0, y0 = init()
+            mine, my0, mt0 = P.detest(name)
+            assert torch.equal(y0, my0) and float(t0) == mt0, name
+            probe = y0 + 0.125
+            assert torch.equal(f(torch.tensor(0.5), probe.clone()), mine(torch.tensor(0.5), probe.clone())), name
+            t = torch.stack([t0, torch.tensor(20.)])
+            with torch.no_grad():
+                truth = torchdiffeq.odeint(f, y0, t, atol=1e-12, rtol=1e-12, method="dopri5")[1]
+            out["%s/truth" % name] = {"y": truth.clone()}
+            for method, tols in (("dopri5", (1e-3, 1e-6, 1e-9)), ("dopri8", (1e-3, 1e-6, 1e-9, 1e-12))):
+                for tol in tols:
+                    rec = Rec(f)
+                    with torch.no_grad():
+                        y = torchdiffeq.odeint(rec, y0, t, method=method, rtol=tol, atol=tol)
+                    err = torch.sqrt(torch.mean((truth - y[1]) ** 2))
+                    out["%s/%s/%g" % (name, method, tol)] = {"y": y[-1].clone(), "nfe": rec.nfe, "err": float(err)}
+                    print(name, method, tol, rec.nfe, float(err), flush=True)
+    finally:
+        torch.set_default_dtype(old)
     torch.save(out, os.path.join(HERE, "detest.pt"))
 
 

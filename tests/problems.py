@@ -2,9 +2,10 @@
 
 The four analytic problems and their parameters follow the reference's tests/problems.py:7-61
 (ConstantODE a=0.2 b=3.0, SineODE, LinearODE with the seeded skew construction, ExpODE); the DETEST
-entries are the published non-stiff test problems of Hull, Enright, Fellen & Sedgwick (1972), classes
-A and B, which the reference carries in tests/DETEST/detest.py:8-117.  They are written batch-first so the
-same definition serves the reference on CPU (golden generation), the oracle and the CUDA path.
+entries are the 25 published non-stiff test problems of Hull, Enright, Fellen & Sedgwick (1972), classes
+A-E, which the reference carries in tests/DETEST/detest.py:8-315 (checked value-for-value against that file
+by tests/golden/make_golden.py).  They take an optional trailing batch dimension, so the same definition
+serves the oracle on CPU and BASELINE config 4's batched form on the CUDA path.
 """
 import math
 
@@ -133,37 +134,150 @@ class MLPField(torch.nn.Module):
         return self.net(y)
 
 
-# ---- DETEST classes A and B, trailing batch dimension: y has shape [d, B] (or [B] for class A) -----------
+# ---- DETEST (Hull, Enright, Fellen & Sedgwick 1972), all 25 problems of tests/DETEST/detest.py:8-315 --------------
+# Written so that ONE definition serves the unbatched form the reference uses (y of shape [d], [] for class A,
+# [2, 3, 5] for C5) and BASELINE config 4's batched form with a TRAILING batch dimension (y of shape [d, B]):
+# they index y[i] and stack on dim 0, matrices act from the left.  Constants are float64 (run.py:8 makes float64
+# the default dtype) and follow the state to its device.
+def _banded(n, diag, lower, upper=None):
+    A = torch.zeros(n, n, dtype=torch.float64)
+    A.view(-1)[::n + 1] = diag
+    A.view(-1)[n::n + 1] = lower
+    if upper is not None:
+        A.view(-1)[1::n + 1] = upper
+    return A
+
+
+class _MatField:
+    """dy/dt = A y (detest.py:58-167: torch.mv(A, y)); A @ y also takes y [d, B]."""
+
+    def __init__(self, A):
+        self.A, self._dev = A, {}
+
+    def __call__(self, t, y):
+        A = self._dev.get(y.device)
+        if A is None:
+            A = self._dev[y.device] = self.A.to(y.device)
+        return A @ y
+
+
+class _FiveBody:
+    """C5, the five outer planets (detest.py:170-214), for y of shape [2, 3, 5] or [2, 3, 5, B]."""
+    k2 = 2.95912208286
+    m0 = 1.00000597682
+    m = [0.000954786104043, 0.000285583733151, 0.0000437273164546, 0.0000517759138449, 0.00000277777777778]
+
+    def __init__(self):
+        self._dev = {}
+
+    def __call__(self, t, y):
+        shape = y.shape
+        yb = y.reshape(2, 3, 5, -1)
+        m = self._dev.get(y.device)
+        if m is None:
+            m = self._dev[y.device] = torch.tensor(self.m, dtype=torch.float64, device=y.device)
+        dy, p = yb[1], yb[0]                                            # [3, 5, B]
+        r = torch.sqrt(torch.sum(p ** 2, 0))                            # [5, B]
+        d = torch.sqrt(torch.sum((p[:, :, None] - p[:, None, :]) ** 2, 0))      # [5, 5, B]
+        F = m.view(1, 1, 5, 1) * ((p[:, None, :] - p[:, :, None]) / (d * d * d)[None] + p[:, None, :] / (r * r * r)[None, None])
+        eye = torch.eye(5, dtype=torch.bool, device=y.device).view(1, 5, 5, 1)
+        F = torch.where(eye, torch.zeros((), dtype=F.dtype, device=F.device), F)     # F.view(3, 25)[:, ::6] = 0
+        ddy = self.k2 * (-(self.m0 + m.view(1, 5, 1)) * p / (r * r * r)[None]) + F.sum(2)
+        return torch.stack([dy, ddy], 0).reshape(shape)
+
+
+def _c5_init():
+    y0 = torch.tensor([
+        3.42947415189, 3.35386959711, 1.35494901715, 6.64145542550, 5.97156957878, 2.18231499728, 11.2630437207,
+        14.6952576794, 6.27960525067, -30.1552268759, 165699966404, 1.43785752721, -21.1238353380, 28.4465098142,
+        15.388265967], dtype=torch.float64).view(5, 3).transpose(0, 1)          # the 165699966404 is the reference's (detest.py:219)
+    dy0 = torch.tensor([
+        -.557160570446, .505696783289, .230578543901, -.415570776342, .365682722812, .169143213293, -.325325669158,
+        .189706021964, .0877265322780, -.0240476254170, -.287659532608, -.117219543175, -.176860753121,
+        -.216393453025, -.0148647893090], dtype=torch.float64).view(5, 3).transpose(0, 1)
+    return torch.stack([y0, dy0], 0).contiguous()
+
+
+def _orbit(eps):
+    def f(t, y):
+        r = (y[0] ** 2 + y[1] ** 2) ** (3 / 2)
+        return torch.stack([y[2], y[3], -y[0] / r, -y[1] / r])
+    return f, [1 - eps, 0, 0, math.sqrt((1 + eps) / (1 - eps))]
+
+
 def detest(name):
-    """Returns (func, y0 [d] float64 list, t0).  Integrate to t = 20 (run.py:22-55)."""
+    """Returns (func, y0 float64 tensor in the reference's shape, t0).  Integrate to t = 20 (run.py:22-55)."""
+    T = lambda v: torch.tensor(v, dtype=torch.float64)
     if name == "A1":
-        return (lambda t, y: -y), [1.0], 0.0
+        return (lambda t, y: -y), T(1.0), 0.0
     if name == "A2":
-        return (lambda t, y: -y ** 3 / 2), [1.0], 0.0
+        return (lambda t, y: -y ** 3 / 2), T(1.0), 0.0
     if name == "A3":
-        return (lambda t, y: y * torch.cos(t)), [1.0], 0.0
+        return (lambda t, y: y * torch.cos(t)), T(1.0), 0.0
     if name == "A4":
-        return (lambda t, y: y / 4 * (1 - y / 20)), [1.0], 0.0
+        return (lambda t, y: y / 4 * (1 - y / 20)), T(1.0), 0.0
     if name == "A5":
-        return (lambda t, y: (y - t) / (y + t)), [4.0], 0.0
+        return (lambda t, y: (y - t) / (y + t)), T(4.0), 0.0
     if name == "B1":
         def f(t, y):
             return torch.stack([2 * (y[0] - y[0] * y[1]), -(y[1] - y[0] * y[1])])
-        return f, [1.0, 3.0], 0.0
+        return f, T([1.0, 3.0]), 0.0
+    if name == "B2":
+        return _MatField(T([[-1., 1., 0.], [1., -2., 1.], [0., 1., -1.]])), T([2., 0., 1.]), 0.0
     if name == "B3":
         def f(t, y):
             return torch.stack([-y[0], y[0] - y[1] * y[1], y[1] * y[1]])
-        return f, [1.0, 0.0, 0.0], 0.0
+        return f, T([1.0, 0.0, 0.0]), 0.0
     if name == "B4":
         def f(t, y):
             a = torch.sqrt(y[0] * y[0] + y[1] * y[1])
             return torch.stack([-y[1] - y[0] * y[2] / a, y[0] - y[1] * y[2] / a, y[0] / a])
-        return f, [3.0, 0.0, 0.0], 0.0
+        return f, T([3.0, 0.0, 0.0]), 0.0
     if name == "B5":
         def f(t, y):
             return torch.stack([y[1] * y[2], -y[0] * y[2], -0.51 * y[0] * y[1]])
-        return f, [0.0, 1.0, 1.0], 0.0
+        return f, T([0.0, 1.0, 1.0]), 0.0
+    if name in ("C1", "C2", "C3", "C4"):
+        n = 51 if name == "C4" else 10
+        if name == "C1":
+            A = torch.zeros(10, 10, dtype=torch.float64)
+            A.view(-1)[:-1:11] = -1
+            A.view(-1)[10::11] = 1
+        elif name == "C2":
+            A = torch.zeros(10, 10, dtype=torch.float64)
+            A.view(-1)[:-1:11] = torch.linspace(-1, -9, 9, dtype=torch.float64)
+            A.view(-1)[10::11] = torch.linspace(1, 9, 9, dtype=torch.float64)
+        else:
+            A = _banded(n, -2, 1, 1)
+        y0 = torch.zeros(n, dtype=torch.float64)
+        y0[0] = 1
+        return _MatField(A), y0, 0.0
+    if name == "C5":
+        return _FiveBody(), _c5_init(), 0.0
+    if name in ("D1", "D2", "D3", "D4", "D5"):
+        f, y0 = _orbit({"D1": 0.1, "D2": 0.3, "D3": 0.5, "D4": 0.7, "D5": 0.9}[name])
+        return f, T(y0), 0.0
+    if name == "E1":
+        def f(t, y):
+            return torch.stack([y[1], -(y[1] / (t + 1) + (1 - 0.25 / (t + 1) ** 2) * y[0])])
+        return f, T([.671396707141803, .0954005144474744]), 0.0
+    if name == "E2":
+        def f(t, y):
+            return torch.stack([y[1], (1 - y[0] ** 2) * y[1] - y[0]])
+        return f, T([2., 0.]), 0.0
+    if name == "E3":
+        def f(t, y):
+            return torch.stack([y[1], y[0] ** 3 / 6 - y[0] + 2 * torch.sin(2.78535 * t)])
+        return f, T([0., 0.]), 0.0
+    if name == "E4":
+        def f(t, y):
+            return torch.stack([y[1], .32 - .4 * y[1] ** 2])
+        return f, T([30., 0.]), 0.0
+    if name == "E5":
+        def f(t, y):
+            return torch.stack([y[1], torch.sqrt(1 + y[1] ** 2) / (25 - t)])
+        return f, T([0., 0.]), 0.0
     raise KeyError(name)
 
 
-DETEST_NAMES = ("A1", "A2", "A3", "A4", "A5", "B1", "B3", "B4", "B5")
+DETEST_NAMES = tuple(c + i for c in "ABCDE" for i in "12345")

@@ -27,7 +27,7 @@ def test_header_symbols_exported(lib):
     assert not missing, missing
     # and the Python binding covers the whole header
     assert declared == set(lib.EXPORTED_SYMBOLS), declared ^ set(lib.EXPORTED_SYMBOLS)
-    assert L.tdq_abi_version() == 1
+    assert L.tdq_abi_version() == lib.ABI_VERSION == 2
 
 
 def test_struct_sizes(lib):

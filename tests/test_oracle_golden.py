@@ -128,14 +128,16 @@ def test_adjoint(key):
 DET = ld("detest.pt")
 
 
-@pytest.mark.parametrize("key", sorted(DET))
+DET_KEYS = sorted(k for k in DET if not k.endswith("/truth"))
+
+
+@pytest.mark.parametrize("key", DET_KEYS)
 def test_detest(key):
+    """All 25 DETEST problems (tests/DETEST/detest.py:8-315, run.py:22-55): NFE against the reference's, y(20) against
+    the reference's, and the RMS error against dopri5 @ 1e-12 that run.py:47 reports."""
     name, method, tol = key.split("/")
     tol = float(tol)
     f, y0, t0 = P.detest(name)
-    y0 = torch.tensor(y0, dtype=torch.float64)
-    if name.startswith("A"):
-        y0 = y0[0]
     cf = O.Counter(f)
     with torch.no_grad():
         y = O.odeint_adaptive(cf, y0, torch.tensor([t0, 20.0], dtype=torch.float64), method, rtol=tol, atol=tol)
@@ -145,7 +147,10 @@ def test_detest(key):
     # y(20) is INTERPOLATED inside the last step (rk_common.py:250) by a 4th-order polynomial, so for
     # dopri8's long steps it is only as accurate as that interpolant and moves with the step sequence
     ytol = max(100 * tol, 1e-3 if method == "dopri8" else 1e-6)
-    assert torch.allclose(y[-1], DET[key]["y"], rtol=ytol, atol=ytol)
+    scale = max(1.0, float(DET[key]["y"].abs().max()))           # C5 carries one coordinate of 1.7e11 (detest.py:219)
+    assert torch.allclose(y[-1], DET[key]["y"], rtol=ytol, atol=ytol * scale)
+    err = float(torch.sqrt(torch.mean((DET[name + "/truth"]["y"] - y[-1]) ** 2)))
+    assert err <= 10 * DET[key]["err"] + 1e-9 * scale, (err, DET[key]["err"])
 
 
 @pytest.mark.parametrize("key", ["min_step", "max_step", "first_step", "step_t", "factors"])

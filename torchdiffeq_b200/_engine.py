@@ -3,18 +3,27 @@
 What the reference does per attempt in ~570 ATen calls and 15-20 host syncs
 (rk_common.py:266-361) is here a fixed launch sequence
 
-    S x (tdq_stage_combine ; func) ; tdq_error_norm ; [all-reduce] ; tdq_controller ;
-    tdq_interp_fit_commit ; tdq_interp_eval
+    S x (tdq_stage_combine ; func) ; tdq_error_norm_commit ; [all-reduce] ; tdq_controller ;
+    tdq_interp_fit_eval
 
-whose every scalar decision (accept/reject, next dt, output cursor, termination, failure status)
-is taken on the device.  The sequence is the same for every attempt, so it is captured once in a
-CUDA graph and replayed; the host only reads a mapped-memory mailbox to learn when to stop.
+(the last combine is tdq_stage_combine_final, which also emits the prefix of the error estimate) whose
+every scalar decision (accept/reject, next dt, output cursor, termination, failure status) is taken on
+the device.  The sequence is the same for every attempt, so it is captured once in a CUDA graph; the
+graph then becomes the body of a device-side WHILE (tdq_loop_create) and a whole solve is one graph
+launch.  Where that is not possible the graph is replayed by the host, which reads a mapped-memory
+mailbox to learn when to stop.
+
+State buffers: the accepted state y0 and f0 = k_0 live in ybuf[par] / kbuf[par]; the error-norm kernel
+writes each attempt's candidate (y1, k_S) into the other pair and the controller accepts by flipping
+`par` -- there is no commit copy, and the interpolant is fitted only for steps that contain an output
+time (or when the caller keeps dense output).
 
 Execution modes (options of our path only, SURVEY.md section 5 "config"):
     graph      True/False/'auto'  capture the attempt body in a CUDA graph.
     run_ahead  D >= 0             attempts the host may queue beyond the last one it has seen finish.
                                   0 = lock step: func is called exactly 2 + S*attempts times in the
                                   reference's order (needed for callbacks / NFE counters).
+    device_loop True/False/'auto' run the captured attempt inside the device-side while loop.
 """
 import ctypes as C
 import time
@@ -160,7 +169,7 @@ class AdaptiveEngine:
                  safety=0.9, ifactor=10.0, dfactor=0.2, max_num_steps=2 ** 31 - 1,
                  rtol_vec=None, atol_vec=None, norm_fn=None, q_view=None,
                  graph="auto", run_ahead=2, reduce_fn=None, n_global=None, seg_counts_global=None,
-                 agree_fn=None, exchange=None, callbacks=None):
+                 agree_fn=None, exchange=None, callbacks=None, keep_interp=False, device_loop="auto"):
         if device.type != "cuda":
             raise _lib.TdqError("torchdiffeq_b200 runs on CUDA devices only (got %s); there is no CPU path" % device)
         if dtype not in _DTYPES:
@@ -186,6 +195,8 @@ class AdaptiveEngine:
         self.callbacks = callbacks or {}
         self.graph_opt = graph
         self.run_ahead = int(run_ahead)
+        self.device_loop = device_loop
+        self.keep_interp = bool(keep_interp)   # dense output / events: store the interpolant of every accepted step
         self.jump_t = jump_t
         if self.callbacks or (jump_t is not None and jump_t.numel() > 0):
             # both need the host between attempts: callbacks by definition, jump_t because f is re-evaluated on
@@ -195,12 +206,17 @@ class AdaptiveEngine:
 
         segs = segs if segs is not None else [(0, self.n)]
         self.n_seg = len(segs)
-        self.seg_off = _lib.i64_array([int(o) for o, _ in segs])
-        self.seg_len = _lib.i64_array([int(l) for _, l in segs])
         n_real = sum(int(l) for _, l in segs)
         counts = seg_counts_global if seg_counts_global is not None else [int(l) for _, l in segs]
         self.seg_counts = torch.tensor(counts, dtype=torch.int64, device=device)
-        max_seg = max(int(l) for _, l in segs)
+        # one segment covering everything needs no table; anything else (tuple states, the adjoint's augmented
+        # state with one segment per parameter tensor -- any number of them) gets a chunk table on the device
+        if len(segs) == 1 and int(segs[0][0]) == 0 and int(segs[0][1]) == self.n:
+            self.norm_table, self.n_chunks, self.table_aligned = None, 0, 0
+        else:
+            words = _lib.norm_table(segs, self.n, _DTYPES[dtype])
+            self.norm_table = torch.tensor(words, dtype=torch.int64, device=device)
+            self.n_chunks, self.table_aligned = int(words[1]), int(words[3])
 
         self.rtol_vec = rtol_vec
         self.atol_vec = atol_vec
@@ -220,13 +236,20 @@ class AdaptiveEngine:
         self.tstage = self.ctrl[o:o + 8 * _lib.TDQ_MAX_K].view(dtype)
         o = self.lib.tdq_ctrl_taux_offset()
         self.taux = self.ctrl[o:o + 32].view(dtype)
-        self.y0w = torch.zeros(self.n, **kw)
+        self.ybuf = [torch.zeros(self.n, **kw) for _ in range(2)]      # pointer table: accepted state ...
+        self.kbuf = [torch.zeros(self.n, **kw) for _ in range(2)]      # ... and its derivative f0 = k_0
+        self.opt.ybuf[0], self.opt.ybuf[1] = self.ybuf[0].data_ptr(), self.ybuf[1].data_ptr()
+        self.opt.kbuf[0], self.opt.kbuf[1] = self.kbuf[0].data_ptr(), self.kbuf[1].data_ptr()
+        self.opt.always_fit = 1 if self.keep_interp else 0
         self.ytmp = torch.zeros(self.n, **kw)
         self.y1 = torch.zeros(self.n, **kw)
-        self.k0 = torch.zeros(self.n, **kw)
-        self.coeff = [torch.zeros(self.n, **kw) for _ in range(5)]
-        self.coeff_ptrs = _lib.ptr_array([c.data_ptr() for c in self.coeff])
-        self.partials = torch.zeros(self.lib.tdq_norm_partials_len(max_seg, self.n_seg), dtype=torch.float64,
+        self.errp = torch.zeros(self.n, **kw)                          # prefix of the error estimate
+        if self.keep_interp:
+            self.coeff = [torch.zeros(self.n, **kw) for _ in range(5)]
+            self.coeff_ptrs = _lib.ptr_array([c.data_ptr() for c in self.coeff])
+        else:
+            self.coeff, self.coeff_ptrs = [], None
+        self.partials = torch.zeros(self.lib.tdq_norm_partials_len(self.n, self.n_chunks), dtype=torch.float64,
                                     device=device)
         self.norm_out = torch.zeros(self.n_seg + 1, dtype=torch.float64, device=device)
         self.dsum = [torch.zeros(self.n_seg + 1, dtype=torch.float64, device=device) for _ in range(3)]
@@ -245,6 +268,9 @@ class AdaptiveEngine:
         self._graph = None
         self._graph_failed = False
         self._graph_keep = None
+        self._loop = None                # tdq_loop handle: the captured attempt inside a device-side while
+        self._loop_handle = 0
+        self._loop_failed = False
         self._always_copy = False        # set when func is seen to reuse its output buffer (see _call_fn)
         self.capture_in_solve = True     # False: only a prime()d graph is used (solves run inside autograd backward)
         self.n_attempts = 0              # attempts that did work (from the mailbox counters)
@@ -256,15 +282,15 @@ class AdaptiveEngine:
     def __del__(self):
         try:
             if self.mbox_host:
-                self._graph = None
                 torch.cuda.synchronize(self.device)
+                self._drop_graph()
                 self.lib.tdq_mailbox_destroy(self.mbox_host)
                 self.mbox_host = None
         except Exception:
             pass
 
     # ---------------------------------------------------------------------------------------
-    def _call_fn(self, t, y, slot, taken=()):
+    def _call_fn(self, t, y, slot, taken=(), dst=None):
         """Evaluate func and return a tensor holding the flat result that is safe to keep as stage
         slot `slot` (rk_common.py:80-81 writes it into k[..., slot]): the reference COPIES f into k, so an
         output that aliases the solver's buffers, func's input, or an earlier stage's output (a func that
@@ -289,9 +315,27 @@ class AdaptiveEngine:
                 f = buf
             return f
         # tuple of pieces -> one pack launch into an engine-owned slot
-        buf = self._slot(slot)
+        buf = dst if dst is not None else self._slot(slot)
         self.launches += pack_pieces(self.lib, self.dt_code, self.dtype, buf, f, self.pieces)
         return buf
+
+    @property
+    def y0w(self):
+        """The accepted state (valid between attempts in lock step, and after a solve)."""
+        return self.ybuf[self.mbox_host.contents.par & 1]
+
+    @property
+    def k0(self):
+        return self.kbuf[self.mbox_host.contents.par & 1]
+
+    def _drop_graph(self):
+        if self._loop is not None:
+            try:
+                self.lib.tdq_loop_destroy(self._loop)
+            except Exception:
+                pass
+        self._loop, self._loop_handle = None, 0
+        self._graph, self._graph_keep = None, None
 
     def _launch(self, rc):
         _lib.check(rc)
@@ -304,7 +348,7 @@ class AdaptiveEngine:
 
     def _aliases(self, f):
         if self._own_ptrs is None:
-            own = [self.y0w, self.ytmp, self.y1, self.k0, self.solution] + self.coeff
+            own = self.ybuf + self.kbuf + [self.ytmp, self.y1, self.errp, self.solution] + self.coeff
             self._own_ptrs = {t.untyped_storage().data_ptr() for t in own}
         return f.untyped_storage().data_ptr() in self._own_ptrs
 
@@ -315,10 +359,11 @@ class AdaptiveEngine:
     def _sumsq(self, x, x2, out):
         self._launch(self.lib.tdq_scaled_sumsq(
             self.ctrl.data_ptr(), self.dt_code, x.data_ptr(), x2.data_ptr() if x2 is not None else None,
-            self.y0w.data_ptr(),
+            None,                                                     # y0: the control block's current pair
             self.rtol_vec.data_ptr() if self.rtol_vec is not None else None,
             self.atol_vec.data_ptr() if self.atol_vec is not None else None,
-            self.seg_off, self.seg_len, self.n_seg, self.n, self.partials.data_ptr(), out.data_ptr(), _stream()))
+            self.norm_table.data_ptr() if self.norm_table is not None else None, self.n_chunks, self.table_aligned,
+            self.n_seg, self.n, self.partials.data_ptr(), out.data_ptr(), _stream()))
         self._reduce(out)
 
     # ---------------------------------------------------------------------------------------
@@ -332,24 +377,32 @@ class AdaptiveEngine:
     def _attempt_front_once(self):
         lib, ctrl, tab, dc, st = self.lib, self.ctrl.data_ptr(), C.byref(self.tab), self.dt_code, _stream()
         S = self.S
-        k = [self.k0.data_ptr()] + [None] * S
-        keep = [self.k0]
+        k = [None] * (S + 1)             # k[0] = NULL: the kernels read k_0 (and y0) through the pointer table
+        keep = []
         for i in range(S):
-            out = self.y1 if (i == S - 1 and self.fsal) else self.ytmp
-            self._launch(lib.tdq_stage_combine(ctrl, tab, dc, i, out.data_ptr(), self.y0w.data_ptr(),
-                                             _lib.ptr_array(k), self.n, st))
+            if i == S - 1 and self.fsal:
+                # the row that yields y1, fused with the available prefix of the error estimate (rk_common.py:83-89)
+                out = self.y1
+                self._launch(lib.tdq_stage_combine_final(ctrl, tab, dc, out.data_ptr(), self.errp.data_ptr(), None,
+                                                         _lib.ptr_array(k), self.n, st))
+            else:
+                out = self.ytmp
+                self._launch(lib.tdq_stage_combine(ctrl, tab, dc, i, out.data_ptr(), None, _lib.ptr_array(k), self.n,
+                                                   st))
             f = self._call_fn(self.tstage[i], out, i + 1, taken=k)
             keep.append(f)
             k[i + 1] = f.data_ptr()
         if not self.fsal:
-            self._launch(lib.tdq_stage_combine(ctrl, tab, dc, S, self.y1.data_ptr(), self.y0w.data_ptr(),
-                                             _lib.ptr_array(k), self.n, st))
+            self._launch(lib.tdq_stage_combine_final(ctrl, tab, dc, self.y1.data_ptr(), self.errp.data_ptr(), None,
+                                                     _lib.ptr_array(k), self.n, st))
         kp = _lib.ptr_array(k)
-        self._launch(lib.tdq_error_norm(
-            ctrl, tab, dc, self.y0w.data_ptr(), self.y1.data_ptr(), kp,
+        # error ratio + candidate commit (y1 -> ybuf[par^1], k_S -> kbuf[par^1]) in one pass
+        self._launch(lib.tdq_error_norm_commit(
+            ctrl, dc, self.errp.data_ptr(), k[S], None, self.y1.data_ptr(),
             self.rtol_vec.data_ptr() if self.rtol_vec is not None else None,
             self.atol_vec.data_ptr() if self.atol_vec is not None else None,
-            self.seg_off, self.seg_len, self.n_seg, self.n, self.partials.data_ptr(), self.norm_out.data_ptr(),
+            self.norm_table.data_ptr() if self.norm_table is not None else None, self.n_chunks, self.table_aligned,
+            self.n_seg, self.n, self.partials.data_ptr(), self.norm_out.data_ptr(),
             self.qbuf.data_ptr() if self.qbuf is not None else None, st))
         ratio_ptr = None
         if self.norm_fn is not None:
@@ -364,11 +417,11 @@ class AdaptiveEngine:
         return k, kp, keep
 
     def _attempt_back(self, kp):
-        """Accepted-step work (predicated on the device accept flag)."""
-        lib, ctrl, tab, dc, st = self.lib, self.ctrl.data_ptr(), C.byref(self.tab), self.dt_code, _stream()
-        self._launch(lib.tdq_interp_fit_commit(ctrl, tab, dc, self.y0w.data_ptr(), self.y1.data_ptr(), kp,
-                                             self.coeff_ptrs, self.n, st))
-        self._launch(lib.tdq_interp_eval(ctrl, dc, self.coeff_ptrs, self.solution.data_ptr(), self.n, st))
+        """Dense output of the step just accepted -- a no-op on the device unless an output time fell into it (or
+        the caller keeps the interpolant of every step)."""
+        self._launch(self.lib.tdq_interp_fit_eval(self.ctrl.data_ptr(), C.byref(self.tab), self.dt_code,
+                                                  self.y1.data_ptr(), kp, self.coeff_ptrs, self.solution.data_ptr(),
+                                                  self.n, _stream()))
 
     def _attempt(self):
         k, kp, keep = self._attempt_front()
@@ -400,16 +453,35 @@ class AdaptiveEngine:
             raise SolverFailure("max_num_steps exceeded ({}>={})".format(self.opt.max_num_steps, self.opt.max_num_steps))
         raise SolverFailure("solver failed with status %d" % s)
 
+    def _lockstep_mode(self):
+        return bool(self.callbacks) or self.run_ahead == 0
+
+    def _use_loop(self):
+        """Run this solve inside the device-side while loop?  Needs the captured attempt and a body without
+        collectives launched by the host between attempts."""
+        return (self._loop is not None and not self._lockstep_mode() and self.agree_fn is None
+                and self.norm_fn is None)
+
     def solve(self, y0_flat, t64, t_start=None):
         """Integrate from t64[0] through t64[-1] (ascending float64 device tensor); returns
         solution [len(t), n] (solvers.py:28-35).  The returned tensor is owned by the engine and is
         overwritten by the next solve() with the same number of output times."""
-        n_out = self._begin(y0_flat, t64, t_start)
-        if n_out > 1:
-            if self.callbacks or self.run_ahead == 0:
-                self._loop_lockstep()
-            else:
-                self._loop_run_ahead()
+        try:
+            n_out = self._begin(y0_flat, t64, t_start, loop=self._use_loop())
+            if n_out > 1:
+                if self._lockstep_mode():
+                    self._loop_lockstep()
+                else:
+                    self._loop_run_ahead()
+        except BaseException:
+            # attempts may still be queued: let them drain before anybody resets the mailbox, and do not let a
+            # half-finished engine be reused (the caller evicts it from the cache)
+            self.poisoned = True
+            try:
+                torch.cuda.current_stream().synchronize()
+            except Exception:
+                pass
+            raise
         mb = self.mbox_host.contents
         self.n_accept, self.n_reject = int(mb.n_accept), int(mb.n_reject)
         self.n_attempts = self.n_accept + self.n_reject
@@ -420,7 +492,7 @@ class AdaptiveEngine:
         attempt, then capture).  Used by odeint_adjoint to capture the backward step body during the
         FORWARD call: capturing inside autograd's backward is unsafe (a re-entrant engine call may run
         unrelated nodes of the outer graph on the legacy stream in the middle of the capture)."""
-        if self.graph_opt not in (True, "auto") or self.callbacks or self.run_ahead == 0:
+        if self.graph_opt not in (True, "auto") or self._lockstep_mode():
             return False
         n_out = self._begin(y0_flat, t64, t_start)
         if n_out <= 1:
@@ -430,7 +502,7 @@ class AdaptiveEngine:
         torch.cuda.current_stream().synchronize()
         return self._graph is not None
 
-    def _begin(self, y0_flat, t64, t_start=None):
+    def _begin(self, y0_flat, t64, t_start=None, loop=False):
         """Everything of a solve that precedes the first attempt (rk_common.py:166-241)."""
         lib = self.lib
         self.nfe_total += self.nfe
@@ -440,22 +512,20 @@ class AdaptiveEngine:
         if getattr(self, "solution", None) is None or self.solution.shape[0] != n_out:
             # a captured graph holds this buffer's address: a new shape invalidates it
             self.solution = torch.empty(n_out, self.n, dtype=self.dtype, device=self.device)
-            self._graph = None
-            self._graph_keep = None
+            self._drop_graph()
             self._own_ptrs = None
+            loop = False
         self.solution[0].copy_(y0_flat)
-        self.y0w.copy_(y0_flat)
-        if not bool(torch.isfinite(self.y0w).all()):                      # rk_common.py:287 on the first attempt
-            if n_out > 1:
-                # the reference evaluates f0 and the initial step before it asserts; results are unaffected
-                raise SolverFailure("non-finite values in state `y`: {}".format(self.y0w))
+        self.ybuf[0].copy_(y0_flat)
         st = _stream()
-        self.mbox_host.contents.seq = 0
-        self.mbox_host.contents.status = 0
-        self.mbox_host.contents.done = 0
-        t_start = float(t64[0]) if t_start is None else float(t_start)
+        mb = self.mbox_host.contents
+        mb.seq, mb.status, mb.done, mb.par, mb.accept = 0, 0, 0, 0, 0
+        mb.n_accept, mb.n_reject = 0, 0
+        if t_start is None:
+            t_start = float(t64[0])                                   # callers pass it whenever they hold t on the host
+        self.opt.loop_handle = self._loop_handle if loop else 0
         _lib.check(lib.tdq_ctrl_init(self.ctrl.data_ptr(), C.byref(self.tab), C.byref(self.opt),
-                                     self.t_out.data_ptr(), t_start, n_out, self.mbox_dev, st))
+                                     self.t_out.data_ptr(), float(t_start), n_out, self.mbox_dev, st))
         if self.exchange is not None:
             self.exchange.arm(self.ctrl.data_ptr(), st)
         if self.jump_t is not None and self.jump_t.numel() > 0:
@@ -467,28 +537,30 @@ class AdaptiveEngine:
         dc, ctrl = self.dt_code, self.ctrl.data_ptr()
 
         # _before_integrate: f0 and the initial step (rk_common.py:213-221, misc.py:36-77)
-        f0 = self._call_fn(self.taux[0], self.y0w, 0)
-        if f0.data_ptr() != self.k0.data_ptr():
-            self.k0.copy_(f0)
+        f0 = self._call_fn(self.taux[0], self.ybuf[0], 0, dst=self.kbuf[0])
+        if f0.data_ptr() != self.kbuf[0].data_ptr():
+            self.kbuf[0].copy_(f0)
         del f0
+        # d0's pass over y0 also counts its non-finite elements: rk_common.py:287 for the first attempt is then
+        # checked on the device by tdq_prepare_attempt, where the reference asserts it (no host sync here)
+        self._sumsq(self.ybuf[0], None, self.dsum[0])
         if self.first_step is None:
             if self.norm_fn is not None:
                 self._initial_step_custom_norm()
             else:
-                self._sumsq(self.y0w, None, self.dsum[0])
-                self._sumsq(self.k0, None, self.dsum[1])
+                self._sumsq(self.kbuf[0], None, self.dsum[1])
                 self._launch(lib.tdq_initial_step_h0(ctrl, dc, self.dsum[0].data_ptr(), self.dsum[1].data_ptr(),
                                                    self.seg_counts.data_ptr(), self.n_seg, st))
-                self._launch(lib.tdq_initial_step_probe(ctrl, dc, self.ytmp.data_ptr(), self.y0w.data_ptr(),
-                                                      self.k0.data_ptr(), self.n, st))
+                self._launch(lib.tdq_initial_step_probe(ctrl, dc, self.ytmp.data_ptr(), None, None, self.n, st))
                 f1 = self._call_fn(self.taux[1], self.ytmp, 1)
-                self._sumsq(f1, self.k0, self.dsum[2])
+                self._sumsq(f1, self.kbuf[0], self.dsum[2])
                 del f1
                 self._launch(lib.tdq_initial_step_finish(ctrl, dc, self.dsum[2].data_ptr(),
                                                        self.seg_counts.data_ptr(), self.n_seg, st))
         else:
             self._launch(lib.tdq_set_first_step(ctrl, float(self.first_step), st))
-        self._launch(lib.tdq_prepare_attempt(ctrl, dc, st))
+        bad_ptr = self.dsum[0].data_ptr() + 8 * self.n_seg if n_out > 1 else None
+        self._launch(lib.tdq_prepare_attempt(ctrl, dc, bad_ptr, st))
         return n_out
 
     # ---- lock step: the reference's exact call sequence --------------------------------------
@@ -510,9 +582,10 @@ class AdaptiveEngine:
         self._attempt_back(kp)
         del k, kp, keep
         if jumped:                                          # rk_common.py:346-351: f on the far side of the jump
-            f = self._call_fn(self.taux[2], self.y0w, 0)
-            if f.data_ptr() != self.k0.data_ptr():
-                self.k0.copy_(f)
+            k0 = self.k0
+            f = self._call_fn(self.taux[2], self.y0w, 0, dst=k0)
+            if f.data_ptr() != k0.data_ptr():
+                k0.copy_(f)
             del f
         return issued, mb
 
@@ -603,6 +676,11 @@ class AdaptiveEngine:
         mb = self.mbox_host.contents
         issued = 0
         use_graph = self.graph_opt in (True, "auto") and not self._graph_failed and self.capture_in_solve
+        if self._use_loop() and self.opt.loop_handle != 0:
+            # the whole adaptive loop is ONE graph launch: a conditional WHILE node around the captured attempt,
+            # re-armed by k_controller until the solve has finished or failed
+            self._launch_loop()
+            return
         # attempt 1 runs eagerly: it is a real attempt and doubles as the warm-up torch wants before capture
         if self._graph is None:
             if use_graph:
@@ -611,12 +689,19 @@ class AdaptiveEngine:
             else:
                 self._attempt()
             issued += 1
+            if self._use_loop():
+                # hand the rest of this solve to the loop (if the first attempt already finished it, the loop's
+                # single iteration is a no-op on the device)
+                _lib.check(self.lib.tdq_ctrl_set_loop(self.ctrl.data_ptr(), self._loop_handle, _stream()))
+                self._launch_loop(first=1)
+                return
         while True:
             seen = mb.seq
             if mb.status != _lib.RUN_OK or mb.done:
                 break
             if issued - seen > D:
-                continue                                   # spin: the device is >D attempts behind
+                time.sleep(0)                              # the device is >D attempts behind: yield the GIL
+                continue
             if self._graph is not None:
                 self._graph.replay()
                 self.nfe += self.S
@@ -640,6 +725,15 @@ class AdaptiveEngine:
         self._raise_if_failed(mb)
         torch.cuda.current_stream().synchronize()
 
+    def _launch_loop(self, first=0):
+        _lib.check(self.lib.tdq_loop_launch(self._loop, _stream()))
+        torch.cuda.current_stream().synchronize()
+        mb = self.mbox_host.contents
+        ran = int(mb.seq) - first
+        self.nfe += self.S * ran
+        self.launches += self._graph_launches * ran
+        self._raise_if_failed(mb)
+
     def _warm_attempt(self):
         """The first attempt of a solve that is about to be captured: a real attempt that doubles as the
         warm-up torch wants before capture (we are already on the solver stream, never the legacy one)."""
@@ -653,7 +747,9 @@ class AdaptiveEngine:
         last = None
         for _try in range(2):
             try:
-                g = torch.cuda.CUDAGraph()
+                want_loop = (self.device_loop in (True, "auto") and not self._loop_failed and self.agree_fn is None
+                             and self.norm_fn is None)
+                g = torch.cuda.CUDAGraph(keep_graph=True) if want_loop else torch.cuda.CUDAGraph()
                 nfe, launches = self.nfe, self.launches
                 try:
                     with torch.cuda.graph(g, stream=solver_stream(self.device)):
@@ -662,6 +758,8 @@ class AdaptiveEngine:
                     self._graph_launches = self.launches - launches
                     self.nfe, self.launches = nfe, launches     # capture runs no kernels
                 self._graph, self._graph_keep = g, keep
+                if want_loop:
+                    self._make_loop(g)
                 return
             except Exception as e:                              # func is not capturable: stay eager
                 last = e
@@ -674,10 +772,25 @@ class AdaptiveEngine:
         warnings.warn("torchdiffeq_b200: CUDA graph capture of the step body failed (%s: %s); "
                       "continuing with eager launches" % (type(last).__name__, last))
 
+    def _make_loop(self, g):
+        """Wrap the captured attempt into a device-side while loop (tdq_loop_create).  The body is a clone of
+        torch's graph; torch's CUDAGraph object stays alive because it owns the memory pool the body uses."""
+        loop, handle = C.c_void_p(), C.c_uint64()
+        try:
+            _lib.check(self.lib.tdq_loop_create(C.c_void_p(g.raw_cuda_graph()), C.byref(loop), C.byref(handle)))
+            self._loop, self._loop_handle = loop.value, int(handle.value)
+        except Exception as e:
+            self._loop, self._loop_handle, self._loop_failed = None, 0, True
+            if self.device_loop is True:
+                raise
+            import warnings
+            warnings.warn("torchdiffeq_b200: the captured step could not be wrapped into a device-side loop "
+                          "(%s: %s); the host replays it instead" % (type(e).__name__, e))
+
     def _initial_step_custom_norm(self):
         """misc.py:36-77 with a user norm callable: torch ops + one host read (compatibility path)."""
         T = self.dtype
-        y0, f0 = self.y0w, self.k0 * self.opt.t_sign
+        y0, f0 = self.ybuf[0], self.kbuf[0] * self.opt.t_sign
         if self.rtol_vec is not None:
             scale = self.atol_vec + torch.abs(y0) * self.rtol_vec
         else:

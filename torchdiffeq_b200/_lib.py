@@ -12,6 +12,7 @@ TDQ_MAX_SEGS = 64
 TDQ_F32, TDQ_F64 = 0, 1
 RUN_OK, RUN_DT_UNDERFLOW, RUN_NONFINITE, RUN_MAX_STEPS, RUN_EXCHANGE_TIMEOUT = 0, 1, 2, 3, 4
 TDQ_MAX_RANKS = 16
+ABI_VERSION = 2
 
 
 class IpcHandle(C.Structure):
@@ -37,6 +38,9 @@ class Options(C.Structure):
         ("safety", C.c_double), ("ifactor", C.c_double), ("dfactor", C.c_double),
         ("t_sign", C.c_double),
         ("max_num_steps", C.c_int64), ("n_global", C.c_int64),
+        ("ybuf", C.c_void_p * 2), ("kbuf", C.c_void_p * 2),
+        ("always_fit", C.c_int32), ("reserved", C.c_int32),
+        ("loop_handle", C.c_uint64),
     ]
 
 
@@ -48,7 +52,7 @@ class Mailbox(C.Structure):
         ("t0", C.c_double), ("t1", C.c_double), ("dt", C.c_double),
         ("ratio", C.c_double), ("att_t0", C.c_double), ("att_dt", C.c_double),
         ("next_t0", C.c_double), ("next_dt", C.c_double),
-        ("on_jump_t", C.c_int32), ("reserved", C.c_int32),
+        ("on_jump_t", C.c_int32), ("par", C.c_int32),
     ]
 
 
@@ -77,21 +81,28 @@ _SIGNATURES = {
     "tdq_ctrl_init": (C.c_int, [_vp, _ptab, C.POINTER(Options), _vp, _dbl, _i32, _vp, _vp]),
     "tdq_ctrl_set_step_t": (C.c_int, [_vp, _vp, _i32, _vp]),
     "tdq_ctrl_set_jump_t": (C.c_int, [_vp, _vp, _i32, _vp]),
-    "tdq_norm_partials_len": (_sz, [_sz, _i32]),
-    "tdq_scaled_sumsq": (C.c_int, [_vp, _i32, _vp, _vp, _vp, _vp, _vp, _pi64, _pi64, _i32, _sz, _vp, _vp, _vp]),
+    "tdq_norm_table_fill": (_i64, [_pi64, _pi64, _i32, _i64, _i32, _pi64, _i64]),
+    "tdq_norm_partials_len": (_sz, [_sz, _i64]),
+    "tdq_scaled_sumsq": (C.c_int, [_vp, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i32, _i32, _sz, _vp, _vp, _vp]),
     "tdq_initial_step_h0": (C.c_int, [_vp, _i32, _vp, _vp, _vp, _i32, _vp]),
     "tdq_initial_step_probe": (C.c_int, [_vp, _i32, _vp, _vp, _vp, _sz, _vp]),
     "tdq_initial_step_finish": (C.c_int, [_vp, _i32, _vp, _vp, _i32, _vp]),
     "tdq_set_first_step": (C.c_int, [_vp, _dbl, _vp]),
-    "tdq_prepare_attempt": (C.c_int, [_vp, _i32, _vp]),
+    "tdq_prepare_attempt": (C.c_int, [_vp, _i32, _vp, _vp]),
     "tdq_stage_combine": (C.c_int, [_vp, _ptab, _i32, _i32, _vp, _vp, _pp, _sz, _vp]),
-    "tdq_error_norm": (C.c_int, [_vp, _ptab, _i32, _vp, _vp, _pp, _vp, _vp, _pi64, _pi64, _i32, _sz, _vp, _vp, _vp, _vp]),
+    "tdq_stage_combine_final": (C.c_int, [_vp, _ptab, _i32, _vp, _vp, _vp, _pp, _sz, _vp]),
+    "tdq_error_norm_commit": (C.c_int, [_vp, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i32, _i32, _sz, _vp, _vp,
+                                        _vp, _vp]),
+    "tdq_commit_candidates": (C.c_int, [_vp, _i32, _vp, _vp, _sz, _vp]),
     "tdq_controller": (C.c_int, [_vp, _i32, _vp, _vp, _i32, _vp, _vp]),
-    "tdq_interp_fit_commit": (C.c_int, [_vp, _ptab, _i32, _vp, _vp, _pp, _pp, _sz, _vp]),
-    "tdq_interp_eval": (C.c_int, [_vp, _i32, _pp, _vp, _sz, _vp]),
+    "tdq_interp_fit_eval": (C.c_int, [_vp, _ptab, _i32, _vp, _pp, _pp, _vp, _sz, _vp]),
     "tdq_interp_eval_at": (C.c_int, [_vp, _i32, _pp, _vp, _vp, _sz, _vp]),
     "tdq_poly_eval": (C.c_int, [_i32, _pp, _dbl, _vp, _sz, _vp]),
     "tdq_ctrl_reset_interval": (C.c_int, [_vp, _vp]),
+    "tdq_loop_create": (C.c_int, [_vp, _pp, C.POINTER(C.c_uint64)]),
+    "tdq_loop_launch": (C.c_int, [_vp, _vp]),
+    "tdq_loop_destroy": (C.c_int, [_vp]),
+    "tdq_ctrl_set_loop": (C.c_int, [_vp, C.c_uint64, _vp]),
     "tdq_rk4_stage": (C.c_int, [_i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "tdq_fixed_emit": (C.c_int, [_i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _sz, _vp]),
     "tdq_pack_segments": (C.c_int, [_i32, _vp, _pp, _pi64, _pi64, _pdbl, _i32, _vp]),
@@ -124,7 +135,7 @@ def load():
             raise TdqError("libtdq.so does not export %s; rebuild it" % name) from e
         fn.restype = res
         fn.argtypes = args
-    if lib.tdq_abi_version() != 1:
+    if lib.tdq_abi_version() != ABI_VERSION:
         raise TdqError("libtdq.so ABI version mismatch")
     for which, st in ((0, Tableau), (1, Options), (2, Mailbox)):
         if lib.tdq_sizeof(which) != C.sizeof(st):
@@ -157,6 +168,21 @@ def tableau_as_dict(name):
         "c_err": [t.c_err[j] for j in range(S + 1)],
         "c_mid": [t.c_mid[j] for j in range(S + 1)],
     }
+
+
+def norm_table(segs, n, dt_code):
+    """Chunk table of tdq_norm_table_fill for segments [(offset, len), ...] of a flat state of n elements, as a
+    host list of int64 words; table[1] = number of chunks, table[3] = 1 when every segment is 16-byte aligned."""
+    lib = load()
+    offs = i64_array([int(o) for o, _ in segs])
+    lens = i64_array([int(l) for _, l in segs])
+    words = lib.tdq_norm_table_fill(offs, lens, len(segs), int(n), dt_code, None, 0)
+    if words < 0:
+        check(1)
+    buf = (C.c_int64 * words)()
+    if lib.tdq_norm_table_fill(offs, lens, len(segs), int(n), dt_code, buf, words) != words:
+        check(1)
+    return list(buf)
 
 
 def ptr_array(ptrs):

@@ -120,7 +120,7 @@ class _BackwardSolver:
         self.views_of = views_of
         if adj_norm is None or adj_norm == "seminorm":
             segs = [(o_t, 1)] + y_segs + a_segs + ([] if adj_norm == "seminorm" else p_segs)
-            if p.norm_fn is not None or len(segs) > _lib.TDQ_MAX_SEGS:
+            if p.norm_fn is not None:          # any number of segments stays on the fused path (device chunk table)
                 state_norm = p.norm_fn if p.norm_fn is not None else (_mixed_norm if p.is_tuple else _rms_norm)
                 semi = adj_norm == "seminorm"
 
@@ -192,9 +192,9 @@ class _BackwardSolver:
         lay, n = self.lay, self.p.n
         aug = torch.zeros(lay.n, dtype=self.p.dtype, device=self.p.device)
         aug[self.o_y:self.o_y + n] = y_last
-        t64 = t.detach().to(device=self.p.device, dtype=torch.float64)
-        pair = torch.stack([t64[-1], t64[-2]]) * self.bsign
-        return self.eng.prime(aug, pair)
+        s_cpu = t.detach().to("cpu", torch.float64) * self.bsign         # engine time of the backward solve
+        pair = torch.stack([s_cpu[-1], s_cpu[-2]]).to(self.p.device)
+        return self.eng.prime(aug, pair, t_start=float(s_cpu[-1]))
 
     def run(self, t, y, grad_sol):
         """adjoint.py:116-153."""
@@ -204,7 +204,11 @@ class _BackwardSolver:
         aug = torch.zeros(lay.n, dtype=T, device=dev)
         aug[o_y:o_y + n] = y[-1]
         aug[o_a:o_a + n] = grad_sol[-1]
-        t64 = t.detach().to(device=dev, dtype=torch.float64)
+        # interval end points in the engine's ascending time, on the host (start times, no per-interval sync) and
+        # on the device (row i-1 = the output times of interval i)
+        s_cpu = t.detach().to("cpu", torch.float64) * self.bsign
+        s_dev = s_cpu.to(dev)
+        pairs = torch.stack([s_dev[1:], s_dev[:-1]], dim=1).contiguous() if len(t) > 1 else None
         time_vjps = torch.empty(len(t), dtype=t.dtype, device=t.device) if self.t_requires_grad else None
         for i in range(len(t) - 1, 0, -1):                            # adjoint.py:124-141
             if self.t_requires_grad:
@@ -223,8 +227,7 @@ class _BackwardSolver:
                 grid = fixed_grid(eng.method, opts, self.aug_fn, aug, pair)
                 sol = eng.solve(aug, grid, pair)
             else:
-                pair = torch.stack([t64[i], t64[i - 1]]) * self.bsign    # ascending for the engine
-                sol = eng.solve(aug, pair)
+                sol = eng.solve(aug, pairs[i - 1], t_start=float(s_cpu[i]))   # ascending for the engine
             aug.copy_(sol[1])
             aug[o_y:o_y + n] = y[i - 1]                               # adjoint.py:140
             aug[o_a:o_a + n] += grad_sol[i - 1]                       # adjoint.py:141

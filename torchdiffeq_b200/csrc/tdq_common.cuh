@@ -49,6 +49,15 @@ struct TdqCtrl {
     int32_t halt, out_cursor, emit_lo, emit_hi;
     int64_t n_accept, n_reject, n_steps_interval;
     uint64_t seq;
+    // ---- state pointer table (tdq_ctrl_init from tdq_options.ybuf/kbuf) -----------------------
+    // The accepted state y0 and its derivative f0 = k_0 live in ybuf[par] / kbuf[par].  Every attempt
+    // the error-norm kernel writes the candidate (y1, k_S) into the OTHER pair; accepting is `par ^= 1`
+    // in the controller -- no copy kernel (rk_common.py:341, :352 y_next = y1, f_next = f1).
+    void *ybuf[2], *kbuf[2];
+    const void *y0_cur, *k0_cur;             // = ybuf[par], kbuf[par]
+    const void *y0_prev, *k0_prev;           // the pair of the step just accepted (interpolant fit)
+    int32_t par, always_fit, fit_now, y0_bad;
+    unsigned long long loop_handle;          // cudaGraphConditionalHandle of the device-side while, or 0
     // ---- per-attempt constants (T-valued), written by prepare / controller -----------------
     double coef[TDQ_ROWS][TDQ_MAX_K];        // t_sign * fl_T(beta_ij * T(dt))   (rk_common.py:79)
     double ecoef[TDQ_MAX_K];                 // t_sign * fl_T(T(dt) * e_j)       (rk_common.py:89)

@@ -5,6 +5,7 @@
 // One thread does the arithmetic (a few hundred flops); what matters is that nothing here needs the
 // host, so a whole attempt can sit inside a CUDA graph.
 #include "tdq_common.cuh"
+#include "tdq_shape.cuh"
 
 namespace {
 
@@ -38,6 +39,11 @@ template <typename T> __device__ void prepare_attempt(TdqCtrl &c) {
     c.att_dt = dt;
     if (!(t0 + dt > t0)) {                                            // :286
         c.status = TDQ_RUN_DT_UNDERFLOW;
+        c.halt = 1;
+        return;
+    }
+    if (c.y0_bad) {                                                   // :287 on the FIRST attempt (later ones: controller)
+        c.status = TDQ_RUN_NONFINITE;
         c.halt = 1;
         return;
     }
@@ -85,19 +91,44 @@ template <typename T> __device__ void prepare_attempt(TdqCtrl &c) {
 
 // Value of the norm from per-segment sums: max over segments of sqrt(mean), each rounded to the
 // ratio dtype (misc.py:22-23 _rms_norm, misc.py:30-33 _mixed_norm, adjoint.py:247-250).
-template <typename T>
-__device__ double norm_from_sums(const TdqCtrl &c, const double *sums, const int64_t *counts, int n_seg) {
+// Computed by a whole block (any number of segments): thread t takes segments t, t+B, ...; max is order
+// independent, so the result equals a serial loop's.  Every thread returns the value.
+template <typename T, int THREADS>
+__device__ double block_norm_from_sums(const TdqCtrl &c, const double *sums, const int64_t *counts, int n_seg,
+                                       double *smem /* THREADS/32 + 1 */) {
     double best = 0.0;
-    bool nan = false;
-    for (int s = 0; s < n_seg; ++s) {
+    int nan = 0;
+    for (int s = threadIdx.x; s < n_seg; s += THREADS) {
         const double cnt = counts ? (double)counts[s] : (double)c.n_global;
         if (cnt <= 0.0) continue;
         double r = sqrt(sums[s] / cnt);
         if (!c.ratio_f64) r = (double)(T)r;
-        if (r != r) nan = true;
+        if (r != r) nan = 1;
         if (r > best) best = r;
     }
-    return nan ? CUDART_NAN : best;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const double ob = __shfl_down_sync(0xffffffffu, best, o);
+        const int on = __shfl_down_sync(0xffffffffu, nan, o);
+        if (ob > best) best = ob;
+        nan |= on;
+    }
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    __syncthreads();
+    if (lane == 0) smem[w] = nan ? CUDART_NAN : best;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double b = 0.0;
+        bool bn = false;
+        for (int i = 0; i < THREADS / 32; ++i) {
+            const double v = smem[i];
+            if (v != v) bn = true;
+            else if (v > b) b = v;
+        }
+        smem[THREADS / 32] = bn ? CUDART_NAN : b;
+    }
+    __syncthreads();
+    return smem[THREADS / 32];
 }
 
 __device__ void write_mailbox(TdqCtrl &c, double fin_t0, double fin_dt, int jumped = 0) {
@@ -119,19 +150,20 @@ __device__ void write_mailbox(TdqCtrl &c, double fin_t0, double fin_dt, int jump
     m->next_t0 = c.att_t0;
     m->next_dt = c.att_dt;
     m->on_jump_t = jumped;
+    m->par = c.par;
     __threadfence_system();
     m->seq = c.seq;                  // kernel completion flushes this last store; no second fence needed
 }
 
 // rk_common.py:323-361 + misc.py:85-95, then the next attempt's constants.
 template <typename T>
-__device__ void controller(TdqCtrl &c, const double *norm_in, const int64_t *seg_counts, int n_seg,
-                           const void *ratio_dev) {
+__device__ void controller(TdqCtrl &c, const double *norm_in, int n_seg, const void *ratio_dev, double ratio_pre) {
     if (c.halt) {
         // Attempts issued after the end are no-ops; the mailbox still ticks so a host that runs
         // ahead can account for every attempt it queued.  Clearing `accept` keeps fit/eval of such an
         // attempt from touching the finished solution.
         c.accept = 0;
+        c.fit_now = 0;
         c.emit_lo = c.emit_hi;
         write_mailbox(c, c.att_t0, c.att_dt);
         return;
@@ -143,7 +175,7 @@ __device__ void controller(TdqCtrl &c, const double *norm_in, const int64_t *seg
                             : (double)*reinterpret_cast<const T *>(ratio_dev);
         ratio = fabs(ratio);                                          // misc.py:82 .abs()
     } else {
-        ratio = norm_from_sums<T>(c, norm_in, seg_counts, n_seg);
+        ratio = ratio_pre;                                            // block_norm_from_sums
     }
     const bool y1_nonfinite = norm_in && norm_in[n_seg] > 0.0;
     if (y1_nonfinite && !ratio_dev) ratio = CUDART_NAN;               // a non-finite y1 poisons err/tol
@@ -159,6 +191,13 @@ __device__ void controller(TdqCtrl &c, const double *norm_in, const int64_t *seg
         c.t0 = c.att_t0;
         c.t1 = c.att_t1;
         c.n_accept += 1;
+        // y_next = y1, f_next = f1 (:341, :352): the error-norm kernel has already written both into the other
+        // pair of the pointer table; accepting is a flip.  The old pair stays valid for the interpolant fit.
+        c.y0_prev = c.y0_cur;
+        c.k0_prev = c.k0_cur;
+        c.par ^= 1;
+        c.y0_cur = c.ybuf[c.par];
+        c.k0_cur = c.kbuf[c.par];
         if (c.on_step_t && c.next_step_index != c.n_step_t - 1) c.next_step_index += 1;
         if (c.on_jump_t) {                                            // :346-351
             if (c.next_jump_index != c.n_jump_t - 1) c.next_jump_index += 1;
@@ -205,6 +244,8 @@ __device__ void controller(TdqCtrl &c, const double *norm_in, const int64_t *seg
         c.out_cursor = cur;
     }
     c.emit_hi = c.out_cursor;
+    // the interpolant is needed only when an output time fell into this step, or when the caller keeps it
+    c.fit_now = (accept && (c.always_fit || c.emit_hi > c.emit_lo)) ? 1 : 0;
     if (c.out_cursor >= c.n_out) {
         c.done = 1;
         c.halt = 1;
@@ -217,10 +258,8 @@ __device__ void controller(TdqCtrl &c, const double *norm_in, const int64_t *seg
 
 // misc.py:55-63: h0 from d0, d1.
 template <typename T>
-__device__ void initial_h0(TdqCtrl &c, const double *s0, const double *s1, const int64_t *counts, int n_seg) {
+__device__ void initial_h0(TdqCtrl &c, double d0d, double d1d) {
     using A = Ar<T>;
-    const double d0d = norm_from_sums<T>(c, s0, counts, n_seg);
-    const double d1d = norm_from_sums<T>(c, s1, counts, n_seg);
     double h0;
     if (c.ratio_f64) {
         h0 = (d0d < 1e-5 || d1d < 1e-5) ? (double)(T)1e-6 : fabs(0.01 * d0d / d1d);
@@ -240,9 +279,8 @@ __device__ void initial_h0(TdqCtrl &c, const double *s0, const double *s1, const
 
 // misc.py:69-77
 template <typename T>
-__device__ void initial_finish(TdqCtrl &c, const double *s2, const int64_t *counts, int n_seg) {
+__device__ void initial_finish(TdqCtrl &c, double nd) {
     using A = Ar<T>;
-    const double nd = norm_from_sums<T>(c, s2, counts, n_seg);
     double dt;
     const double order_p1 = (double)c.order;                           // called with order-1 (rk_common.py:217)
     if (c.ratio_f64) {
@@ -274,8 +312,10 @@ __device__ void initial_finish(TdqCtrl &c, const double *s2, const int64_t *coun
     c.dt = dt;
 }
 
-template <typename T> __global__ void k_prepare(TdqCtrl *c) {
+template <typename T> __global__ void k_prepare(TdqCtrl *c, const double *y0_bad) {
+    if (y0_bad && *y0_bad > 0.0) c->y0_bad = 1;
     prepare_attempt<T>(*c);
+    c->y0_bad = 0;                       // later attempts start from states the controller has checked
     if (c->mbox) {                       // first attempt of a solve: let the host see its (t0, dt) and status
         c->mbox->status = c->status;
         c->mbox->next_t0 = c->att_t0;
@@ -303,7 +343,7 @@ k_controller(TdqCtrl *c, const double *norm_in, const int64_t *cnt, int n_seg, c
     TdqCtrl &sc = *reinterpret_cast<TdqCtrl *>(raw);
     __shared__ double xsum[TDQ_MAX_SEGS + 2];
     __shared__ int xfail;
-    if (sc.xworld > 1 && !sc.halt && norm_in != nullptr && ratio_dev == nullptr) {
+    if (sc.xworld > 1 && !sc.halt && norm_in != nullptr && ratio_dev == nullptr && n_seg <= TDQ_MAX_SEGS) {
         // Fused all-reduce over NVLink peer memory: thread t talks to rank t.
         const int R = sc.xworld, me = sc.xrank, nv = n_seg + 1;
         const int par = (int)(sc.seq & 1ull);
@@ -343,19 +383,36 @@ k_controller(TdqCtrl *c, const double *norm_in, const int64_t *cnt, int n_seg, c
         __syncthreads();
         norm_in = xsum;
     }
-    if (threadIdx.x == 0) controller<T>(sc, norm_in, cnt, n_seg, ratio_dev);
+    __shared__ double nsm[kCtrlThreads / 32 + 1];
+    double ratio_pre = 0.0;
+    if (!sc.halt && ratio_dev == nullptr)
+        ratio_pre = block_norm_from_sums<T, kCtrlThreads>(sc, norm_in, cnt, n_seg, nsm);
+    if (threadIdx.x == 0) controller<T>(sc, norm_in, n_seg, ratio_dev, ratio_pre);
     __syncthreads();
     unsigned long long *go = reinterpret_cast<unsigned long long *>(c);
     for (int i = threadIdx.x; i < kWords; i += kCtrlThreads) go[i] = sw[i];
+    // Device-side while loop (tdq_loop_create): this attempt's graph is the body of a conditional WHILE node;
+    // another iteration runs only while the solve has neither finished nor failed.
+    if (threadIdx.x == 0 && sc.loop_handle != 0ull)
+        cudaGraphSetConditional((cudaGraphConditionalHandle)sc.loop_handle, sc.halt ? 0u : 1u);
+}
+constexpr int kInitThreads = 128;
+template <typename T>
+__global__ void __launch_bounds__(kInitThreads)
+k_initial_h0(TdqCtrl *c, const double *s0, const double *s1, const int64_t *cnt, int n_seg) {
+    __shared__ double nsm[kInitThreads / 32 + 1];
+    const double d0 = block_norm_from_sums<T, kInitThreads>(*c, s0, cnt, n_seg, nsm);
+    const double d1 = block_norm_from_sums<T, kInitThreads>(*c, s1, cnt, n_seg, nsm);
+    if (threadIdx.x == 0) initial_h0<T>(*c, d0, d1);
 }
 template <typename T>
-__global__ void k_initial_h0(TdqCtrl *c, const double *s0, const double *s1, const int64_t *cnt, int n_seg) {
-    initial_h0<T>(*c, s0, s1, cnt, n_seg);
+__global__ void __launch_bounds__(kInitThreads)
+k_initial_finish(TdqCtrl *c, const double *s2, const int64_t *cnt, int n_seg) {
+    __shared__ double nsm[kInitThreads / 32 + 1];
+    const double nd = block_norm_from_sums<T, kInitThreads>(*c, s2, cnt, n_seg, nsm);
+    if (threadIdx.x == 0) initial_finish<T>(*c, nd);
 }
-template <typename T>
-__global__ void k_initial_finish(TdqCtrl *c, const double *s2, const int64_t *cnt, int n_seg) {
-    initial_finish<T>(*c, s2, cnt, n_seg);
-}
+__global__ void k_set_loop(TdqCtrl *c, unsigned long long h) { c->loop_handle = h; }
 __global__ void k_set_first_step(TdqCtrl *c, double dt) { c->dt = dt; }
 struct XPtrs { const void *p[TDQ_MAX_RANKS]; };
 __global__ void k_set_exchange(TdqCtrl *c, XPtrs xp, int rank, int world, unsigned long long epoch) {
@@ -384,13 +441,6 @@ __global__ void k_set_step_t(TdqCtrl *c, const double *st, int n) {
 }
 
 }  // namespace
-
-#define TDQ_DISPATCH_T(dtype, ...)                                         \
-    do {                                                                   \
-        if ((dtype) == TDQ_F32) { using T = float; __VA_ARGS__; }          \
-        else if ((dtype) == TDQ_F64) { using T = double; __VA_ARGS__; }    \
-        else { tdq_set_error("unsupported dtype %d", (int)(dtype)); return TDQ_ERR_INVALID; } \
-    } while (0)
 
 // The dtype is stored in the block, but launchers must not read device memory: the host passes it.
 extern "C" {
@@ -453,6 +503,20 @@ int tdq_ctrl_init(void *ctrl_dev, const tdq_tableau *tab, const tdq_options *opt
     h.mbox = reinterpret_cast<tdq_mailbox *>(mailbox_dev);
     h.t0 = h.t1 = t_start;                                            // rk_common.py:221
     h.dt = 0.0;
+    TDQ_REQUIRE((opt->ybuf[0] == nullptr) == (opt->ybuf[1] == nullptr) &&
+                    (opt->ybuf[0] == nullptr) == (opt->kbuf[0] == nullptr) &&
+                    (opt->ybuf[0] == nullptr) == (opt->kbuf[1] == nullptr),
+                "ybuf/kbuf: give all four state buffers or none");
+    for (int i = 0; i < 2; ++i) {
+        TDQ_REQUIRE(tdq_aligned16(opt->ybuf[i]) && tdq_aligned16(opt->kbuf[i]), "state buffers must be 16-byte aligned");
+        h.ybuf[i] = opt->ybuf[i];
+        h.kbuf[i] = opt->kbuf[i];
+    }
+    h.par = 0;
+    h.y0_cur = h.y0_prev = h.ybuf[0];
+    h.k0_cur = h.k0_prev = h.kbuf[0];
+    h.always_fit = opt->always_fit ? 1 : 0;
+    h.loop_handle = opt->loop_handle;
     h.out_cursor = 1;                                                 // solution[0] = y0 (solvers.py:30)
     h.emit_lo = h.emit_hi = 1;
     if (n_out <= 1) { h.done = 1; h.halt = 1; }
@@ -482,9 +546,9 @@ int tdq_ctrl_set_jump_t(void *ctrl_dev, const double *jump_t_dev, int32_t n, voi
     return TDQ_OK;
 }
 
-int tdq_prepare_attempt(void *ctrl_dev, int32_t dtype, void *stream) {
+int tdq_prepare_attempt(void *ctrl_dev, int32_t dtype, const double *y0_nonfinite_count_dev, void *stream) {
     TDQ_REQUIRE(ctrl_dev, "null ctrl");
-    TDQ_DISPATCH_T(dtype, (k_prepare<T><<<1, 1, 0, (cudaStream_t)stream>>>((TdqCtrl *)ctrl_dev)));
+    TDQ_DISPATCH_T(dtype, (k_prepare<T><<<1, 1, 0, (cudaStream_t)stream>>>((TdqCtrl *)ctrl_dev, y0_nonfinite_count_dev)));
     TDQ_CHECK_CUDA(cudaGetLastError());
     return TDQ_OK;
 }
@@ -503,7 +567,7 @@ int tdq_controller(void *ctrl_dev, int32_t dtype, const double *norm_in, const i
 int tdq_initial_step_h0(void *ctrl_dev, int32_t dtype, const double *d0_sumsq, const double *d1_sumsq,
                         const int64_t *seg_counts_dev, int32_t n_seg, void *stream) {
     TDQ_REQUIRE(ctrl_dev && d0_sumsq && d1_sumsq, "null argument");
-    TDQ_DISPATCH_T(dtype, (k_initial_h0<T><<<1, 1, 0, (cudaStream_t)stream>>>(
+    TDQ_DISPATCH_T(dtype, (k_initial_h0<T><<<1, kInitThreads, 0, (cudaStream_t)stream>>>(
                                (TdqCtrl *)ctrl_dev, d0_sumsq, d1_sumsq, seg_counts_dev, n_seg)));
     TDQ_CHECK_CUDA(cudaGetLastError());
     return TDQ_OK;
@@ -512,7 +576,7 @@ int tdq_initial_step_h0(void *ctrl_dev, int32_t dtype, const double *d0_sumsq, c
 int tdq_initial_step_finish(void *ctrl_dev, int32_t dtype, const double *d2_sumsq,
                             const int64_t *seg_counts_dev, int32_t n_seg, void *stream) {
     TDQ_REQUIRE(ctrl_dev && d2_sumsq, "null argument");
-    TDQ_DISPATCH_T(dtype, (k_initial_finish<T><<<1, 1, 0, (cudaStream_t)stream>>>(
+    TDQ_DISPATCH_T(dtype, (k_initial_finish<T><<<1, kInitThreads, 0, (cudaStream_t)stream>>>(
                                (TdqCtrl *)ctrl_dev, d2_sumsq, seg_counts_dev, n_seg)));
     TDQ_CHECK_CUDA(cudaGetLastError());
     return TDQ_OK;
@@ -575,6 +639,13 @@ int tdq_xchg_close(void *peer_ptr) {
 
 int tdq_xchg_destroy(void *dev_ptr) {
     if (dev_ptr) TDQ_CHECK_CUDA(cudaFree(dev_ptr));
+    return TDQ_OK;
+}
+
+int tdq_ctrl_set_loop(void *ctrl_dev, uint64_t loop_handle, void *stream) {
+    TDQ_REQUIRE(ctrl_dev, "null ctrl");
+    k_set_loop<<<1, 1, 0, (cudaStream_t)stream>>>((TdqCtrl *)ctrl_dev, (unsigned long long)loop_handle);
+    TDQ_CHECK_CUDA(cudaGetLastError());
     return TDQ_OK;
 }
 

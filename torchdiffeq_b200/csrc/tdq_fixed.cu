@@ -7,6 +7,7 @@
 // The step size comes from a device array indexed by a device step counter so that one captured
 // step graph serves the whole grid.
 #include "tdq_common.cuh"
+#include "tdq_shape.cuh"
 
 namespace {
 
@@ -146,13 +147,6 @@ __global__ void __launch_bounds__(kThreads) k_pack(T *__restrict__ dst, PackArgs
 }
 
 }  // namespace
-
-#define TDQ_DISPATCH_T(dtype, ...)                                         \
-    do {                                                                   \
-        if ((dtype) == TDQ_F32) { using T = float; __VA_ARGS__; }          \
-        else if ((dtype) == TDQ_F64) { using T = double; __VA_ARGS__; }    \
-        else { tdq_set_error("unsupported dtype %d", (int)(dtype)); return TDQ_ERR_INVALID; } \
-    } while (0)
 
 extern "C" {
 

@@ -30,7 +30,7 @@ _ADJOINT_CALLBACK_NAMES = [name + "_adjoint" for name in _CALLBACK_NAMES]       
 _ADAPTIVE_OPTIONS = {"min_step", "max_step", "first_step", "step_t", "jump_t", "safety", "ifactor", "dfactor",
                      "max_num_steps", "dtype", "norm"}
 _FIXED_OPTIONS = {"step_size", "grid_constructor", "interp", "perturb", "norm"}
-_OUR_OPTIONS = {"graph", "run_ahead", "process_group", "cache", "exchange"}
+_OUR_OPTIONS = {"graph", "run_ahead", "process_group", "cache", "exchange", "device_loop"}
 
 
 def _rms_norm(tensor):
@@ -231,7 +231,8 @@ def _warn_unused(solver_name, options, known):                                  
 
 
 def _make_adaptive_engine(p, method, rtol, atol, rtol_vec, atol_vec, options, fn=None, n=None, segs=None,
-                          pieces=None, norm_fn=None, q_view=None, callbacks=None, solver_name=None):
+                          pieces=None, norm_fn=None, q_view=None, callbacks=None, solver_name=None,
+                          keep_interp=False):
     o = options
     _warn_unused(solver_name or method, o, _ADAPTIVE_OPTIONS)
     if o.get("dtype", torch.float64) != torch.float64:
@@ -270,7 +271,7 @@ def _make_adaptive_engine(p, method, rtol, atol, rtol_vec, atol_vec, options, fn
         max_num_steps=o.get("max_num_steps", 2 ** 31 - 1),
         norm_fn=norm_fn, q_view=q_view, graph=o.get("graph", "auto"), run_ahead=o.get("run_ahead", 2),
         reduce_fn=reduce_fn, n_global=n_global, seg_counts_global=seg_counts_global, agree_fn=agree_fn,
-        exchange=exchange, callbacks=callbacks)
+        exchange=exchange, callbacks=callbacks, keep_interp=keep_interp, device_loop=o.get("device_loop", "auto"))
 
 
 # ---- engine cache -------------------------------------------------------------------------------
@@ -413,7 +414,7 @@ def _solve_event(p):
     """odeint.py:97-100 + solvers.py:41-49: integrate until the event; returns (event_t tensor like t, [2, n])."""
     eng = _make_adaptive_engine(p, p.method, p.rtol, p.atol, p.rtol_vec, p.atol_vec,
                                 dict(p.options, run_ahead=0, graph=False), segs=p.segs, pieces=p.pieces,
-                                norm_fn=p.norm_fn, q_view=p.q_view, callbacks=p.callbacks)
+                                norm_fn=p.norm_fn, q_view=p.q_view, callbacks=p.callbacks, keep_interp=True)
     tol = p.atol if p.atol is not None else float(p.atol_vec.min())
     event_t, y_event = eng.solve_until_event(p.y0_flat, float(p.t_cpu[0]), p.event_fn, tol)
     sol = torch.stack([p.y0_flat.to(p.dtype), y_event], dim=0)                         # solvers.py:48
@@ -510,7 +511,7 @@ def odeint_dense(func, y0, t0, t1, *, rtol=1e-7, atol=1e-9, method=None, options
     with torch.no_grad(), on_solver_stream(p.device) as ss:
         eng = _make_adaptive_engine(p, p.method, p.rtol, p.atol, p.rtol_vec, p.atol_vec,
                                     dict(p.options, run_ahead=0, graph=False), segs=p.segs, pieces=p.pieces,
-                                    norm_fn=p.norm_fn, q_view=p.q_view, callbacks=p.callbacks)
+                                    norm_fn=p.norm_fn, q_view=p.q_view, callbacks=p.callbacks, keep_interp=True)
         t64 = p.t_cpu.to(torch.float64).to(p.device)
         _, times, coeffs = eng.solve_dense(p.y0_flat, t64)
     lib, dc, n, sign_, shape, dtype, dev = eng.lib, eng.dt_code, p.n, p.t_sign, p.shape, p.dtype, p.device
