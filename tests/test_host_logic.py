@@ -92,12 +92,12 @@ def test_fixed_grid_tables(case, dtype):
 
 
 def test_cache_signature_tracks_reachable_tensors():
-    def make():
-        A = torch.randn(3, 3)
-        return (lambda t, y: y @ A), A
-    f, _ = make()
-    g, _ = make()
-    assert _func_signature(f) == _func_signature(f) and _func_signature(f) != _func_signature(g)
+    # plain callables are never cached on their own (globals, defaults and cells cannot be enumerated safely):
+    # no signature unless the caller opts in with options={'cache': True}
+    A = torch.randn(3, 3)
+    f = lambda t, y: y @ A
+    assert _func_signature(f) is None
+    assert _func_signature(f, explicit=True) == (id(f),)
 
     class M(torch.nn.Module):
         def __init__(self):
@@ -119,5 +119,20 @@ def test_cache_signature_tracks_reachable_tensors():
         m.lin.weight.add_(1.0)               # in-place update keeps the storage: same key
     assert _func_signature(m) == k
     m.lin.weight = torch.nn.Parameter(torch.zeros(2, 2))
+    assert _func_signature(m) != k
+    k = _func_signature(m)
+    m.scale = 2.0                            # plain Python attributes a captured graph would have baked in
+    assert _func_signature(m) != k
+    k = _func_signature(m)
+    m.scale = 3.0
+    assert _func_signature(m) != k
+    k = _func_signature(m)
+    m.extra = [torch.zeros(2), 1.5]          # tensors inside containers
+    k2 = _func_signature(m)
+    assert k2 != k
+    m.extra[0] = torch.zeros(2)
+    assert _func_signature(m) != k2
+    k = _func_signature(m)
+    m.lin.training = False                   # a submodule's flag
     assert _func_signature(m) != k
     hash(_func_signature(m))

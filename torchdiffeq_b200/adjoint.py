@@ -22,8 +22,8 @@ import torch.nn as nn
 from . import _lib
 from ._engine import Layout, on_solver_stream
 from ._fixed import FixedGridEngine
-from .odeint import (ADAPTIVE_METHODS, FIXED_METHODS, _ADJOINT_CALLBACK_NAMES, _CALLBACK_NAMES, _cache_get, _cache_key,
-                     _cache_put, _make_adaptive_engine, _mixed_norm, _rms_norm, _solve, _solve_event, _unflatten,
+from .odeint import (ADAPTIVE_METHODS, FIXED_METHODS, _ADJOINT_CALLBACK_NAMES, _CALLBACK_NAMES, _cache_drop, _cache_get,
+                     _cache_key, _cache_put, _make_adaptive_engine, _mixed_norm, _rms_norm, _solve, _solve_event, _unflatten,
                      fixed_grid, normalise, Problem)
 
 
@@ -157,6 +157,7 @@ class _BackwardSolver:
         self.bsign = -fwd_sign
         bp = Problem()                       # the backward problem as the engine factory sees it
         bp.t_sign, bp.device, bp.dtype, bp.n, bp.fn = self.bsign, dev, T, lay.n, aug_fn
+        bp.original_func = p.original_func          # decides graph='auto' (only nn.Module funcs are captured)
         bp.t_cpu = (p.t_cpu.to(torch.float64) * fwd_sign * self.bsign).flip(0)
         self.fixed = adjoint_method in FIXED_METHODS
         if self.fixed:
@@ -265,7 +266,7 @@ class _AdjointFunction(torch.autograd.Function):
                 *adjoint_params):
         ctx.p = p
         ctx.bargs = (adjoint_rtol, adjoint_atol, adjoint_method, adjoint_options, t_requires_grad)
-        ctx.bsolver = None
+        ctx.bsolver, ctx.bkey = None, None
         ctx.event_mode = p.event_fn is not None                          # adjoint.py:21
         with torch.no_grad():
             if ctx.event_mode:                                           # adjoint.py:30-31
@@ -278,14 +279,14 @@ class _AdjointFunction(torch.autograd.Function):
             if any(ctx.needs_input_grad) and len(t) > 1 and graph_opt in (True, "auto") \
                     and int(adjoint_options.get("run_ahead", 2)) > 0:
                 try:
-                    bkey = _backward_key(p, adjoint_params, ctx.bargs)
-                    hit = _cache_get(bkey)
+                    bkey = ctx.bkey = _backward_key(p, adjoint_params, ctx.bargs)
+                    hit = _cache_get(bkey, "backward")
                     if hit is not None:
                         bs = hit[0]
                     else:
                         bs = _BackwardSolver(p, adjoint_params, *ctx.bargs)
                         bs.prime(t, sol[-1])
-                        _cache_put(bkey, (bs, p.original_func))
+                        _cache_put(bkey, (bs, p.original_func), "backward")
                     ctx.bsolver = bs
                 except Exception as e:
                     if graph_opt is True:
@@ -311,7 +312,11 @@ class _AdjointFunction(torch.autograd.Function):
             bs = ctx.bsolver
             if bs is None:
                 bs = _BackwardSolver(p, adjoint_params, *ctx.bargs)
-            time_vjps, adj_y, adj_params = bs.run(t, y, grad_sol)
+            try:
+                time_vjps, adj_y, adj_params = bs.run(t, y, grad_sol)
+            except BaseException:
+                _cache_drop(ctx.bkey, "backward")         # a half-finished backward engine is never reused
+                raise
             if ctx.event_mode and time_vjps is not None:                 # adjoint.py:146-148
                 time_vjps = torch.cat([time_vjps[0].reshape(-1), torch.zeros_like(t_all[1:])])
         ctx.bsolver = None

@@ -230,11 +230,22 @@ def _warn_unused(solver_name, options, known):                                  
         warnings.warn('{}: Unexpected arguments {}'.format(solver_name, unused))
 
 
+def _resolve_graph(graph, func):
+    """'auto' captures the step body only for nn.Module funcs.  Capturing runs func's Python ONCE and replays its
+    kernels afterwards, which silently freezes Python side effects (NFE counters, schedules, Python RNG) and
+    data-dependent branches; for a Module that is the documented contract (README "Graph mode"), for an arbitrary
+    callable it is not assumed -- pass options={'graph': True} to opt in."""
+    if graph == "auto" and not isinstance(func, torch.nn.Module):
+        return False
+    return graph
+
+
 def _make_adaptive_engine(p, method, rtol, atol, rtol_vec, atol_vec, options, fn=None, n=None, segs=None,
                           pieces=None, norm_fn=None, q_view=None, callbacks=None, solver_name=None,
                           keep_interp=False):
     o = options
     _warn_unused(solver_name or method, o, _ADAPTIVE_OPTIONS)
+    graph = _resolve_graph(o.get("graph", "auto"), getattr(p, "original_func", None))
     if o.get("dtype", torch.float64) != torch.float64:
         raise NotImplementedError("time dtype other than float64 (options['dtype']) is not implemented")
     def _tvals(v):                                                                     # rk_common.py:372-375
@@ -269,62 +280,102 @@ def _make_adaptive_engine(p, method, rtol, atol, rtol_vec, atol_vec, options, fn
         first_step=o.get("first_step"), step_t=step_t, jump_t=jump_t,
         safety=o.get("safety", 0.9), ifactor=o.get("ifactor", 10.0), dfactor=o.get("dfactor", 0.2),
         max_num_steps=o.get("max_num_steps", 2 ** 31 - 1),
-        norm_fn=norm_fn, q_view=q_view, graph=o.get("graph", "auto"), run_ahead=o.get("run_ahead", 2),
+        norm_fn=norm_fn, q_view=q_view, graph=graph, run_ahead=o.get("run_ahead", 2),
         reduce_fn=reduce_fn, n_global=n_global, seg_counts_global=seg_counts_global, agree_fn=agree_fn,
         exchange=exchange, callbacks=callbacks, keep_interp=keep_interp, device_loop=o.get("device_loop", "auto"))
 
 
 # ---- engine cache -------------------------------------------------------------------------------
-# An engine owns ~20 state-sized buffers and, in graph mode, a captured step graph with its private
+# An engine owns ~10 state-sized buffers and, in graph mode, a captured step graph with its private
 # memory pool; building and tearing that down costs far more than a solve of the benchmark size.
 # Engines are therefore kept (LRU) and reused when the same func is integrated again with the same
-# shapes and options -- the normal situation in a training or serving loop.  The key contains
-# everything a captured graph has baked in; anything unhashable (tensor options, callbacks, vector
-# tolerances, custom norms) simply disables caching.  options={'cache': False} opts out;
-# torchdiffeq_b200.clear_cache() drops the engines and their memory.
-_ENGINE_CACHE = collections.OrderedDict()
-_ENGINE_CACHE_MAX = 4
+# shapes and options -- the normal situation in a training or serving loop.
+#
+# A captured graph bakes in everything func did while it was captured, so reuse is restricted to what can be
+# keyed reliably: func must be an nn.Module, and the key holds the module object, every
+# parameter / buffer / tensor attribute (address, shape, dtype, requires_grad; also inside list / tuple / dict
+# attributes), every plain Python attribute (int, float, bool, str, None) and the `training` flag of every
+# submodule.  Plain functions, closures, partials and bound methods are NOT cached (their globals, defaults and
+# cells cannot be enumerated safely): they get a fresh engine per call unless the caller passes
+# options={'cache': True} and thereby promises that func is a pure function of (t, y) between calls.
+# Anything unhashable (tensor options, callbacks, vector tolerances, custom norms) disables caching;
+# options={'cache': False} opts out; torchdiffeq_b200.clear_cache() drops the engines and their memory.
+# What no key can see -- data-dependent Python branches inside forward(), state mutated in place through
+# channels other than attributes -- is the caller's contract (README "Graph mode").
+_ENGINE_CACHE = collections.OrderedDict()          # forward engines
+_BACKWARD_CACHE = collections.OrderedDict()        # adjoint backward solvers (their own LRU: no thrashing)
+_CACHE_MAX = {"forward": 4, "backward": 4}
 
 
 def clear_cache():
     _ENGINE_CACHE.clear()
+    _BACKWARD_CACHE.clear()
+
+
+def set_cache_size(forward=4, backward=4):
+    """Number of engines kept per cache (each holds ~10 state-sized buffers plus its graph's memory pool)."""
+    _CACHE_MAX["forward"], _CACHE_MAX["backward"] = int(forward), int(backward)
+    for which, c in (("forward", _ENGINE_CACHE), ("backward", _BACKWARD_CACHE)):
+        while len(c) > _CACHE_MAX[which]:
+            c.popitem(last=False)
 
 
 def _tensor_sig(x):
     return (x.data_ptr(), tuple(x.shape), x.dtype, x.requires_grad)
 
 
-def _func_signature(func):
-    """Identity of everything a captured step graph bakes in about func: the object itself plus the storage
-    of every tensor it can reach without running it -- module parameters and buffers (recursively), tensor
-    attributes of the object, tensors in a plain function's closure cells.  Rebinding any of them to a new
-    tensor changes the key, so a stale graph is never replayed for them."""
-    sig = [id(func)]
+_PLAIN = (int, float, bool, str, type(None), complex)
+
+
+def _attr_sig(name, v):
+    """Key contribution of one attribute of a module (None: nothing to add)."""
+    if isinstance(v, torch.Tensor):
+        return (name,) + _tensor_sig(v)
+    if isinstance(v, _PLAIN):
+        return (name, v)
+    if isinstance(v, (list, tuple)):
+        items = tuple(_attr_sig(i, x) for i, x in enumerate(v) if isinstance(x, (torch.Tensor,) + _PLAIN))
+        return (name, type(v).__name__, len(v), items)
+    if isinstance(v, dict):
+        items = tuple(_attr_sig(str(k), x) for k, x in v.items() if isinstance(x, (torch.Tensor,) + _PLAIN))
+        return (name, "dict", len(v), items)
+    return None
+
+
+_SKIP_ATTRS = {"_parameters", "_buffers", "_modules", "_non_persistent_buffers_set", "_backward_hooks",
+               "_backward_pre_hooks", "_forward_hooks", "_forward_pre_hooks", "_forward_hooks_with_kwargs",
+               "_forward_pre_hooks_with_kwargs", "_forward_hooks_always_called", "_state_dict_hooks",
+               "_state_dict_pre_hooks", "_load_state_dict_pre_hooks", "_load_state_dict_post_hooks",
+               "_is_full_backward_hook", "_compiled_call_impl", "training"}
+
+
+def _func_signature(func, explicit=False):
+    """Identity of everything a captured step graph bakes in about func, or None when it cannot be established
+    (func is not an nn.Module and the caller did not opt in)."""
     if isinstance(func, torch.nn.Module):
-        sig.append(func.training)
-        sig.extend(_tensor_sig(q) for q in func.parameters())
-        sig.extend(_tensor_sig(b) for b in func.buffers())
-        for m in func.modules():
-            sig.extend((k,) + _tensor_sig(v) for k, v in vars(m).items() if isinstance(v, torch.Tensor))
-    else:
-        owner = getattr(func, "__self__", func)
-        if hasattr(owner, "__dict__"):
-            sig.extend((k,) + _tensor_sig(v) for k, v in vars(owner).items() if isinstance(v, torch.Tensor))
-        for cell in getattr(func, "__closure__", None) or ():
-            try:
-                v = cell.cell_contents
-            except ValueError:
-                continue
-            if isinstance(v, torch.Tensor):
-                sig.append(_tensor_sig(v))
-            elif isinstance(v, torch.nn.Module):
-                sig.append(_func_signature(v))
-    return tuple(sig)
+        sig = [id(func)]
+        for name, m in func.named_modules():
+            sig.append((name, type(m).__name__, m.training))
+            sig.extend((name,) + _tensor_sig(q) for q in m.parameters(recurse=False))
+            sig.extend((name,) + _tensor_sig(b) for b in m.buffers(recurse=False))
+            for k, v in vars(m).items():
+                if k in _SKIP_ATTRS:
+                    continue
+                a = _attr_sig(k, v)
+                if a is not None:
+                    sig.append((name,) + a)
+        return tuple(sig)
+    if explicit:
+        return (id(func),)
+    return None
 
 
 def _cache_key(p, extra=()):
     o = p.options
     if o.get("cache", True) is False or p.callbacks or p.norm_fn is not None or p.rtol_vec is not None:
+        return None
+    fsig = _func_signature(p.original_func, explicit=o.get("cache", None) is True)
+    if fsig is None:
         return None
     items = []
     for k, v in sorted(o.items()):
@@ -335,7 +386,7 @@ def _cache_key(p, extra=()):
         items.append((k, v))
     shapes = tuple(tuple(s_) for s_ in p.layout.shapes) if p.is_tuple else tuple(p.shape)
     try:
-        key = (_func_signature(p.original_func), p.method, p.dtype, str(p.device), p.is_tuple, shapes, p.rtol, p.atol,
+        key = (fsig, p.method, p.dtype, str(p.device), p.is_tuple, shapes, p.rtol, p.atol,
                p.t_sign, tuple(items), torch.is_autocast_enabled(), extra)
         hash(key)
     except TypeError:
@@ -343,19 +394,37 @@ def _cache_key(p, extra=()):
     return key
 
 
-def _cache_get(key):
-    if key is None or key not in _ENGINE_CACHE:
+def _cache_get(key, which="forward"):
+    c = _ENGINE_CACHE if which == "forward" else _BACKWARD_CACHE
+    if key is None or key not in c:
         return None
-    _ENGINE_CACHE.move_to_end(key)
-    return _ENGINE_CACHE[key]
+    c.move_to_end(key)
+    return c[key]
 
 
-def _cache_put(key, value):
+def _cache_put(key, value, which="forward"):
     if key is None:
         return
-    _ENGINE_CACHE[key] = value
-    while len(_ENGINE_CACHE) > _ENGINE_CACHE_MAX:
-        _ENGINE_CACHE.popitem(last=False)
+    c = _ENGINE_CACHE if which == "forward" else _BACKWARD_CACHE
+    c[key] = value
+    while len(c) > _CACHE_MAX[which]:
+        c.popitem(last=False)
+
+
+def _cache_drop(key, which="forward"):
+    c = _ENGINE_CACHE if which == "forward" else _BACKWARD_CACHE
+    if key is not None:
+        c.pop(key, None)
+
+
+# The last solve's counters: func runs once at capture and is replayed afterwards in graph mode, so Python-side
+# NFE counters inside func do not advance; this is the supported way to read them (torchdiffeq_b200.last_stats()).
+_LAST_STATS = {}
+
+
+def last_stats():
+    """{'nfe', 'n_accept', 'n_reject', 'attempts', 'launches'} of the most recent odeint call in this process."""
+    return dict(_LAST_STATS)
 
 
 def _solve(p):
@@ -371,7 +440,11 @@ def _solve(p):
                                         callbacks=p.callbacks)
             _cache_put(key, (eng, p.original_func))     # the func reference keeps id(func) from being recycled
         t64 = p.t_cpu.to(torch.float64).to(p.device)                                   # solvers.py:31
-        sol = eng.solve(p.y0_flat, t64, t_start=float(p.t_cpu[0]))
+        try:
+            sol = eng.solve(p.y0_flat, t64, t_start=float(p.t_cpu[0]))
+        except BaseException:
+            _cache_drop(key)                            # a half-finished engine is never reused
+            raise
         if key is not None:
             sol = sol.clone()                           # the engine reuses its solution buffer
         return sol, eng
@@ -380,8 +453,8 @@ def _solve(p):
     y0_view = p.layout.views(p.y0_flat) if p.is_tuple else p.y0_flat.view(p.shape)
     grid = fixed_grid(p.method, o, p.original_func, y0_view, p.t_cpu)
     eng = FixedGridEngine(p.fn, p.n, p.dtype, p.device, method=p.method, t_sign=p.t_sign,
-                          perturb=o.get("perturb", False), graph=o.get("graph", "auto"), callbacks=p.callbacks,
-                          pieces=p.pieces)
+                          perturb=o.get("perturb", False), graph=_resolve_graph(o.get("graph", "auto"), p.original_func),
+                          callbacks=p.callbacks, pieces=p.pieces)
     sol = eng.solve(p.y0_flat, grid, p.t_cpu)
     return sol, eng
 
@@ -569,6 +642,9 @@ def odeint(func, y0, t, *, rtol=1e-7, atol=1e-9, method=None, options=None, even
             return torch.tensor(event_t, dtype=t.dtype, device=t.device), _unflatten(p, sol)     # odeint.py:98, :105-108
         sol, eng = _solve(p)
         ss.publish(sol)
+    _LAST_STATS.clear()
+    _LAST_STATS.update(nfe=eng.nfe, launches=getattr(eng, "launches", 0), attempts=getattr(eng, "n_attempts", None),
+                       n_accept=getattr(eng, "n_accept", None), n_reject=getattr(eng, "n_reject", None))
     if _stats is not None:               # private: solver counters for bench.py and the tests
         _stats["nfe"] = eng.nfe
         _stats["launches"] = _stats.get("launches", 0) + getattr(eng, "launches", 0)
