@@ -133,6 +133,6 @@ def test_cache_signature_tracks_reachable_tensors():
     m.extra[0] = torch.zeros(2)
     assert _func_signature(m) != k2
     k = _func_signature(m)
-    m.lin.training = False                   # a submodule's flag
+    m.lin.training = True                    # a submodule's flag (m.eval() above cleared it)
     assert _func_signature(m) != k
     hash(_func_signature(m))
