@@ -283,11 +283,21 @@ int tdq_rk4_stage(int32_t dtype, int32_t which, void *y_out, const void *y0, con
  * in [rec_begin[step], rec_begin[step+1]): solution[out_idx[r]] = y0 | y1 | y0 + slope[r]*(y1 - y0)
  * for mode[r] = 0|1|2; then y0 <- y1, the step counter is incremented and the next step's four func
  * times are copied from tstage_all[step+1][0..4) to tstage_cur[0..4) (state dtype; what func's time
- * argument aliases). */
+ * argument aliases).  step_dev points at TWO int64 words: [0] the step counter, [1] a ticket the kernel uses
+ * (zero-initialised by the caller, self-resetting). */
 int tdq_fixed_emit(int32_t dtype, void *y0, const void *y1, void *solution,
                    const int32_t *rec_begin_dev, const int32_t *out_idx_dev, const int32_t *mode_dev,
                    const void *slope_dev, int64_t *step_dev, const void *tstage_all_dev,
                    void *tstage_cur_dev, int64_t n_steps, size_t n, void *stream);
+
+/* interp='cubic' (solvers.py:120-125, :166-173): for records r in [rec_lo, rec_hi) of one step
+ * solution[out_idx[r]] = h00*y0 + (h10*dt)*f0 + h01*y1 + (h11*dt)*f1 with the four weights of record r at
+ * coef_dev[4*r .. 4*r+4) (state dtype; the caller evaluates them in t's dtype like the reference and folds the
+ * reverse-time sign into the two dt*f weights).  f0 = f(t0, y0) and f1 = f(t1, y1) are RAW func outputs.
+ * Does not commit y0 <- y1: tdq_fixed_emit (with an empty record range) still ends the step. */
+int tdq_fixed_emit_cubic(int32_t dtype, const void *y0, const void *y1, const void *f0, const void *f1, void *solution,
+                         const int32_t *out_idx_dev, const void *coef_dev, int32_t rec_lo, int32_t rec_hi, size_t n,
+                         void *stream);
 
 /* ---- sharded solves: norm partials exchanged over NVLink peer memory INSIDE tdq_controller ----- */
 /* The reference has no multi-GPU path; its RMS norm is a mean over the whole batch (misc.py:22-23), so

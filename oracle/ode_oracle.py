@@ -333,24 +333,29 @@ def odeint_adaptive(func, y0, t, method="dopri5", rtol=1e-7, atol=1e-9, norm=rms
 _ONE_THIRD, _TWO_THIRDS = 1 / 3, 2 / 3
 
 
-def rk4_increment(func, t0, dt, t1, y0, perturb=False):
+def rk4_increment(func, t0, dt, t1, y0, perturb=False, f0_out=None):
     """fixed_grid.py:27-29 + rk_common.py:110-118.  Returns dy."""
     T = _real_dtype(y0)
-    cast = lambda tt: tt.to(T)
+    cast = lambda tt: torch.as_tensor(tt).to(T)
     k1 = func(_next(cast(t0)) if perturb else cast(t0), y0)
+    if f0_out is not None:
+        f0_out.append(k1)
     k2 = func(cast(t0 + dt * _ONE_THIRD), y0 + dt * k1 * _ONE_THIRD)
     k3 = func(cast(t0 + dt * _TWO_THIRDS), y0 + dt * (k2 - k1 * _ONE_THIRD))
     k4 = func(_prev(cast(t1)) if perturb else cast(t1), y0 + dt * (k1 - k2 + k3))
     return (k1 + 3 * (k2 + k3) + k4) * dt * 0.125
 
 
-def fixed_increment(method, func, t0, dt, t1, y0, perturb=False):
-    """dy of one step of a fixed-grid method: fixed_grid.py:6-60 with rk_common.py:110-158."""
+def fixed_increment(method, func, t0, dt, t1, y0, perturb=False, f0_out=None):
+    """dy of one step of a fixed-grid method: fixed_grid.py:6-60 with rk_common.py:110-158.  f0_out (a list), when
+    given, receives f0 = func(t0, y0), the second value the reference's _step_func returns."""
     if method == "rk4":
-        return rk4_increment(func, t0, dt, t1, y0, perturb)
+        return rk4_increment(func, t0, dt, t1, y0, perturb, f0_out)
     T = _real_dtype(y0)
-    cast = lambda tt: tt.to(T)
+    cast = lambda tt: torch.as_tensor(tt).to(T)
     f0 = func(_next(cast(t0)) if perturb else cast(t0), y0)
+    if f0_out is not None:
+        f0_out.append(f0)
     if method == "euler":                                            # fixed_grid.py:9-11
         return dt * f0
     if method == "midpoint":                                         # fixed_grid.py:17-21
@@ -368,12 +373,88 @@ def fixed_increment(method, func, t0, dt, t1, y0, perturb=False):
     raise ValueError(method)
 
 
-def odeint_fixed(func, y0, t, method="rk4", grid=None, perturb=False):
-    """solvers.py:102-128 for any explicit fixed-grid method, linear interpolation (:175-181)."""
-    return odeint_rk4(func, y0, t, grid=grid, perturb=perturb, method=method)
+def odeint_fixed(func, y0, t, method="rk4", grid=None, perturb=False, interp="linear"):
+    """solvers.py:102-128 for any explicit fixed-grid method, linear (:175-181) or cubic Hermite (:166-173) outputs."""
+    return odeint_rk4(func, y0, t, grid=grid, perturb=perturb, method=method, interp=interp)
 
 
-def odeint_rk4(func, y0, t, grid=None, perturb=False, method="rk4"):
+def cubic_hermite(t0, y0, f0, t1, y1, f1, t):
+    """solvers.py:166-173."""
+    h = (t - t0) / (t1 - t0)
+    h00 = (1 + 2 * h) * (1 - h) * (1 - h)
+    h10 = h * (1 - h) * (1 - h)
+    h01 = h * h * (3 - 2 * h)
+    h11 = h * h * (h - 1)
+    dt = (t1 - t0)
+    return h00 * y0 + h10 * dt * f0 + h01 * y1 + h11 * dt * f1
+
+
+def linear_interp(t0, t1, y0, y1, t):
+    """solvers.py:175-181."""
+    if t == t0:
+        return y0
+    if t == t1:
+        return y1
+    slope = (t - t0) / (t1 - t0)
+    return y0 + slope * (y1 - y0)
+
+
+def find_event(interp_fn, sign0, t0, t1, event_fn, tol):
+    """event_handling.py:5-20."""
+    import math
+    nitrs = torch.ceil(torch.log((t1 - t0) / tol) / math.log(2.0))
+    for _ in range(int(nitrs.long())):
+        t_mid = (t1 + t0) / 2.0
+        y_mid = interp_fn(t_mid)
+        sign_mid = torch.sign(event_fn(t_mid, y_mid))
+        same = (sign0 == sign_mid)
+        t0 = torch.where(same, t_mid, t0)
+        t1 = torch.where(same, t1, t_mid)
+    event_t = (t0 + t1) / 2.0
+    return event_t, interp_fn(event_t)
+
+
+def odeint_fixed_event(func, y0, t0, event_fn, method, step_size, interp="linear", atol=1e-9, reverse=False):
+    """FixedGridODESolver.integrate_until_event (solvers.py:130-164) behind odeint's event plumbing
+    (odeint.py:97-100, misc.py:203-207, :273-282): returns (event_t in the caller's time, [y0, y(event)]).
+    event_fn is the user's (caller's time); a multivariate one is combined as event_handling.py:23-35 does."""
+    T = _real_dtype(y0)
+    signs = torch.sign(event_fn(t0, y0))
+    combined = lambda tt, yy: torch.min(event_fn(tt, yy) * signs)
+    user = func
+    if reverse:
+        t0 = -t0
+        func = lambda tt, yy: -1.0 * user(-tt, yy)
+        ev = lambda tt, yy: combined(-tt, yy)
+    else:
+        ev = combined
+    t0 = torch.as_tensor(t0).to(T)                                   # t0.type_as(self.y0.abs())
+    dt = step_size
+    sign0 = torch.sign(ev(t0, y0))
+    y, itr = y0, 0
+    while True:
+        itr += 1
+        t1 = t0 + dt
+        f0s = []
+        y1 = y + fixed_increment(method, func, t0, dt, t1, y, False, f0s)
+        sign1 = torch.sign(ev(t1, y1))
+        if sign0 != sign1:
+            if interp == "linear":
+                interp_fn = lambda t: linear_interp(t0, t1, y, y1, t)
+            else:
+                f1 = func(t1.to(T), y1)
+                interp_fn = lambda t: cubic_hermite(t0, y, f0s[0], t1, y1, f1, t)
+            event_t, y_ev = find_event(interp_fn, sign0, t0, t1, ev, float(atol))
+            break
+        t0, y = t1, y1
+        if itr >= 20000:
+            raise RuntimeError("Reached maximum number of iterations 20000.")
+    if reverse:
+        event_t = -event_t
+    return event_t, torch.stack([y0, y_ev], dim=0)
+
+
+def odeint_rk4(func, y0, t, grid=None, perturb=False, method="rk4", interp="linear"):
     """solvers.py:102-128 with linear interpolation (:175-181).  t keeps its own dtype (no float64 cast)."""
     sign = 1.0
     if len(t) > 1 and t[0] > t[1]:
@@ -391,9 +472,13 @@ def odeint_rk4(func, y0, t, grid=None, perturb=False, method="rk4"):
     j, y = 1, y0
     for t0, t1 in zip(grid[:-1], grid[1:]):
         dt = t1 - t0
-        y1 = y + fixed_increment(method, func, t0, dt, t1, y, perturb)
+        f0s = []
+        y1 = y + fixed_increment(method, func, t0, dt, t1, y, perturb, f0s)
         while j < len(t) and t1 >= t[j]:
-            if t[j] == t0:
+            if interp == "cubic":                                    # solvers.py:120-122: f1 re-evaluated per output
+                f1 = func(t1.to(_real_dtype(y0)), y1)
+                solution[j] = cubic_hermite(t0, y, f0s[0], t1, y1, f1, t[j])
+            elif t[j] == t0:
                 solution[j] = y
             elif t[j] == t1:
                 solution[j] = y1

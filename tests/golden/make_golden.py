@@ -14,6 +14,7 @@ Outputs (committed):
     detest.pt             all 25 DETEST problems: NFE, end states and RMS error vs dopri5@1e-12 for dopri5/dopri8 at
                           rtol=atol in {1e-3, 1e-6, 1e-9} (+ dopri8 at 1e-12)
     options.pt            step_t / min_step / max_step / first_step / tuple-state / vector-tol cases
+    fixed_extra.pt        interp='cubic' and event handling for the fixed-grid methods
 """
 import json
 import os
@@ -265,6 +266,46 @@ def events():
     torch.save(out, os.path.join(HERE, "events.pt"))
 
 
+def fixed_extra():
+    """interp='cubic' (solvers.py:120-125, :166-173) and event handling with the fixed-grid methods (solvers.py:130-164;
+    event_tests.py:14-49 runs every fixed method with {"step_size": 0.01, "interp": "cubic"})."""
+    out = {}
+    f = P.Spiral()
+    g = torch.Generator().manual_seed(0)
+    y0 = torch.tensor([[2., 0.]]) * (1 + 0.1 * torch.rand(1024, 1, generator=g))
+    t2 = torch.linspace(0., 5., 7)
+    for method in ("euler", "midpoint", "heun2", "heun3", "rk4"):
+        for perturb in (False, True):
+            rec = Rec(f)
+            with torch.no_grad():
+                y = torchdiffeq.odeint(rec, y0[:16], t2, method=method,
+                                       options={"step_size": 0.03, "interp": "cubic", "perturb": perturb})
+            out["cubic/%s/%d" % (method, perturb)] = {"y": y, "nfe": rec.nfe}
+    # cubic on the output grid itself, both directions and dtypes (constant problem: exact solution known)
+    for dtype in (torch.float32, torch.float64):
+        for reverse in (False, True):
+            fc, yc, tc, sol = P.construct_problem("cpu", ode="constant", reverse=reverse, dtype=dtype)
+            rec = Rec(fc)
+            with torch.no_grad():
+                y = torchdiffeq.odeint(rec, yc, tc, method="rk4", options={"step_size": 0.1, "interp": "cubic"})
+            out["cubic_grid/%s/%s" % (str(dtype).split(".")[1], "rev" if reverse else "fwd")] = {"y": y, "nfe": rec.nfe}
+    for ode in ("constant", "sine"):
+        for method in ("euler", "midpoint", "heun2", "heun3", "rk4"):
+            for dtype in (torch.float32, torch.float64):
+                for reverse in (False, True):
+                    for interp in ("cubic", "linear"):
+                        fe, ye, te, sol = P.construct_problem("cpu", ode=ode, reverse=reverse, dtype=dtype)
+                        target = sol[2]
+                        rec = Rec(fe)
+                        with torch.no_grad():
+                            et, ys = torchdiffeq.odeint(rec, ye, te[0:2], event_fn=lambda t_, y_: torch.sum(y_ - target).real,
+                                                        method=method, options={"step_size": 0.01, "interp": interp})
+                        out["event/%s/%s/%s/%s/%s" % (ode, method, str(dtype).split(".")[1], "rev" if reverse else "fwd",
+                                                    interp)] = {"event_t": et, "y": ys, "nfe": rec.nfe, "t2": te[2],
+                                                                "target": target}
+    torch.save(out, os.path.join(HERE, "fixed_extra.pt"))
+
+
 def dense():
     """odeint_dense (odeint.py:111-157): the dense-output closure of a dopri5 solve."""
     out = {}
@@ -293,5 +334,6 @@ if __name__ == "__main__":
     options_cases()
     events()
     dense()
+    fixed_extra()
     for fn in sorted(os.listdir(HERE)):
         print(fn, os.path.getsize(os.path.join(HERE, fn)))

@@ -680,3 +680,58 @@ def test_func_outputs_that_alias(mode):
                 y = tdq().odeint(f, y0, t, method=method, rtol=1e-10, atol=1e-12, options=opts)
                 assert torch.allclose(y[-1].cpu(), want[method], rtol=1e-8, atol=0), (name, method, (y[-1].cpu() - want[method]).abs().max())
     assert torch.equal(y0, torch.tensor([1.0, -2.0, 0.5, 3.0], dtype=torch.float64, device=DEV))   # input untouched
+
+
+FX = ld("fixed_extra.pt")
+
+
+@pytest.mark.parametrize("key", sorted(k for k in FX if k.startswith("cubic")))
+def test_fixed_cubic_golden(key):
+    """interp='cubic' for the fixed-grid methods (solvers.py:120-125, :166-173) against the reference's outputs; the
+    extra f(t1, y1) evaluations are counted like the reference's."""
+    case = FX[key]
+    parts = key.split("/")
+    if parts[0] == "cubic":
+        f = P.Spiral().to(DEV)
+        g = torch.Generator().manual_seed(0)
+        y0 = (torch.tensor([[2., 0.]]) * (1 + 0.1 * torch.rand(1024, 1, generator=g)))[:16].to(DEV)
+        t = torch.linspace(0., 5., 7).to(DEV)
+        method, opts, dtype = parts[1], {"step_size": 0.03, "interp": "cubic", "perturb": bool(int(parts[2]))}, torch.float32
+    else:
+        dtype = getattr(torch, parts[1])
+        f, y0, t, _ = P.construct_problem(DEV, ode="constant", reverse=parts[2] == "rev", dtype=dtype)
+        method, opts = "rk4", {"step_size": 0.1, "interp": "cubic"}
+    cf = Counted(f)
+    with torch.no_grad():
+        y = tdq().odeint(cf, y0, t, method=method, options=opts)
+    want = case["y"]
+    finite = torch.isfinite(want)                        # explicit Euler overflows on the cubic spiral, in the reference too
+    if method != "euler":
+        assert torch.equal(torch.isfinite(y.cpu()), finite)
+        tol = 1e-4 if dtype == torch.float32 else 1e-11
+        assert torch.allclose(y.cpu()[finite], want[finite], rtol=tol, atol=tol * 1e-2), (y.cpu() - want).abs().max()
+    assert cf.nfe == case["nfe"]
+
+
+@pytest.mark.parametrize("key", sorted(k for k in FX if k.startswith("event/")))
+def test_fixed_event_golden(key):
+    """Event handling with the fixed-grid methods (solvers.py:130-164): the reference's event_tests.py:14-49 thresholds
+    and the reference's own event time / state."""
+    _, ode, method, dt, direction, interp = key.split("/")
+    dtype = getattr(torch, dt)
+    case = FX[key]
+    f, y0, t, sol = P.construct_problem(DEV, ode=ode, reverse=direction == "rev", dtype=dtype)
+    target = sol[2]
+    cf = Counted(f)
+    with torch.no_grad():
+        et, ys = tdq().odeint(cf, y0, t[0:2], event_fn=lambda t_, y_: torch.sum(y_ - target).real, method=method,
+                              options={"step_size": 0.01, "interp": interp})
+    assert et.dtype == t.dtype and ys.shape == (2, *y0.shape)
+    tol = 5e-3 if method == "euler" else 1e-4                                   # event_tests.py:26-33
+    if interp == "cubic":
+        assert ((sol[2] - ys[-1]) / sol[2]).abs().max() < tol
+        assert abs((t[2] - et) / t[2]) < tol
+    close = dict(rtol=2e-5, atol=1e-6) if dtype == torch.float32 else dict(rtol=1e-9, atol=1e-11)
+    assert torch.allclose(ys.cpu(), case["y"], **close), (ys.cpu() - case["y"]).abs().max()
+    assert abs(float(et) - float(case["event_t"])) <= (2e-5 if dtype == torch.float32 else 1e-9) * abs(float(case["event_t"]))
+    assert cf.nfe == case["nfe"]

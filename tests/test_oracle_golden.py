@@ -208,3 +208,47 @@ def test_events(key):
     assert torch.allclose(ys, case["y"], rtol=close, atol=close)
     if dtype == torch.float64 and method != "dopri8":
         assert cf.nfe == case["nfe"]
+
+
+FX = ld("fixed_extra.pt")
+
+
+@pytest.mark.parametrize("key", sorted(k for k in FX if k.startswith("cubic")))
+def test_fixed_cubic_interp(key):
+    """interp='cubic' (solvers.py:120-125, :166-173): same op order as the reference => bitwise, same NFE."""
+    case = FX[key]
+    parts = key.split("/")
+    if parts[0] == "cubic":
+        f = P.Spiral()
+        g = torch.Generator().manual_seed(0)
+        y0 = (torch.tensor([[2., 0.]]) * (1 + 0.1 * torch.rand(1024, 1, generator=g)))[:16]
+        t = torch.linspace(0., 5., 7)
+        cf = O.Counter(f)
+        with torch.no_grad():
+            y = O.odeint_fixed(cf, y0, t, parts[1], grid=_grid(t, 0.03), perturb=bool(int(parts[2])), interp="cubic")
+    else:
+        dtype = getattr(torch, parts[1])
+        f, y0, t, _ = P.construct_problem("cpu", ode="constant", reverse=parts[2] == "rev", dtype=dtype)
+        cf = O.Counter(f)
+        ta = -t if parts[2] == "rev" else t
+        with torch.no_grad():
+            y = O.odeint_fixed(cf, y0, t, "rk4", grid=(-_grid(ta, 0.1) if parts[2] == "rev" else _grid(ta, 0.1)),
+                               interp="cubic")
+    assert torch.allclose(y, case["y"], rtol=0, atol=0, equal_nan=True), (y - case["y"]).abs().max()
+    assert cf.nfe == case["nfe"]
+
+
+@pytest.mark.parametrize("key", sorted(k for k in FX if k.startswith("event/")))
+def test_fixed_event(key):
+    """Event handling with the fixed-grid methods (solvers.py:130-164, event_tests.py:14-49)."""
+    _, ode, method, dt, direction, interp = key.split("/")
+    dtype = getattr(torch, dt)
+    case = FX[key]
+    f, y0, t, sol = P.construct_problem("cpu", ode=ode, reverse=direction == "rev", dtype=dtype)
+    target = sol[2]
+    cf = O.Counter(f)
+    with torch.no_grad():
+        et, ys = O.odeint_fixed_event(cf, y0, t[0], lambda t_, y_: torch.sum(y_ - target).real, method, 0.01, interp=interp,
+                                      atol=1e-9, reverse=direction == "rev")
+    assert torch.equal(ys, case["y"]) and float(et) == float(case["event_t"]), (et, case["event_t"])
+    assert cf.nfe == case["nfe"]

@@ -33,7 +33,7 @@ class FixedGridEngine:
     """Explicit fixed-step methods of fixed_grid.py:6-60 on one captured step graph."""
 
     def __init__(self, fn, n, dtype, device, *, method="rk4", t_sign=1.0, perturb=False, graph="auto",
-                 callbacks=None, pieces=None):
+                 callbacks=None, pieces=None, interp="linear"):
         if method not in FIXED_METHODS:
             raise ValueError("unknown fixed-grid method %r" % method)
         self.method = method
@@ -47,7 +47,12 @@ class FixedGridEngine:
         self.t_sign = float(t_sign)
         self.perturb = bool(perturb)
         self.callbacks = callbacks or {}
-        self.graph_opt = False if self.callbacks else graph
+        if interp not in ("linear", "cubic"):
+            raise ValueError(f"Unknown interpolation method {interp}")           # solvers.py:125
+        self.interp = interp
+        # cubic Hermite outputs need f(t1, y1) on the steps that contain an output time (solvers.py:120-122): the
+        # host knows which steps those are, so they are stepped eagerly instead of through one captured graph
+        self.graph_opt = False if (self.callbacks or interp == "cubic") else graph
         self._always_copy = False
         self.pieces = pieces            # fn returns a tuple of pieces (tuple states, the adjoint's augmented state)
         self.nfe = 0
@@ -96,6 +101,17 @@ class FixedGridEngine:
         rec_begin = torch.zeros(n_steps + 1, dtype=torch.int32)
         rec_begin[1:] = torch.cumsum(counts, 0).to(torch.int32)
         out_idx = torch.arange(1, t.numel(), dtype=torch.int32)
+        # cubic Hermite weights (solvers.py:166-173), evaluated in t's dtype like the reference's 0-dim tensors and
+        # cast to the state dtype where they meet a state tensor; dt*f carries _ReverseFunc's sign
+        h = (tj - g0) / (g1 - g0)
+        dtj = (g1 - g0)
+        h00 = (1 + 2 * h) * (1 - h) * (1 - h)
+        h10 = h * (1 - h) * (1 - h)
+        h01 = h * h * (3 - 2 * h)
+        h11 = h * h * (h - 1)
+        self._cubic = torch.stack([h00.to(T), (h10 * dtj).to(T) * self.t_sign, h01.to(T), (h11 * dtj).to(T) * self.t_sign],
+                                  dim=1).contiguous() if tj.numel() else torch.zeros(1, 4, dtype=T)
+        self._t1_T = (t1.to(T) * self.t_sign).contiguous()          # time of the extra evaluation f(t1, y1), as func sees it
         return ts.contiguous(), dtT.contiguous(), rec_begin, out_idx, mode.contiguous(), slope.contiguous(), n_steps
 
     # ---- one step -----------------------------------------------------------------------------
@@ -120,13 +136,14 @@ class FixedGridEngine:
         self._taken.add(f.data_ptr())
         return f
 
-    def _step(self):
+    def _step(self, step=None):
         try:
-            return self._step_once()
+            return self._step_once(step)
         except _RetryWithCopies:                           # nothing of the step has been committed yet
-            return self._step_once()
+            return self._step_once(step)
 
-    def _step_once(self):
+    def _stages(self):
+        """The method's stage values and y1 (in self.y1); returns the tensors func returned (k1 first)."""
         lib, dc, n, st = self.lib, self.dc, self.n, _stream()
         y0, ya, y1 = self.y0w.data_ptr(), self.ytmp.data_ptr(), self.y1.data_ptr()
         dtp, stp = self.dt_dev.data_ptr(), self.step_dev.data_ptr()
@@ -167,10 +184,34 @@ class FixedGridEngine:
             k3 = self._call_fn(self.tcur[2], self.y1, None)
             stage(9, y1, k1, None, k3)                         # y0 + dt * (k1/4 + k2*0 + 3*k3/4)
             keep += [k2, k3]
-        _lib.check(lib.tdq_fixed_emit(dc, y0, y1, self.solution.data_ptr(), self.rec_begin.data_ptr(),
-                                      self.out_idx.data_ptr(), self.mode.data_ptr(), self.slope.data_ptr(), stp,
-                                      self.ts_all.data_ptr(), self.tcur.data_ptr(), self.n_steps, n, st))
-        self.launches += 2
+        return keep
+
+    def _emit(self):
+        """Outputs of the step by linear interpolation, y0 <- y1, step counter and func times of the next step."""
+        _lib.check(self.lib.tdq_fixed_emit(self.dc, self.y0w.data_ptr(), self.y1.data_ptr(), self.solution.data_ptr(),
+                                           self.rec_begin.data_ptr(), self.out_idx.data_ptr(), self.mode.data_ptr(),
+                                           self.slope.data_ptr(), self.step_dev.data_ptr(), self.ts_all.data_ptr(),
+                                           self.tcur.data_ptr(), self.n_steps, self.n, _stream()))
+        self.launches += 1
+
+    def _emit_cubic(self, step, k1):
+        """solvers.py:120-122: f1 = func(t1, y1), then the cubic Hermite outputs of this step (one launch).  The
+        reference re-evaluates f1 for EVERY output time of the step; the call count is reproduced."""
+        lo, hi = int(self._rec_begin_cpu[step]), int(self._rec_begin_cpu[step + 1])
+        if hi <= lo:
+            return
+        for _ in range(hi - lo):
+            f1 = self._call_fn(self.t1_dev[step], self.y1, None)
+        _lib.check(self.lib.tdq_fixed_emit_cubic(self.dc, self.y0w.data_ptr(), self.y1.data_ptr(), k1.data_ptr(),
+                                                 f1.data_ptr(), self.solution.data_ptr(), self.out_idx.data_ptr(),
+                                                 self.cubic_dev.data_ptr(), lo, hi, self.n, _stream()))
+        self.launches += 1
+
+    def _step_once(self, step=None):
+        keep = self._stages()
+        if self.interp == "cubic" and step is not None:
+            self._emit_cubic(step, keep[0])
+        self._emit()
         return keep
 
     def solve(self, y0_flat, grid_cpu, t_cpu):
@@ -180,12 +221,17 @@ class FixedGridEngine:
         self.ts_all = ts.to(dev)
         self.dt_dev = dtT.to(dev)
         self.rec_begin, self.out_idx = rec_begin.to(dev), out_idx.to(dev)
+        self._rec_begin_cpu = rec_begin
+        if self.interp == "cubic":
+            # every record is written by tdq_fixed_emit_cubic; the linear emit only commits y0 <- y1 and advances
+            self.cubic_dev, self.t1_dev = self._cubic.to(dev), self._t1_T.to(dev)
+            self.rec_begin = torch.zeros_like(self.rec_begin)
         self.mode = mode.to(dev)
         self.slope = slope.to(dev) if slope.numel() else torch.zeros(1, dtype=T, device=dev)
         if self.out_idx.numel() == 0:
             self.out_idx = torch.zeros(1, dtype=torch.int32, device=dev)
             self.mode = torch.zeros(1, dtype=torch.int32, device=dev)
-        self.step_dev = torch.zeros(1, dtype=torch.int64, device=dev)
+        self.step_dev = torch.zeros(2, dtype=torch.int64, device=dev)     # [0] step counter, [1] ticket of the emit kernel
         self.tcur = self.ts_all[0].clone() if n_steps > 0 else torch.zeros(4, dtype=T, device=dev)
         kw = dict(dtype=T, device=dev)
         self.solution = torch.empty(t_cpu.numel(), self.n, **kw)
@@ -201,11 +247,11 @@ class FixedGridEngine:
             t0s, dts = grid_cpu[:-1], grid_cpu[1:] - grid_cpu[:-1]
             for s in range(n_steps):
                 cb(t0s[s].to(dev), self.y0w, dts[s].to(dev))
-                self._step()
+                self._step(s)
             torch.cuda.current_stream().synchronize()
             return self.solution
         done = 0
-        self._step()                                                  # eager first step = warm-up for capture
+        self._step(0)                                                 # eager first step = warm-up for capture
         done += 1
         graph = None
         if self.graph_opt in (True, "auto") and n_steps > 2:
@@ -229,11 +275,113 @@ class FixedGridEngine:
                 self.nfe += self._evals
                 self.launches += self._graph_launches
             else:
-                self._step()
+                self._step(done)
             done += 1
         torch.cuda.current_stream().synchronize()
         del graph
         return self.solution
+
+    # ---- event handling with a fixed step (solvers.py:130-164) ------------------------------------------------
+    def solve_until_event(self, y0_flat, t0, step_size, event_fn, atol, max_itrs=20000):
+        """Step with dt = step_size from t0 until event_fn(t, y) changes sign, then bisect on the step's interpolant
+        (event_handling.py:5-20).  event_fn takes a 0-dim tensor of the state dtype (solver time, ascending) and the
+        flat state.  Host driven by nature: one sign test per step.  Returns (event_t tensor, y(event_t))."""
+        import math
+        dev, T = self.device, self.dtype
+        kw = dict(dtype=T, device=dev)
+        t0c = torch.as_tensor(t0).detach().to("cpu").to(T).reshape(())              # t0.type_as(y0.abs())
+        dt = step_size.detach().to("cpu") if torch.is_tensor(step_size) else step_size
+        self.solution = torch.empty(1, self.n, **kw)                                # nothing is emitted
+        self.y0w = y0_flat.detach().clone()
+        self.ytmp, self.y1 = torch.empty(self.n, **kw), torch.empty(self.n, **kw)
+        self._own = {x.untyped_storage().data_ptr() for x in (self.y0w, self.ytmp, self.y1, self.solution)}
+        z32 = torch.zeros(2, dtype=torch.int32, device=dev)
+        self.rec_begin, self.out_idx, self.mode = z32, z32, z32
+        self.slope = torch.zeros(1, **kw)
+        self.n_steps = 1
+        sign0 = torch.sign(event_fn(t0c.to(dev), self.y0w))
+        itr = 0
+        while True:
+            itr += 1
+            t1c = t0c + dt                                                         # solvers.py:143
+            self._one_step_tables(t0c, dt, t1c)
+            keep = self._stages_retry()
+            sign1 = torch.sign(event_fn(t1c.to(dev), self.y1))
+            if bool(sign0 != sign1):
+                break
+            self._emit()                                                           # y0 <- y1
+            t0c = t1c
+            if itr >= max_itrs:
+                raise RuntimeError(f"Reached maximum number of iterations {max_itrs}.")
+        # the interpolant of the last step on the device, evaluated with torch ops at a handful of bisection points
+        y0, y1 = self.y0w, self.y1
+        if self.interp == "cubic":
+            f0 = keep[0] * self.t_sign
+            f1 = self._call_fn((t1c.to(T) * self.t_sign).to(dev), self.y1, None) * self.t_sign
+
+            def interp_fn(t):                                                      # solvers.py:166-173
+                h = (t - t0c) / (t1c - t0c)
+                h00 = (1 + 2 * h) * (1 - h) * (1 - h)
+                h10 = h * (1 - h) * (1 - h)
+                h01 = h * h * (3 - 2 * h)
+                h11 = h * h * (h - 1)
+                d = (t1c - t0c)
+                return float(h00) * y0 + float(h10 * d) * f0 + float(h01) * y1 + float(h11 * d) * f1
+        else:
+            def interp_fn(t):                                                      # solvers.py:175-181
+                if t == t0c:
+                    return y0
+                if t == t1c:
+                    return y1
+                slope = (t - t0c) / (t1c - t0c)
+                return y0 + float(slope) * (y1 - y0)
+        lo, hi = t0c, t1c                                                          # event_handling.py:5-20
+        nitrs = torch.ceil(torch.log((hi - lo) / atol) / math.log(2.0))
+        for _ in range(int(nitrs.long())):
+            t_mid = (hi + lo) / 2.0
+            same = bool(sign0 == torch.sign(event_fn(t_mid.to(dev), interp_fn(t_mid))))
+            if same:
+                lo = t_mid
+            else:
+                hi = t_mid
+        event_t = (lo + hi) / 2.0
+        y_ev = interp_fn(event_t).clone()
+        torch.cuda.current_stream().synchronize()
+        return event_t.to(dev), y_ev
+
+    def _stages_retry(self):
+        try:
+            return self._stages()
+        except _RetryWithCopies:
+            return self._stages()
+
+    def _one_step_tables(self, t0c, dt, t1c):
+        """Func times and dt of ONE step taken with an explicit dt (solvers.py:143-145 calls _step_func with
+        dt = step_size, not t1 - t0), evaluated like the reference's 0-dim expressions."""
+        T, dev, m = self.dtype, self.device, self.method
+        z = torch.zeros((), dtype=T)
+        if m == "rk4":
+            cols, prev_col = [t0c, t0c + dt * _ONE_THIRD, t0c + dt * _TWO_THIRDS, t1c], 3
+        elif m == "euler":
+            cols, prev_col = [t0c, z, z, z], None
+        elif m == "midpoint":
+            cols, prev_col = [t0c, t0c + 0.5 * dt, z, z], None
+        elif m == "heun2":
+            cols, prev_col = [t0c, t0c + dt * 1.0, z, z], 1
+        else:
+            cols, prev_col = [t0c, t0c + dt * (1 / 3), t0c + dt * (2 / 3), z], None
+        ts = torch.stack([c.to(T).reshape(()) for c in cols]).reshape(1, 4)
+        if self.perturb:
+            ts[:, 0] = torch.nextafter(ts[:, 0], ts[:, 0] + 1)
+            if prev_col is not None:
+                ts[:, prev_col] = torch.nextafter(ts[:, prev_col], ts[:, prev_col] - 1)
+        ts = ts * self.t_sign
+        dtT = (torch.as_tensor(dt).to(T).reshape(1)) * self.t_sign
+        self.ts_all = torch.cat([ts, ts]).to(dev)              # row 1: what tdq_fixed_emit stages for a next step
+        self.dt_dev = dtT.to(dev)
+        self.step_dev = torch.zeros(2, dtype=torch.int64, device=dev)
+        self.tcur = self.ts_all[0].clone()
+        self.n_steps = 2
 
 
 FixedRK4Engine = FixedGridEngine      # r1 name

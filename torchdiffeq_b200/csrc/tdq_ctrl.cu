@@ -135,6 +135,9 @@ __device__ void write_mailbox(TdqCtrl &c, double fin_t0, double fin_dt, int jump
     c.seq += 1;
     tdq_mailbox *m = c.mbox;
     if (!m) return;
+    // inside the device-side loop nobody polls between attempts: only the attempt that ends the solve reports
+    // (saves the system-scope fence and the stores over PCIe on every other attempt)
+    if (c.loop_handle != 0ull && !c.halt) return;
     m->status = c.status;
     m->accept = c.accept;
     m->done = c.done;

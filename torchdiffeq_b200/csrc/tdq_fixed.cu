@@ -94,14 +94,16 @@ void launch_rk4(void *out, const void *y0, const void *k1, const void *k2, const
 
 // Linear-interpolation outputs of the step that just finished, then the carry y0 <- y1.
 // mode 0: y0 (t == t0), 1: y1 (t == t1), 2: y0 + slope*(y1 - y0) (solvers.py:175-181).
+// The last block to finish (ticket in step[1]) advances the device step counter and stages the next step's four
+// func times -- every block has read step[0] by then, so no second launch is needed.
 template <typename T>
 __global__ void __launch_bounds__(kThreads)
 k_fixed_emit(T *__restrict__ y0, const T *__restrict__ y1, T *__restrict__ solution,
              const int32_t *__restrict__ rec_begin, const int32_t *__restrict__ out_idx,
-             const int32_t *__restrict__ mode, const T *__restrict__ slope, const int64_t *__restrict__ step,
-             size_t n) {
+             const int32_t *__restrict__ mode, const T *__restrict__ slope, int64_t *step,
+             const unsigned char *__restrict__ tst_all, unsigned char *__restrict__ tcur, int64_t n_steps, size_t n) {
     using A = Ar<T>;
-    const int64_t s = *step;
+    const int64_t s = step[0];
     const int lo = rec_begin[s], hi = rec_begin[s + 1];
     for (size_t i = (size_t)blockIdx.x * kThreads + threadIdx.x; i < n; i += (size_t)gridDim.x * kThreads) {
         const T a = y0[i], b = y1[i];
@@ -111,14 +113,38 @@ k_fixed_emit(T *__restrict__ y0, const T *__restrict__ y1, T *__restrict__ solut
         }
         y0[i] = b;                                            // solvers.py:126  y0 = y1
     }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        unsigned long long *ticket = reinterpret_cast<unsigned long long *>(step + 1);
+        const unsigned long long t = atomicAdd(ticket, 1ull);
+        if (t == gridDim.x - 1) {
+            *ticket = 0ull;
+            const int64_t nxt = s + 1;
+            step[0] = nxt;
+            if (nxt < n_steps)
+                for (int b = 0; b < 4 * (int)sizeof(T); ++b) tcur[b] = tst_all[nxt * 4 * sizeof(T) + b];
+        }
+    }
 }
-// Advance the device step counter and stage the next step's four func times (state dtype).
-__global__ void k_step_advance(int64_t *step, const unsigned char *tst_all, unsigned char *tcur, int64_t n_steps,
-                               int esize) {
-    const int64_t s = *step + 1;
-    *step = s;
-    if (s < n_steps)
-        for (int b = 0; b < 4 * esize; ++b) tcur[b] = tst_all[s * 4 * esize + b];
+
+// Cubic Hermite outputs of one step (solvers.py:120-125, :166-173): for records r in [lo, hi)
+//   solution[out_idx[r]] = ((c0*y0 + c1*f0) + c2*y1) + c3*f1,  c = (h00, h10*dt, h01, h11*dt) cast to T
+// f0 / f1 are RAW func outputs; the reverse-time sign is already inside c1 and c3.
+template <typename T>
+__global__ void __launch_bounds__(kThreads)
+k_fixed_emit_cubic(const T *__restrict__ y0, const T *__restrict__ y1, const T *__restrict__ f0,
+                   const T *__restrict__ f1, T *__restrict__ solution, const int32_t *__restrict__ out_idx,
+                   const T *__restrict__ coef, int lo, int hi, size_t n) {
+    using A = Ar<T>;
+    for (size_t i = (size_t)blockIdx.x * kThreads + threadIdx.x; i < n; i += (size_t)gridDim.x * kThreads) {
+        const T a = y0[i], b = y1[i], fa = f0[i], fb = f1[i];
+        for (int r = lo; r < hi; ++r) {
+            const T *c = coef + 4 * (size_t)r;
+            const T v = A::add(A::add(A::add(A::mul(c[0], a), A::mul(c[1], fa)), A::mul(c[2], b)), A::mul(c[3], fb));
+            solution[(size_t)out_idx[r] * n + i] = v;
+        }
+    }
 }
 
 struct PackArgs {
@@ -192,9 +218,23 @@ int tdq_fixed_emit(int32_t dtype, void *y0, const void *y1, void *solution, cons
     if (blocks > 148 * 8) blocks = 148 * 8;
     TDQ_DISPATCH_T(dtype, (k_fixed_emit<T><<<(unsigned)blocks, kThreads, 0, st>>>(
                                (T *)y0, (const T *)y1, (T *)solution, rec_begin_dev, out_idx_dev, mode_dev,
-                               (const T *)slope_dev, step_dev, n)));
-    k_step_advance<<<1, 1, 0, st>>>(step_dev, (const unsigned char *)tstage_all_dev, (unsigned char *)tstage_cur_dev,
-                                    n_steps, dtype == TDQ_F32 ? 4 : 8);
+                               (const T *)slope_dev, step_dev, (const unsigned char *)tstage_all_dev,
+                               (unsigned char *)tstage_cur_dev, n_steps, n)));
+    TDQ_CHECK_CUDA(cudaGetLastError());
+    return TDQ_OK;
+}
+
+int tdq_fixed_emit_cubic(int32_t dtype, const void *y0, const void *y1, const void *f0, const void *f1, void *solution,
+                         const int32_t *out_idx_dev, const void *coef_dev, int32_t rec_lo, int32_t rec_hi, size_t n,
+                         void *stream) {
+    TDQ_REQUIRE(y0 && y1 && f0 && f1 && solution && out_idx_dev && coef_dev, "null argument");
+    TDQ_REQUIRE(rec_lo >= 0 && rec_hi >= rec_lo, "bad record range");
+    if (n == 0 || rec_hi == rec_lo) return TDQ_OK;
+    size_t blocks = (n + kThreads - 1) / kThreads;
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    TDQ_DISPATCH_T(dtype, (k_fixed_emit_cubic<T><<<(unsigned)blocks, kThreads, 0, (cudaStream_t)stream>>>(
+                               (const T *)y0, (const T *)y1, (const T *)f0, (const T *)f1, (T *)solution, out_idx_dev,
+                               (const T *)coef_dev, rec_lo, rec_hi, n)));
     TDQ_CHECK_CUDA(cudaGetLastError());
     return TDQ_OK;
 }

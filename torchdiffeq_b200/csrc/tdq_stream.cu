@@ -148,7 +148,7 @@ k_combine_final(const TdqCtrl *__restrict__ c, int row, T *__restrict__ out, T *
                 KPtrs kp, FinalMap fm, size_t n) {
     if (c->halt) return;
     using A = Ar<T>;
-    constexpr int THREADS = 256, U = 2;
+    constexpr int THREADS = 256, U = (NU <= 5) ? 2 : 1;     // wide rows: one vector per operand keeps two blocks per SM
     T cr[NU], ce[NU];
     bool ur[NU], ue[NU];
     const T *k[NU];
@@ -234,7 +234,7 @@ k_combine_final(const TdqCtrl *__restrict__ c, int row, T *__restrict__ out, T *
 template <typename T, int NU>
 int launch_final(const TdqCtrl *c, int row, void *out, void *err_out, const void *y0, const KPtrs &kp,
                  const FinalMap &fm, size_t n, bool vec, cudaStream_t st) {
-    constexpr int THREADS = 256, U = 2;
+    constexpr int THREADS = 256, U = (NU <= 5) ? 2 : 1;
     if (vec) {
         const size_t nvec = n / Vec<T>::N;
         size_t blocks = (nvec + (size_t)THREADS * U - 1) / ((size_t)THREADS * U);

@@ -205,8 +205,6 @@ def normalise(func, y0, t, rtol, atol, method, options, event_fn, adjoint=False)
     # event function on the flat state, in the solver's ascending time (misc.py:224-225, :281-282)
     p.event_fn = None
     if event_fn is not None:
-        if method not in ADAPTIVE_METHODS:
-            raise NotImplementedError("event handling is implemented for the adaptive methods only")
         unflat = (lambda yf: p.layout.views(yf)) if p.is_tuple else (lambda yf: yf.view(p.shape))
         sign_ = p.t_sign
         p.event_fn = lambda t_, y_flat: event_fn(t_ * sign_, unflat(y_flat))
@@ -454,9 +452,20 @@ def _solve(p):
     grid = fixed_grid(p.method, o, p.original_func, y0_view, p.t_cpu)
     eng = FixedGridEngine(p.fn, p.n, p.dtype, p.device, method=p.method, t_sign=p.t_sign,
                           perturb=o.get("perturb", False), graph=_resolve_graph(o.get("graph", "auto"), p.original_func),
-                          callbacks=p.callbacks, pieces=p.pieces)
+                          callbacks=p.callbacks, pieces=p.pieces, interp=o.get("interp", "linear"))
     sol = eng.solve(p.y0_flat, grid, p.t_cpu)
     return sol, eng
+
+
+def _cubic_or_linear(interp):
+    if interp not in ("linear", "cubic"):                                              # solvers.py:125
+        raise ValueError(f"Unknown interpolation method {interp}")
+    return interp
+
+
+def fixed_event_solve(eng, y0_flat, t0, step_size, event_fn, atol):
+    """solvers.py:130-164 on a FixedGridEngine: (event_t, y(event_t))."""
+    return eng.solve_until_event(y0_flat, t0, step_size, event_fn, atol)
 
 
 _FIXED_NAMES = {"euler": "Euler", "midpoint": "Midpoint", "heun2": "Heun2", "heun3": "Heun3", "rk4": "RK4"}
@@ -473,11 +482,7 @@ def fixed_grid(method, o, func, y0_view, t_cpu):
         if gc is not None:
             raise ValueError("step_size and grid_constructor are mutually exclusive arguments.")   # solvers.py:79
         grid_constructor = grid_from_step_size(step_size)
-    interp = o.get("interp", "linear")
-    if interp == "cubic":
-        raise NotImplementedError("interp='cubic' is not implemented on the B200 path yet")
-    if interp != "linear":
-        raise ValueError(f"Unknown interpolation method {interp}")
+    _cubic_or_linear(o.get("interp", "linear"))
     grid = grid_constructor(func, y0_view, t_cpu).detach().to("cpu")
     assert grid[0] == t_cpu[0] and grid[-1] == t_cpu[-1]                               # solvers.py:104
     return grid
@@ -485,6 +490,21 @@ def fixed_grid(method, o, func, y0_view, t_cpu):
 
 def _solve_event(p):
     """odeint.py:97-100 + solvers.py:41-49: integrate until the event; returns (event_t tensor like t, [2, n])."""
+    if p.method in FIXED_METHODS:                                                      # solvers.py:130-164
+        o = p.options
+        _warn_unused(_FIXED_NAMES[p.method], o, _FIXED_OPTIONS)
+        if o.get("step_size") is None:
+            raise AssertionError("Event handling for fixed step solvers currently requires `step_size` to be provided "
+                                 "in options.")
+        if o.get("grid_constructor") is not None:
+            raise ValueError("step_size and grid_constructor are mutually exclusive arguments.")
+        eng = FixedGridEngine(p.fn, p.n, p.dtype, p.device, method=p.method, t_sign=p.t_sign,
+                              perturb=o.get("perturb", False), graph=False, pieces=p.pieces,
+                              interp=_cubic_or_linear(o.get("interp", "linear")))
+        tol = p.atol if p.atol is not None else float(p.atol_vec.min())
+        event_t, y_event = fixed_event_solve(eng, p.y0_flat, p.t_cpu[0], o["step_size"], p.event_fn, tol)
+        sol = torch.stack([p.y0_flat.to(p.dtype), y_event], dim=0)
+        return float(event_t) * p.t_sign, sol, eng
     eng = _make_adaptive_engine(p, p.method, p.rtol, p.atol, p.rtol_vec, p.atol_vec,
                                 dict(p.options, run_ahead=0, graph=False), segs=p.segs, pieces=p.pieces,
                                 norm_fn=p.norm_fn, q_view=p.q_view, callbacks=p.callbacks, keep_interp=True)
