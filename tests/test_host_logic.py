@@ -136,3 +136,50 @@ def test_cache_signature_tracks_reachable_tensors():
     m.lin.training = True                    # a submodule's flag (m.eval() above cleared it)
     assert _func_signature(m) != k
     hash(_func_signature(m))
+
+
+def test_plugin_registration_and_seam_identification():
+    """torchdiffeq_b200.plugin on the CPU: registration is in place and reversible, CPU states keep the previous
+    solver class, and the two identity tests the seam forces on us (default RMS norm, null callback) recognise the
+    reference's actual objects when the reference is importable."""
+    import os
+    import sys
+    from torchdiffeq_b200 import plugin
+
+    class Prev:
+        def __init__(self, func, y0, **kw):
+            self.kw = kw
+
+        @classmethod
+        def valid_callbacks(cls):
+            return set()
+    solvers = {"dopri5": Prev, "rk4": Prev}
+    replaced = plugin.register(solvers, methods=("dopri5", "rk4", "tsit5"))
+    assert replaced == {"dopri5": Prev, "rk4": Prev, "tsit5": None}
+    assert solvers["dopri5"].valid_callbacks() == {"callback_step", "callback_accept_step", "callback_reject_step"}
+    assert solvers["rk4"].valid_callbacks() == {"callback_step"}
+    s = solvers["dopri5"](func=lambda t, y: y, y0=torch.zeros(3), rtol=1e-3, atol=1e-4, norm=None)
+    assert isinstance(s, Prev) and s.kw["rtol"] == 1e-3             # CPU tensors: the reference's own class
+    plugin.register(solvers, methods=("dopri5",))                   # registering twice does not nest dispatchers
+    assert solvers["dopri5"].cpu_cls is Prev
+    plugin.unregister(replaced, solvers)
+    assert solvers == {"dopri5": Prev, "rk4": Prev}
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    for path in (os.path.join(root, "baseline", "_ref"), "/root/reference"):
+        if os.path.isdir(os.path.join(path, "torchdiffeq")):
+            sys.path.insert(0, path)
+            import importlib
+            misc = importlib.import_module("torchdiffeq._impl.misc")
+            assert plugin._is_default_rms(misc._rms_norm) and not plugin._is_default_rms(misc._mixed_norm)
+            assert plugin._is_null_callback(misc._null_callback) and not plugin._is_null_callback(lambda *a: None)
+            assert plugin._unwrap_perturb(misc._PerturbFunc(abs)) is abs
+            odeint_mod = importlib.import_module("torchdiffeq._impl.odeint")
+            rep = plugin.register()                                  # the reference's own dict, in place
+            assert isinstance(odeint_mod.SOLVERS["dopri5"], plugin._Dispatch)
+            assert importlib.import_module("torchdiffeq._impl.adjoint").SOLVERS is odeint_mod.SOLVERS
+            # a CPU solve through the patched registry still runs the reference's solver
+            y = odeint_mod.odeint(lambda t, y: -y, torch.ones(3), torch.tensor([0., 1.]), method="dopri5")
+            assert torch.allclose(y[-1], torch.exp(torch.tensor(-1.0)).expand(3), atol=1e-5)
+            plugin.unregister(rep)
+            assert not isinstance(odeint_mod.SOLVERS["dopri5"], plugin._Dispatch)
+            break
