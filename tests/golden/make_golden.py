@@ -15,6 +15,7 @@ Outputs (committed):
                           rtol=atol in {1e-3, 1e-6, 1e-9} (+ dopri8 at 1e-12)
     options.pt            step_t / min_step / max_step / first_step / tuple-state / vector-tol cases
     fixed_extra.pt        interp='cubic' and event handling for the fixed-grid methods
+    backprop.pt           gradients of plain odeint (autograd through the reference's solver operations)
 """
 import json
 import os
@@ -306,6 +307,49 @@ def fixed_extra():
     torch.save(out, os.path.join(HERE, "fixed_extra.pt"))
 
 
+def backprop():
+    """Plain odeint differentiated by autograd through the solver's own operations (rk_common.py:31-90,
+    gradient_tests.py:13-23, api_tests.py:28-39): gradients w.r.t. y0, t and the parameters of func."""
+    out = {}
+    for dtype in (torch.float32, torch.float64):
+        dn = str(dtype).split(".")[1]
+        for name, tv in (("span", [0., 1.]), ("multi", [0., 0.4, 1.0]), ("rev", [1.0, 0.3, 0.])):
+            for method in ("dopri5", "tsit5", "bosh3", "rk4", "midpoint", "euler"):
+                f = P.MLPField(dim=8, hidden=16, seed=0, dtype=dtype)
+                g = torch.Generator().manual_seed(1)
+                y0 = torch.randn(32, 8, generator=g).to(dtype).requires_grad_(True)
+                t = torch.tensor(tv, dtype=torch.float64).requires_grad_(True)
+                tols = dict(rtol=1e-6, atol=1e-8) if dtype == torch.float64 else dict(rtol=1e-4, atol=1e-6)
+                kw = tols if method in ("dopri5", "tsit5", "bosh3") else {}
+                opts = {"step_size": 0.05} if method in ("rk4", "midpoint", "euler") and name != "multi" else None
+                y = torchdiffeq.odeint(f, y0, t, method=method, options=opts, **kw)
+                loss = y[-1].pow(2).mean() + (y[1].sum() * 0.01 if len(tv) > 2 else 0)
+                loss.backward()
+                out["mlp/%s/%s/%s" % (name, method, dn)] = {
+                    "y": y.detach().clone(), "gy0": y0.grad.clone(), "gt": t.grad.clone(),
+                    "gp": [q.grad.clone() for q in f.parameters()], "t": t.detach().clone(), "opts": opts, "kw": kw}
+    # a time-dependent field with parameters: the constant problem (problems.py:7-17), all outputs weighted
+    for method in ("dopri5", "dopri8", "adaptive_heun", "fehlberg2", "rk4", "heun3", "heun2"):
+        f, y0, t, _ = P.construct_problem("cpu", ode="constant", dtype=torch.float64)
+        y0 = y0.requires_grad_(True)
+        t = t.detach().clone().requires_grad_(True)
+        y = torchdiffeq.odeint(f, y0, t, method=method)
+        torch.manual_seed(0)
+        w = torch.rand_like(y)
+        y.backward(w)
+        out["constant/%s" % method] = {"y": y.detach().clone(), "w": w, "gy0": y0.grad.clone(), "gt": t.grad.clone(),
+                                       "gp": [q.grad.clone() for q in f.parameters()]}
+    # tuple state (api_tests.py:28-39)
+    f, y0, t, _ = P.construct_problem("cpu", ode="constant", dtype=torch.float64)
+    y0 = y0.requires_grad_(True)
+    t = t.detach().clone().requires_grad_(True)
+    tuple_f = lambda t_, y_: (f(t_, y_[0]), f(t_, y_[1]))
+    ys = torchdiffeq.odeint(tuple_f, (y0, y0 + 0.1), t, method="dopri5")
+    (ys[0].sum() + 2 * ys[1][-1].sum()).backward()
+    out["tuple/dopri5"] = {"gy0": y0.grad.clone(), "gt": t.grad.clone(), "gp": [q.grad.clone() for q in f.parameters()]}
+    torch.save(out, os.path.join(HERE, "backprop.pt"))
+
+
 def dense():
     """odeint_dense (odeint.py:111-157): the dense-output closure of a dopri5 solve."""
     out = {}
@@ -335,5 +379,6 @@ if __name__ == "__main__":
     events()
     dense()
     fixed_extra()
+    backprop()
     for fn in sorted(os.listdir(HERE)):
         print(fn, os.path.getsize(os.path.join(HERE, fn)))

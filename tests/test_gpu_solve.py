@@ -369,9 +369,87 @@ def test_jump_t_golden(key):
                                                           "step_t": torch.tensor([0.5], device=DEV)})
 
 
-def test_plain_odeint_with_grad_routes_to_adjoint():
-    """gradient_tests.py style: gradients requested through plain odeint on an nn.Module are served by the
-    adjoint method (with a warning); they must agree with odeint_adjoint's."""
+BP = ld("backprop.pt")
+
+
+def _rel(a, b):
+    return float((a - b).abs().max() / max(float(b.abs().max()), 1e-12))
+
+
+@pytest.mark.parametrize("key", sorted(k for k in BP if k.startswith("mlp/")))
+def test_backprop_golden_mlp(key):
+    """Plain odeint under autograd (rk_common.py:31-90 recorded by autograd in the reference; backprop.py here):
+    gradients w.r.t. y0, every output time and the parameters against the unmodified reference's, adaptive and
+    fixed-grid methods, both time directions, both dtypes."""
+    case = BP[key]
+    _, name, method, dn = key.split("/")
+    dtype = getattr(torch, dn)
+    f = P.MLPField(dim=8, hidden=16, seed=0, dtype=dtype).to(DEV)
+    y0 = torch.randn(32, 8, generator=torch.Generator().manual_seed(1)).to(dtype).to(DEV).requires_grad_(True)
+    t = case["t"].to(DEV).requires_grad_(True)
+    y = tdq().odeint(f, y0, t, method=method, options=case["opts"], **case["kw"])
+    assert y.requires_grad
+    loss = y[-1].pow(2).mean() + (y[1].sum() * 0.01 if len(t) > 2 else 0)
+    loss.backward()
+    tol = 2e-4 if dtype == torch.float32 else 2e-5          # adaptive: step sequences differ by the stage-sum order
+    if method in ("rk4", "midpoint", "euler"):
+        tol = 2e-4 if dtype == torch.float32 else 1e-9      # fixed grid: the same discrete map
+    assert torch.allclose(y.detach().cpu(), case["y"], rtol=1e-4, atol=1e-6)
+    assert _rel(y0.grad.cpu(), case["gy0"]) < tol, _rel(y0.grad.cpu(), case["gy0"])
+    assert _rel(t.grad.cpu(), case["gt"]) < 5 * tol, (t.grad.cpu(), case["gt"])
+    for q, w in zip(f.parameters(), case["gp"]):
+        assert _rel(q.grad.cpu(), w) < tol, _rel(q.grad.cpu(), w)
+
+
+@pytest.mark.parametrize("key", sorted(k for k in BP if k.startswith("constant/")))
+def test_backprop_golden_constant(key):
+    """A time-dependent field with parameters, every output row weighted (gradient_tests.py:41-86 style)."""
+    case = BP[key]
+    method = key.split("/")[1]
+    f, y0, t, _ = P.construct_problem(DEV, ode="constant", dtype=torch.float64)
+    y0 = y0.requires_grad_(True)
+    t = t.detach().clone().requires_grad_(True)
+    y = tdq().odeint(f, y0, t, method=method)
+    y.backward(case["w"].to(DEV))
+    tol = 1e-9 if method in ("rk4", "heun3", "heun2") else 1e-5
+    assert _rel(y0.grad.cpu(), case["gy0"]) < tol
+    assert _rel(t.grad.cpu(), case["gt"]) < 10 * tol, (t.grad.cpu(), case["gt"])
+    for q, w in zip(f.parameters(), case["gp"]):
+        assert _rel(q.grad.cpu(), w) < 10 * tol
+
+
+def test_backprop_tuple_state_and_closures():
+    """api_tests.py:28-39: a tuple state through a lambda that closes over the module -- its parameters are found in
+    the closure; plain callables without parameters differentiate w.r.t. y0 and t."""
+    case = BP["tuple/dopri5"]
+    f, y0, t, _ = P.construct_problem(DEV, ode="constant", dtype=torch.float64)
+    y0 = y0.requires_grad_(True)
+    t = t.detach().clone().requires_grad_(True)
+    tuple_f = lambda t_, y_: (f(t_, y_[0]), f(t_, y_[1]))
+    ys = tdq().odeint(tuple_f, (y0, y0 + 0.1), t, method="dopri5")
+    (ys[0].sum() + 2 * ys[1][-1].sum()).backward()
+    assert _rel(y0.grad.cpu(), case["gy0"]) < 1e-5 and _rel(t.grad.cpu(), case["gt"]) < 1e-4
+    for q, w in zip(f.parameters(), case["gp"]):
+        assert _rel(q.grad.cpu(), w) < 1e-4
+    yy = torch.tensor([1.0, 2.0], dtype=torch.float64, device=DEV, requires_grad=True)
+    tt = torch.tensor([0., 0.5, 1.], dtype=torch.float64, device=DEV)
+    out = tdq().odeint(lambda t_, y_: -y_, yy, tt, rtol=1e-9, atol=1e-11)
+    out[-1].sum().backward()
+    assert torch.allclose(yy.grad, torch.exp(torch.tensor(-1.0, dtype=torch.float64, device=DEV)).expand(2), rtol=1e-7)
+
+
+@pytest.mark.parametrize("method", ["dopri5", "bosh3", "rk4", "midpoint"])
+def test_backprop_gradcheck(method):
+    """gradient_tests.py:13-23: torch.autograd.gradcheck of odeint w.r.t. (y0, t)."""
+    f, y0, t, _ = P.construct_problem(DEV, ode="constant", dtype=torch.float64)
+    y0 = y0.detach().clone().requires_grad_(True)
+    t = t[:4].detach().clone().requires_grad_(True)
+    func = lambda y0_, t_: tdq().odeint(f, y0_, t_, method=method)
+    assert torch.autograd.gradcheck(func, (y0, t))
+
+
+def test_backprop_agrees_with_adjoint():
+    """gradient_tests.py:34-86: discretise-then-differentiate and the continuous adjoint agree to solver accuracy."""
     f = P.MLPField(dim=8, hidden=16, seed=0, dtype=torch.float64).to(DEV)
     y0 = torch.randn(16, 8, generator=torch.Generator().manual_seed(1), dtype=torch.float64).to(DEV)
     t = torch.tensor([0., 0.5, 1.], dtype=torch.float64, device=DEV)
@@ -379,16 +457,11 @@ def test_plain_odeint_with_grad_routes_to_adjoint():
     for api in ("odeint", "odeint_adjoint"):
         f.zero_grad()
         yy = y0.clone().requires_grad_(True)
-        with warnings.catch_warnings():
-            warnings.simplefilter("ignore")
-            y = getattr(tdq(), api)(f, yy, t, method="dopri5", rtol=1e-8, atol=1e-10)
+        y = getattr(tdq(), api)(f, yy, t, method="dopri5", rtol=1e-9, atol=1e-11)
         y[-1].pow(2).sum().backward()
         grads.append([yy.grad.clone()] + [q.grad.clone() for q in f.parameters()])
     for a, b in zip(*grads):
-        assert torch.equal(a, b)
-    with pytest.raises(NotImplementedError):
-        yy = y0.clone().requires_grad_(True)
-        tdq().odeint(lambda t_, y_: -y_, yy, t)
+        assert _rel(a, b) < 1e-6
 
 
 def test_adjoint_time_gradients_analytic():

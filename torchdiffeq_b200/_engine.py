@@ -619,6 +619,32 @@ class AdaptiveEngine:
         torch.cuda.current_stream().synchronize()
         return self.solution, times, coeffs
 
+    # ---- taped solve for the differentiable (non-adjoint) odeint (torchdiffeq_b200/backprop.py) ------------------
+    def solve_taped(self, y0_flat, t64, t_start=None):
+        """Lock-step solve that records every ACCEPTED step: start time, step size, the (y0, k_0) pair it started from
+        (clones: 2 n elements per step), the output rows it produced and whether it followed a jump_t re-evaluation.
+        Returns (solution, tape)."""
+        n_out = self._begin(y0_flat, t64, t_start)
+        torch.cuda.current_stream().synchronize()
+        mb = self.mbox_host.contents
+        self._raise_if_failed(mb)
+        tape, issued, cursor, first, jumped = [], 0, 1, True, None
+        while n_out > 1:
+            issued, mb = self._lockstep_attempt(issued, mb)
+            if mb.accept:
+                prev = (mb.par ^ 1) & 1                                     # the pair the accepted step started from
+                k0 = self.kbuf[prev]
+                tape.append(dict(t0=float(mb.att_t0), dt=float(mb.att_dt), y0=self.ybuf[prev].clone(), k0=k0.clone(),
+                                 out_lo=cursor, out_hi=int(mb.out_cursor), first=first, jumped_into=jumped))
+                cursor, first = int(mb.out_cursor), False
+                jumped = True if mb.on_jump_t else None
+            if mb.done:
+                break
+        torch.cuda.current_stream().synchronize()
+        self.n_accept, self.n_reject = int(mb.n_accept), int(mb.n_reject)
+        self.n_attempts = self.n_accept + self.n_reject
+        return self.solution, tape
+
     # ---- event handling (solvers.py:38-49, rk_common.py:252-264, event_handling.py:5-20) ----------------
     def solve_until_event(self, y0_flat, t0, event_fn, tol):
         """Integrate from t0 until event_fn(t, y) changes sign, then bisect on the dense output of the last

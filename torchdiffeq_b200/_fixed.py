@@ -137,6 +137,8 @@ class FixedGridEngine:
         return f
 
     def _step(self, step=None):
+        if getattr(self, "_taping", None) is not None:
+            self._taping.append({"y0": self.y0w.clone()})
         try:
             return self._step_once(step)
         except _RetryWithCopies:                           # nothing of the step has been committed yet
@@ -215,6 +217,10 @@ class FixedGridEngine:
         return keep
 
     def solve(self, y0_flat, grid_cpu, t_cpu):
+        self._taping = None
+        return self._solve_impl(y0_flat, grid_cpu, t_cpu)
+
+    def _solve_impl(self, y0_flat, grid_cpu, t_cpu):
         dev, T = self.device, self.dtype
         ts, dtT, rec_begin, out_idx, mode, slope, n_steps = self._tabulate(grid_cpu, t_cpu)
         self.n_steps = n_steps
@@ -280,6 +286,22 @@ class FixedGridEngine:
         torch.cuda.current_stream().synchronize()
         del graph
         return self.solution
+
+    # ---- taped solve for the differentiable (non-adjoint) odeint (torchdiffeq_b200/backprop.py) ------------------
+    def solve_taped(self, y0_flat, grid_cpu, t_cpu):
+        """Eager solve that keeps the state every step started from and the output records it produced."""
+        graph_opt, self.graph_opt = self.graph_opt, False
+        ts, dtT, rec_begin, out_idx, mode, slope, n_steps = self._tabulate(grid_cpu, t_cpu)
+        self._taping = tape = []
+        try:
+            sol = self._solve_impl(y0_flat, grid_cpu, t_cpu)
+        finally:
+            self.graph_opt, self._taping = graph_opt, None
+        for k, st in enumerate(tape):
+            st["k"], st["perturb"] = k, self.perturb
+            st["outs"] = [(int(out_idx[r]), int(mode[r]), float(slope[r]))
+                          for r in range(int(rec_begin[k]), int(rec_begin[k + 1]))]
+        return sol, tape
 
     # ---- event handling with a fixed step (solvers.py:130-164) ------------------------------------------------
     def solve_until_event(self, y0_flat, t0, step_size, event_fn, atol, max_itrs=20000):
@@ -376,7 +398,8 @@ class FixedGridEngine:
             if prev_col is not None:
                 ts[:, prev_col] = torch.nextafter(ts[:, prev_col], ts[:, prev_col] - 1)
         ts = ts * self.t_sign
-        dtT = (torch.as_tensor(dt).to(T).reshape(1)) * self.t_sign
+        dt_t = dt if torch.is_tensor(dt) else torch.tensor(dt, dtype=torch.float64)   # a Python float is a double
+        dtT = (dt_t.to(T).reshape(1)) * self.t_sign
         self.ts_all = torch.cat([ts, ts]).to(dev)              # row 1: what tdq_fixed_emit stages for a next step
         self.dt_dev = dtT.to(dev)
         self.step_dev = torch.zeros(2, dtype=torch.int64, device=dev)

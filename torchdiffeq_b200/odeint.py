@@ -471,7 +471,7 @@ def fixed_event_solve(eng, y0_flat, t0, step_size, event_fn, atol):
 _FIXED_NAMES = {"euler": "Euler", "midpoint": "Midpoint", "heun2": "Heun2", "heun3": "Heun3", "rk4": "RK4"}
 
 
-def fixed_grid(method, o, func, y0_view, t_cpu):
+def fixed_grid(method, o, func, y0_view, t_cpu, keep_graph=False):
     """Option handling and time grid of FixedGridODESolver (solvers.py:55-79, :85-96, :103-104) for an
     ascending CPU `t_cpu`; the caller has already wrapped a user grid_constructor for reversed time."""
     _warn_unused(_FIXED_NAMES[method], o, _FIXED_OPTIONS)
@@ -483,7 +483,8 @@ def fixed_grid(method, o, func, y0_view, t_cpu):
             raise ValueError("step_size and grid_constructor are mutually exclusive arguments.")   # solvers.py:79
         grid_constructor = grid_from_step_size(step_size)
     _cubic_or_linear(o.get("interp", "linear"))
-    grid = grid_constructor(func, y0_view, t_cpu).detach().to("cpu")
+    grid = grid_constructor(func, y0_view, t_cpu)
+    grid = grid.to("cpu") if keep_graph else grid.detach().to("cpu")
     assert grid[0] == t_cpu[0] and grid[-1] == t_cpu[-1]                               # solvers.py:104
     return grid
 
@@ -524,9 +525,6 @@ def _func_requires_grad(func):
     if isinstance(func, torch.nn.Module):
         return any(q.requires_grad for q in func.parameters())
     return False
-
-
-_WARNED_ADJOINT_ROUTE = False
 
 
 class _ImplicitFnGradientRerouting(torch.autograd.Function):
@@ -625,36 +623,79 @@ def odeint_dense(func, y0, t0, t1, *, rtol=1e-7, atol=1e-9, method=None, options
     return dense_output_fn
 
 
+def _odeint_backprop(p, func, y0, t, params, _stats):
+    """Plain odeint under autograd: gradients of the discrete solve w.r.t. y0, t and every parameter func reaches
+    (odeint.py:49-108 differentiated as the reference's recorded graph would be; see backprop.py)."""
+    from .backprop import _BackpropFunction, adaptive_tableau
+    if p.is_tuple:
+        y0_flat = p.layout.flatten(list(y0))          # differentiable w.r.t. every piece
+    else:
+        y0_flat = y0.reshape(-1)
+    holder = {}
+
+    def run():
+        if p.method in ADAPTIVE_METHODS:
+            eng = _make_adaptive_engine(p, p.method, p.rtol, p.atol, p.rtol_vec, p.atol_vec,
+                                        dict(p.options, run_ahead=0, graph=False), segs=p.segs, pieces=p.pieces,
+                                        norm_fn=p.norm_fn, q_view=p.q_view, callbacks=p.callbacks)
+            t64 = p.t_cpu.to(torch.float64).to(p.device)
+            sol, tape = eng.solve_taped(p.y0_flat, t64, t_start=float(p.t_cpu[0]))
+            holder["eng"] = eng
+            return sol.clone(), {"kind": "adaptive", "tape": tape, "tab": adaptive_tableau(p.method)}
+        o = p.options
+        if o.get("interp", "linear") != "linear":
+            raise NotImplementedError("gradients through interp='cubic' are not implemented (use the default linear "
+                                      "interpolation, or odeint_adjoint)")
+        y0_view = p.layout.views(p.y0_flat) if p.is_tuple else p.y0_flat.view(p.shape)
+        with torch.enable_grad():                     # the grid as a differentiable function of the output times
+            t_req = p.t_cpu.detach().clone().requires_grad_(True)
+            grid_req = fixed_grid(p.method, o, p.original_func, y0_view, t_req, keep_graph=True)
+        grid = grid_req.detach()
+        eng = FixedGridEngine(p.fn, p.n, p.dtype, p.device, method=p.method, t_sign=p.t_sign,
+                              perturb=o.get("perturb", False), graph=False, callbacks=p.callbacks, pieces=p.pieces)
+        sol, tape = eng.solve_taped(p.y0_flat, grid, p.t_cpu)
+        holder["eng"] = eng
+        return sol, {"kind": "fixed", "tape": tape, "grid": grid, "grid_req": grid_req, "t_req": t_req}
+    with on_solver_stream(p.device) as ss:
+        sol = _BackpropFunction.apply(p, run, t, y0_flat, *params)
+        ss.publish(sol)
+    eng = holder.get("eng")
+    if eng is not None:
+        _LAST_STATS.clear()
+        _LAST_STATS.update(nfe=eng.nfe, launches=getattr(eng, "launches", 0), attempts=getattr(eng, "n_attempts", None),
+                           n_accept=getattr(eng, "n_accept", None), n_reject=getattr(eng, "n_reject", None))
+        if _stats is not None:
+            _stats.update(_LAST_STATS)
+    return _unflatten(p, sol)
+
+
 def odeint(func, y0, t, *, rtol=1e-7, atol=1e-9, method=None, options=None, event_fn=None, _stats=None):
     """Integrate dy/dt = func(t, y), y(t[0]) = y0 and return y at every t (odeint.py:49-108).
 
     Arguments, defaults, output shape/dtype and errors are the reference's.  `options` additionally
     accepts `graph` (True/False/'auto'), `run_ahead` (int; 0 reproduces the reference's exact func
     call sequence) and `process_group` (batch-sharded solve with a common step size).
-    Gradients are provided by odeint_adjoint; plain odeint returns a tensor without history.
+    Under autograd the result carries the gradient of the discrete solve w.r.t. y0, t and func's parameters
+    (backprop.py); odeint_adjoint gives the continuous adjoint instead.
     """
     p = normalise(func, y0, t, rtol, atol, method, options, event_fn)
     if torch.is_grad_enabled():
+        from .backprop import discover_params
         y_req = any(y_.requires_grad for y_ in y0) if p.is_tuple else y0.requires_grad
-        if y_req or t.requires_grad or _func_requires_grad(func):
-            # The reference backpropagates through the solver's own ops here.  That discretise-then-
-            # differentiate path is not part of the B200 hot path (SURVEY.md section 8(f) item 4); for an
-            # nn.Module the adjoint method yields the same gradients up to the solver tolerance, so it is used
-            # instead (loudly).  A plain callable's parameters cannot be discovered, hence the error.
-            if isinstance(func, torch.nn.Module):
-                global _WARNED_ADJOINT_ROUTE
-                if not _WARNED_ADJOINT_ROUTE:
-                    _WARNED_ADJOINT_ROUTE = True
-                    warnings.warn("torchdiffeq_b200.odeint: gradients are computed with the adjoint method "
-                                  "(odeint_adjoint); backpropagation through the solver internals is not implemented",
+        params = discover_params(func)
+        if y_req or t.requires_grad or params:
+            if p.event_fn is not None:
+                # gradients through an event solve: the reference backpropagates through the solver up to the event
+                # and through the bisection's interpolant; here the adjoint method serves that case
+                if isinstance(func, torch.nn.Module):
+                    warnings.warn("torchdiffeq_b200.odeint(event_fn=...): gradients are computed with the adjoint method",
                                   stacklevel=2)
-                from .adjoint import odeint_adjoint
-                return odeint_adjoint(func, y0, t, rtol=rtol, atol=atol, method=method, options=options,
-                                      event_fn=event_fn)
-            raise NotImplementedError(
-                "backpropagation through the solver's internals is not part of the B200 hot path "
-                "(SURVEY.md section 8(f) item 4); use odeint_adjoint(..., adjoint_params=...) for gradients or call "
-                "odeint under torch.no_grad()")
+                    from .adjoint import odeint_adjoint
+                    return odeint_adjoint(func, y0, t, rtol=rtol, atol=atol, method=method, options=options,
+                                          event_fn=event_fn)
+                raise NotImplementedError("gradients through odeint(event_fn=...) need an nn.Module func (they are "
+                                          "computed by odeint_adjoint)")
+            return _odeint_backprop(p, func, y0, t, params, _stats)
     with torch.no_grad(), on_solver_stream(p.device) as ss:
         if p.event_fn is not None:
             event_t, sol, eng = _solve_event(p)
