@@ -36,13 +36,16 @@ RTOL, ATOL = 1e-5, 1e-7
 METRIC = "trajectories/sec (dopri5, batch=65536 dim=128)"
 
 
-def make_problem(device, batch, rank=0):
+def make_problem(device, batch, rank=0, world=1):
+    """The workload: ONE seeded batch of `batch * world` trajectories (y0 = randn, generator
+    seed 1); rank r owns rows [r*batch, (r+1)*batch).  Returns (func, this rank's rows, t, the whole batch)."""
     import problems as P
     f = P.BatchedLinear(DIM, torch.float32).to(device)
-    g = torch.Generator().manual_seed(1 + rank)
-    y0 = torch.randn(batch, DIM, generator=g)
+    g = torch.Generator().manual_seed(1)
+    y_all = torch.randn(batch * world, DIM, generator=g)
+    y0 = y_all[rank * batch:(rank + 1) * batch].contiguous()
     t = torch.tensor(T_SPAN)
-    return f, y0, t
+    return f, y0, t, y_all
 
 
 def measured_peaks():
@@ -92,6 +95,8 @@ class ClockSampler:
                 "samples": len(sm)}
 
 
+# DRAM traffic of the six stage-combine launches of one attempt, from the committed ncu capture; a literal, labelled as such
+TRAFFIC_STATIC = {"bytes": 921.6e6, "source": "static, from profiles/r1_ncu_full_summary.csv (ncu --set full; not measured by this run)"}
 FULL_ATTEMPTS = 74         # step attempts of the full workload (reference, oracle and CUDA path agree)
 CPU_SAMPLE_T_END = 1.0     # the CPU sample integrates the FULL batch over t in [0, 1] (9 of the 74 attempts, + the start-up work)
 REF_DIR = os.path.join(ROOT, "baseline", "_ref")      # the unmodified reference, `pip install --target`
@@ -136,7 +141,7 @@ def cpu_run(batch, threads, t_end=T_SPAN[1]):
     """One solve of the workload at `batch` rows over t in [0, t_end] on the host cores: the unmodified reference
     when available (kind 'reference'), else the CPU oracle (kind 'port').  Returns (seconds, attempts, kind)."""
     torch.set_num_threads(threads)
-    f, y0, _ = make_problem("cpu", batch)
+    f, y0, _, _ = make_problem("cpu", batch)
     t = torch.tensor([T_SPAN[0], t_end])
     ref = reference_package()
     with torch.no_grad():
@@ -269,11 +274,15 @@ def run_ours(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
         pg = True
-    f, y0_host, t = make_problem(dev, B_PER_GPU, rank)
+    strong = args.scaling == "strong"
+    if strong:
+        assert B_PER_GPU % world == 0
+    rows = B_PER_GPU // world if strong else B_PER_GPU      # strong: the 65,536 trajectories are split over the ranks
+    f, y0_host, t, y_all = make_problem(dev, rows, rank, world)
     y0_host = y0_host.pin_memory()
     y0 = y0_host.to(dev)
     t_dev = t.to(dev)
-    opts = {"graph": True, "run_ahead": 2}
+    opts = {"graph": True, "run_ahead": 2, "device_loop": not args.no_device_loop}
     if pg:
         opts["process_group"] = pg
     stats = {}
@@ -307,7 +316,7 @@ def run_ours(args):
     launches = stats.get("launches", 0) - launches0
     clocks = sampler.stop() if rank == 0 else None
     # ---- end to end: pinned host y0 -> device -> solve -> y(t_end) back to pinned host -----------------
-    res_host = torch.empty(B_PER_GPU, DIM, dtype=torch.float32).pin_memory()
+    res_host = torch.empty(rows, DIM, dtype=torch.float32).pin_memory()
     for _ in range(2):
         res_host.copy_(solve(y0_host.to(dev, non_blocking=True))[-1], non_blocking=True)
     barrier()
@@ -326,6 +335,24 @@ def run_ours(args):
     n0, n1 = y0.norm(dim=1), out[-1].norm(dim=1)
     drift = float(((n1 - n0).abs() / n0).max())
     assert drift < 5e-3, "solution drifted: %g" % drift
+    # N > 1: the sharded rows must be the rows of the UNSHARDED solve of the same seeded batch (global RMS norm =>
+    # same dt sequence): rank 0 solves the whole batch alone (outside the timed region) and compares its own rows
+    check = {"max_rel_norm_drift": drift}
+    if world > 1:
+        n_acc, n_rej = stats.get("n_accept"), stats.get("n_reject")
+        if rank == 0:
+            st1 = {}
+            with torch.no_grad():
+                full = tdq.odeint(f, y_all.to(dev), t_dev, method="dopri5", rtol=RTOL, atol=ATOL,
+                                  options={"graph": True, "run_ahead": 2, "cache": False}, _stats=st1)
+            mine = full[-1][:rows]
+            check.update({"unsharded_rows": int(y_all.shape[0]), "max_abs_diff_vs_unsharded": float((out[-1] - mine).abs().max()),
+                          "bitwise_equal": bool(torch.equal(out[-1], mine)),
+                          "steps_sharded": [n_acc, n_rej], "steps_unsharded": [st1.get("n_accept"), st1.get("n_reject")],
+                          "same_step_sequence_counts": [n_acc, n_rej] == [st1.get("n_accept"), st1.get("n_reject")]})
+            del full, mine
+            torch.cuda.empty_cache()
+        dist.barrier()
 
     if rank == 0:
         n_elems = B_PER_GPU * DIM
@@ -338,14 +365,19 @@ def run_ours(args):
         group = (comb_bytes + norm_bytes) / (group_ms * 1e-3) / 1e9
         threads = cpu_threads()
         cpu_val, _cpu_s, cpu_desc, cpu_kind = cpu_sample(threads) if args.cpu_baseline and world == 1 else (None,) * 4
-        total_traj = B_PER_GPU * world * args.steps
+        total_traj = rows * world * args.steps
         line = {
             "metric": METRIC, "value": total_traj / (ms * 1e-3), "unit": "trajectories/s", "n_gpus": world,
             "steps": args.steps, "warmup": W, "ms_per_step": ms / args.steps, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "scaling": "strong" if strong else "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": "configs[1]: dopri5 adaptive, batch=65536 dim=128 linear ODE y'=Ay, f32, rtol=1e-5 "
-                                   "atol=1e-7, t=[0,10]" + (" x %d ranks (configs[4] layout)" % world if world > 1 else ""),
-                       "batch_per_gpu": B_PER_GPU, "dim": DIM, "exec": "cuda-graph step body, run_ahead=2",
+                                   "atol=1e-7, t=[0,10]" + ((" split over %d ranks (strong scaling)" % world) if strong and world > 1
+                                                            else (" x %d ranks (configs[4] layout)" % world if world > 1 else "")),
+                       "batch_per_gpu": rows, "dim": DIM,
+                       "exec": ("cuda-graph step body inside a device-side while loop (one launch per solve)"
+                                if not args.no_device_loop else "cuda-graph step body replayed by the host, run_ahead=2"),
+                       "func_share": "the user's func (y @ A^T, cuBLAS fp32 SIMT SGEMM, 6 per attempt) is ~60 % of a step; "
+                                     "the solver's own kernels are the rest (profiles/README.md)",
                        "attempts_per_solve": stats.get("attempts"), "nfe_per_solve": stats.get("nfe"),
                        "l2": "working set 20 arrays x 33.5 MB >> 126 MB L2 (no flush needed)",
                        "parallelism": "batch-sharded, 1 all-reduce(3 x f64)/attempt" if world > 1 else "single GPU"},
@@ -355,16 +387,15 @@ def run_ours(args):
             "clocks": clocks,
             "roofline": {"bound": "hbm", "kernel": "k_combine (6 launches per attempt)", "achieved": achieved,
                          "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         # dram__bytes_read + dram__bytes_write of the six launches of one attempt, from the ncu
-                         # --set full capture of this command (profiles/r1_ncu_full_summary.csv: rows NK=4 and NK=5
-                         # measured, 176.0 / 209.5 MB; the other rows scaled by their operand count)
-                         "traffic": 921.6e6, "traffic_source": "profiles/r1_ncu_full_summary.csv",
+                         # STATIC: dram__bytes_read + dram__bytes_write of the six launches of one attempt from the
+                         # committed ncu --set full capture (not re-measured by this run)
+                         "traffic": TRAFFIC_STATIC["bytes"], "traffic_source": TRAFFIC_STATIC["source"],
                          "peak_source": peak_src, "algorithmic_bytes_per_attempt": comb_bytes,
                          "ms_per_attempt": comb_ms, "launches_per_attempt": 6,
                          "combine_plus_error_norm": {"achieved": group, "frac": group / peak,
                                                      "bytes": comb_bytes + norm_bytes, "ms": group_ms,
                                                      "target": "BASELINE.md: >= 0.70 of the HBM roofline"}},
-            "result_check": {"max_rel_norm_drift": drift},
+            "result_check": check,
         }
         if cpu_val is not None:
             line["cpu_baseline"] = {"value": cpu_val, "unit": "trajectories/s", "cores": threads, "kind": cpu_kind,
@@ -385,6 +416,11 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", dest="cpu_baseline", action="store_false")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="N > 1: weak = 65536 trajectories per rank (configs[4]); strong = 65536 split over the ranks")
+    ap.add_argument("--no-device-loop", action="store_true",
+                    help="replay the step graph from the host instead of the device-side while loop (needed under ncu: "
+                         "kernels inside a conditional graph node are not visible to its kernel-level profiling)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

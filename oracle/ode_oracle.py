@@ -493,14 +493,19 @@ def odeint_rk4(func, y0, t, grid=None, perturb=False, method="rk4", interp="line
 # adjoint backward (adjoint.py:36-153) for a tensor state
 # ------------------------------------------------------------------------------------------------
 def adjoint_gradients(func, params, y0, t, grad_y, method="dopri5", rtol=1e-7, atol=1e-9,
-                      adjoint_rtol=None, adjoint_atol=None, seminorm=False, record=None):
+                      adjoint_rtol=None, adjoint_atol=None, seminorm=False, record=None,
+                      state_rms=None, reduce_partial=None):
     """Solve forward with odeint_adaptive, then the augmented system backwards interval by interval.
-    grad_y: dL/dy at every output time, [len(t), *y0.shape].  Returns (solution, dL/dy0, [dL/dparam])."""
+    grad_y: dL/dy at every output time, [len(t), *y0.shape].  Returns (solution, dL/dy0, [dL/dparam]).
+    Batch-sharded form: state_rms(x) is the RMS over the rows of ALL ranks (forward norm and
+    the y / adj_y segments of the adjoint norm), reduce_partial(v) sums a rank-partial vector (vjp_t and the parameter
+    gradients of one evaluation) over the ranks in place."""
+    srms = rms if state_rms is None else state_rms
     adjoint_rtol = rtol if adjoint_rtol is None else adjoint_rtol
     adjoint_atol = atol if adjoint_atol is None else adjoint_atol
     params = tuple(params)
     with torch.no_grad():
-        ys = odeint_adaptive(func, y0, t, method, rtol, atol)
+        ys = odeint_adaptive(func, y0, t, method, rtol, atol, norm=srms)
     shape, n = y0.shape, y0.numel()
     sizes = [1, n, n] + [p.numel() for p in params]
     bounds = [0]
@@ -519,12 +524,14 @@ def adjoint_gradients(func, params, y0, t, grad_y, method="dopri5", rtol=1e-7, a
             grads = torch.autograd.grad(fe, (yv,) + params, -adj, allow_unused=True)
         vjp_y = torch.zeros_like(yv) if grads[0] is None else grads[0]
         vjp_p = [torch.zeros_like(p) if g is None else g for p, g in zip(params, grads[1:])]
-        return torch.cat([torch.zeros(1, dtype=v.dtype), fe.detach().reshape(-1), vjp_y.reshape(-1)] +
-                         [g.reshape(-1) for g in vjp_p])
+        tail = torch.cat([torch.zeros(1, dtype=v.dtype)] + [g.reshape(-1) for g in vjp_p])
+        if reduce_partial is not None:                              # vjp_t and vjp_theta: sums over ALL rows
+            reduce_partial(tail)
+        return torch.cat([tail[:1], fe.detach().reshape(-1), vjp_y.reshape(-1), tail[1:]])
 
     def aug_norm(q):                                                # adjoint.py:247-250, :267-271
         parts = split(q)
-        vals = [parts[0].abs().max(), rms(parts[1]), rms(parts[2])]
+        vals = [parts[0].abs().max(), srms(parts[1]), srms(parts[2])]
         if not seminorm and len(parts) > 3:
             vals.append(mixed(parts[3:]))
         return max(vals)

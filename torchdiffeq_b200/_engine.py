@@ -169,7 +169,7 @@ class AdaptiveEngine:
                  safety=0.9, ifactor=10.0, dfactor=0.2, max_num_steps=2 ** 31 - 1,
                  rtol_vec=None, atol_vec=None, norm_fn=None, q_view=None,
                  graph="auto", run_ahead=2, reduce_fn=None, n_global=None, seg_counts_global=None,
-                 agree_fn=None, exchange=None, callbacks=None, keep_interp=False, device_loop="auto"):
+                 agree_fn=None, exchange=None, callbacks=None, keep_interp=False, device_loop="auto", post_fn=None):
         if device.type != "cuda":
             raise _lib.TdqError("torchdiffeq_b200 runs on CUDA devices only (got %s); there is no CPU path" % device)
         if dtype not in _DTYPES:
@@ -190,7 +190,8 @@ class AdaptiveEngine:
         self.reduce_fn = reduce_fn
         self.agree_fn = agree_fn        # sharded solves: host-side max over ranks of the attempts queued
         self.exchange = exchange        # sharded solves: per-attempt all-reduce fused into tdq_controller
-        if exchange is not None:
+        self.post_fn = post_fn          # sharded adjoint: all-reduce of the rank-partial pieces of every func result
+        if exchange is not None and post_fn is None:
             self.agree_fn = None        # no collective launch inside an attempt: trailing no-ops need no agreement
         self.callbacks = callbacks or {}
         self.graph_opt = graph
@@ -317,6 +318,8 @@ class AdaptiveEngine:
         # tuple of pieces -> one pack launch into an engine-owned slot
         buf = dst if dst is not None else self._slot(slot)
         self.launches += pack_pieces(self.lib, self.dt_code, self.dtype, buf, f, self.pieces)
+        if self.post_fn is not None:
+            self.post_fn(buf)
         return buf
 
     @property

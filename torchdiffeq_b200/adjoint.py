@@ -160,6 +160,8 @@ class _BackwardSolver:
         bp.original_func = p.original_func          # decides graph='auto' (only nn.Module funcs are captured)
         bp.t_cpu = (p.t_cpu.to(torch.float64) * fwd_sign * self.bsign).flip(0)
         self.fixed = adjoint_method in FIXED_METHODS
+        if self.fixed and opts.get("process_group") is not None:
+            raise NotImplementedError("sharded adjoint with a fixed-grid adjoint_method is not implemented")
         if self.fixed:
             # fixed-grid backward (adjoint.py:134-138 with a FixedGridODESolver): the same step kernels; the grid of
             # every interval comes from adjoint_options (step_size / grid_constructor), solvers.py:85-104
@@ -173,6 +175,30 @@ class _BackwardSolver:
             self.eng = FixedGridEngine(aug_fn, lay.n, T, dev, method=adjoint_method, t_sign=self.bsign,
                                        perturb=opts.get("perturb", False), graph=False, callbacks=valid, pieces=pieces)
             return
+        # ---- batch-sharded backward solve -------------------------------------------------
+        # y and adj_y are this rank's rows; vjp_t and the parameter gradients every evaluation produces are PARTIAL
+        # sums over the local rows.  They are all-reduced right after the pack (two contiguous ranges of the slot:
+        # vjp_t at the front, the parameter block at the tail), so every rank integrates the same GLOBAL adj_theta --
+        # which is what the default adjoint norm needs (rms of each global gradient tensor, adjoint.py:250), and what
+        # leaves the gradients complete on every rank at the end, with no extra reduction.
+        replicated, post_fn = (), None
+        pg = opts.get("process_group")
+        if pg is not None:
+            import torch.distributed as dist
+            group = None if pg is True else pg
+            if norm_fn is not None:
+                raise NotImplementedError("sharded adjoint: custom norm callables are not supported (replicas only)")
+            o_p = lay.offsets[3] if len(lay.offsets) > 3 else lay.n
+            n_lay = lay.n
+
+            def post_fn(buf):
+                dist.all_reduce(buf[o_t:o_t + 1], group=group)
+                if o_p < n_lay:
+                    dist.all_reduce(buf[o_p:n_lay], group=group)
+            n_state_segs = len(y_segs) + len(a_segs)
+            replicated = (0,) + tuple(range(1 + n_state_segs, len(segs)))
+        self.dist_group = None if pg is None else (None if pg is True else pg)
+        self.sharded = pg is not None
         rtol_s, rtol_v = _adj_tol(adjoint_rtol, lay, dev)
         atol_s, atol_v = _adj_tol(adjoint_atol, lay, dev)
         if (rtol_v is None) != (atol_v is None):
@@ -182,7 +208,8 @@ class _BackwardSolver:
                 atol_v = torch.full_like(rtol_v, atol_s)
         self.eng = _make_adaptive_engine(bp, adjoint_method, rtol_s, atol_s, rtol_v, atol_v, opts, fn=aug_fn,
                                          n=lay.n, segs=segs, pieces=pieces, norm_fn=norm_fn, q_view=q_view,
-                                         callbacks=callbacks, solver_name=adjoint_method)
+                                         callbacks=callbacks, solver_name=adjoint_method, replicated=replicated,
+                                         post_fn=post_fn)
         # solves run inside autograd's backward: never capture there (see AdaptiveEngine.prime)
         self.eng.capture_in_solve = False
 
@@ -217,6 +244,9 @@ class _BackwardSolver:
                 if isinstance(fe, tuple):
                     fe = self.fwd_layout.flatten([f_.detach() for f_ in fe])
                 dLd_cur_t = fe.reshape(-1).dot(grad_sol[i].reshape(-1))
+                if getattr(self, "sharded", False):                  # a sum over ALL rows of the batch
+                    import torch.distributed as dist
+                    dist.all_reduce(dLd_cur_t, group=self.dist_group)
                 aug[o_t] -= dLd_cur_t
                 time_vjps[i] = dLd_cur_t
             if self.fixed:

@@ -39,14 +39,17 @@ def make_agree(process_group):
     return agree
 
 
-def make_reduce(process_group, segs, device):
+def make_reduce(process_group, segs, device, replicated=()):
     """Returns (reduce_fn, n_global, seg_counts_global) for AdaptiveEngine.
 
     reduce_fn(buf) sums the float64 buffer [n_seg + 1] across ranks in place, on the current stream
-    (capturable with the NCCL backend).  Segment element counts are summed once, here."""
+    (capturable with the NCCL backend).  Segment element counts are summed once, here.
+    `replicated`: indices of segments every rank holds IDENTICALLY (the adjoint's vjp_t and parameter-gradient
+    segments after their per-evaluation all-reduce): their sums arrive R times in the all-reduce, so their count is
+    R x len and the mean is the local one."""
     pg = None if process_group is True else process_group
     counts = torch.tensor([int(l) for _, l in segs], dtype=torch.int64, device=device)
-    dist.all_reduce(counts, op=dist.ReduceOp.SUM, group=pg)
+    dist.all_reduce(counts, op=dist.ReduceOp.SUM, group=pg)       # replicated: same len everywhere => R x len
     counts_list = [int(c) for c in counts.tolist()]
 
     def reduce_fn(buf):

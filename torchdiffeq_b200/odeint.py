@@ -240,7 +240,7 @@ def _resolve_graph(graph, func):
 
 def _make_adaptive_engine(p, method, rtol, atol, rtol_vec, atol_vec, options, fn=None, n=None, segs=None,
                           pieces=None, norm_fn=None, q_view=None, callbacks=None, solver_name=None,
-                          keep_interp=False):
+                          keep_interp=False, replicated=(), post_fn=None):
     o = options
     _warn_unused(solver_name or method, o, _ADAPTIVE_OPTIONS)
     graph = _resolve_graph(o.get("graph", "auto"), getattr(p, "original_func", None))
@@ -260,12 +260,19 @@ def _make_adaptive_engine(p, method, rtol, atol, rtol_vec, atol_vec, options, fn
     pg = o.get("process_group")
     if pg is not None:
         from .dist import make_agree, make_reduce
+        if norm_fn is not None:
+            raise NotImplementedError("a custom norm callable cannot be evaluated on a batch-sharded state "
+                                      "(SURVEY.md section 8(e): replicas only); use the default norm or 'seminorm'")
         reduce_fn, n_global, seg_counts_global = make_reduce(pg, segs if segs is not None else
-                                                             [(0, n if n is not None else p.n)], p.device)
+                                                             [(0, n if n is not None else p.n)], p.device,
+                                                             replicated=replicated)
         agree_fn = make_agree(pg)
         if o.get("exchange", "peer") == "peer" and norm_fn is None:
             try:
                 from .dist import PeerExchange
+                n_seg_ = len(segs) if segs is not None else 1
+                if n_seg_ > _lib.TDQ_MAX_SEGS:
+                    raise _lib.TdqError("more than %d norm segments" % _lib.TDQ_MAX_SEGS)
                 exchange = PeerExchange(pg, p.device)
             except Exception as e:      # e.g. CUDA IPC not permitted in this container: keep the NCCL all-reduce
                 warnings.warn("torchdiffeq_b200: NVLink peer exchange unavailable (%s: %s); using the process "
@@ -280,7 +287,8 @@ def _make_adaptive_engine(p, method, rtol, atol, rtol_vec, atol_vec, options, fn
         max_num_steps=o.get("max_num_steps", 2 ** 31 - 1),
         norm_fn=norm_fn, q_view=q_view, graph=graph, run_ahead=o.get("run_ahead", 2),
         reduce_fn=reduce_fn, n_global=n_global, seg_counts_global=seg_counts_global, agree_fn=agree_fn,
-        exchange=exchange, callbacks=callbacks, keep_interp=keep_interp, device_loop=o.get("device_loop", "auto"))
+        exchange=exchange, callbacks=callbacks, keep_interp=keep_interp, device_loop=o.get("device_loop", "auto"),
+        post_fn=post_fn)
 
 
 # ---- engine cache -------------------------------------------------------------------------------
