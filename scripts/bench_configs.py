@@ -61,6 +61,32 @@ def c3():
                       "traj_per_s": 8192 / ms * 1e3, "cpu_reference_build_container": "3840 ms (SURVEY 6)"}), flush=True)
 
 
+def c3_bf16():
+    """configs[2] as BASELINE.json words it: forward func under bf16 autocast on an fp32 state, adjoint in fp32."""
+    f = P.MLPField(dim=64, hidden=256, seed=0).to(DEV)
+    y0 = torch.randn(8192, 64, generator=torch.Generator().manual_seed(1)).to(DEV)
+    t = torch.tensor([0., 1.], device=DEV)
+
+    class BF16(torch.nn.Module):
+        def __init__(self, g):
+            super().__init__()
+            self.g = g
+
+        def forward(self, t_, y_):
+            with torch.autocast("cuda", dtype=torch.bfloat16):
+                return self.g(t_, y_).float()
+    fb = BF16(f)
+
+    def step():
+        f.zero_grad()
+        yy = y0.clone().requires_grad_(True)
+        y = tdq.odeint_adjoint(fb, yy, t, method="dopri5", rtol=1e-4, atol=1e-6)
+        y[-1].pow(2).mean().backward()
+    ms = timed(step)
+    print(json.dumps({"config": "C3 odeint_adjoint dopri5 MLP B=8192, func under bf16 autocast, fp32 state/adjoint, fwd+bwd",
+                      "ms": ms, "traj_per_s": 8192 / ms * 1e3}), flush=True)
+
+
 def c4():
     for name in ("B1", "B5"):
         f, y0, t0 = P.detest(name)
@@ -69,7 +95,8 @@ def c4():
         for tol in (1e-3, 1e-6, 1e-9):
             st = {}
             with torch.no_grad():
-                ms = timed(lambda: tdq.odeint(f, yb, t, method="dopri8", rtol=tol, atol=tol, _stats=st), reps=3, warm=1)
+                ms = timed(lambda: tdq.odeint(f, yb, t, method="dopri8", rtol=tol, atol=tol, _stats=st,
+                                              options={"graph": True, "cache": True}), reps=3, warm=1)
             print(json.dumps({"config": "C4 dopri8 f64 DETEST %s x4096 tol=%g" % (name, tol), "ms": ms,
                               "attempts": st.get("attempts"), "nfe": 2 + 13 * (st.get("attempts") or 0)}), flush=True)
 
@@ -114,5 +141,6 @@ def dopri8_roofline():
 if __name__ == "__main__":
     c1()
     c3()
+    c3_bf16()
     c4()
     dopri8_roofline()

@@ -211,6 +211,75 @@ __global__ void __launch_bounds__(THREADS) k_tma(float *out, const float *y0, KP
     }
 }
 
+// ---- round 2: warp-specialised bulk-async pipeline ---------------------------------------------------------
+// the r1 sweep kept too few bytes in flight for some shapes and synchronised the whole block
+// once per stage.  This variant has ONE producer warp (lane 0 issues cp.async.bulk for all NK+1 operands of a stage
+// as soon as the consumers have released it through an `empty` mbarrier) and CONSUMERS-1 consumer warps that never
+// meet the producer at a __syncthreads: full[s] (tx-count) -> compute from shared -> arrive on empty[s].
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(smem_u32(bar)) : "memory");
+}
+template <int NK, int THREADS, int TILE_V, int STAGES>
+__global__ void __launch_bounds__(THREADS) k_tma2(float *out, const float *y0, KP kp, size_t nvec) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    float4 *buf = reinterpret_cast<float4 *>(smem_raw);                 // [STAGES][NK+1][TILE_V]
+    __shared__ uint64_t full[STAGES], empty[STAGES];
+    constexpr int CONS = THREADS - 32;                                  // consumer threads
+    const size_t ntiles = (nvec + TILE_V - 1) / TILE_V;
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], CONS); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (threadIdx.x < 32) {                                             // producer warp
+        if (threadIdx.x == 0) {
+            int s = 0;
+            uint32_t phase = 0;
+            size_t it = 0;
+            for (size_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+                if (it >= (size_t)STAGES) mbar_wait(&empty[s], phase ^ 1);      // consumers released the slot
+                const size_t v0 = tile * TILE_V;
+                const uint32_t nv = (uint32_t)((nvec - v0 < (size_t)TILE_V) ? (nvec - v0) : TILE_V);
+                const uint32_t bytes = nv * 16;
+                mbar_expect_tx(&full[s], bytes * (NK + 1));
+                float4 *st = buf + (size_t)s * (NK + 1) * TILE_V;
+                bulk_g2s(st, y0 + v0 * 4, bytes, &full[s]);
+#pragma unroll
+                for (int m = 0; m < NK; ++m) bulk_g2s(st + (size_t)(m + 1) * TILE_V, kp.p[m] + v0 * 4, bytes, &full[s]);
+                if (++s == STAGES) { s = 0; phase ^= 1; }
+            }
+        }
+        return;
+    }
+    const int ct = threadIdx.x - 32;
+    int s = 0;
+    uint32_t phase = 0;
+    for (size_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        mbar_wait(&full[s], phase);
+        const size_t v0 = tile * TILE_V;
+        float4 *st = buf + (size_t)s * (NK + 1) * TILE_V;
+        constexpr int PER = (TILE_V + CONS - 1) / CONS;
+        float4 r[PER];
+#pragma unroll
+        for (int j = 0; j < PER; ++j) {
+            const int i = ct + j * CONS;
+            if (i < TILE_V) {
+                float4 kv[NK];
+#pragma unroll
+                for (int m = 0; m < NK; ++m) kv[m] = st[(size_t)(m + 1) * TILE_V + i];
+                r[j] = comb<NK>(st[i], kv, kp.c);
+            }
+        }
+        mbar_arrive(&empty[s]);                                          // operands are in registers: release the slot
+#pragma unroll
+        for (int j = 0; j < PER; ++j) {
+            const int i = ct + j * CONS;
+            if (i < TILE_V && v0 + i < nvec) stv(out + (v0 + i) * 4, r[j]);
+        }
+        if (++s == STAGES) { s = 0; phase ^= 1; }
+    }
+}
+
 struct Bufs { float *y0, *out, *k[8]; size_t n; };
 
 template <typename F> float time_ms(F f, int reps = 30) {
@@ -270,6 +339,25 @@ template <int NK> void run_all(const Bufs &B) {
     TMA(256, 512, 3, 1, "tma T=256 tile=8KB S=3 R=1");
     TMA(512, 512, 3, 1, "tma T=512 tile=8KB S=3 R=1");
     TMA(256, 128, 4, 4, "tma T=256 tile=2KB S=4 R=4");
+    // round 2: >= 96 KB in flight per SM wherever shared memory allows it (227 KB per block), warp-specialised
+    // pipeline (k_tma2: producer warp + empty/full mbarriers, no block-wide sync per stage)
+#define TMA2(T, TV, S, R, label) do { \
+        size_t sm = (size_t)S * (NK + 1) * TV * 16; \
+        if (sm * R <= 220 * 1024 && sm <= 220 * 1024) { \
+            char nm[96]; snprintf(nm, sizeof(nm), "%s [%zu KB/SM]", label, sm * R / 1024); \
+            CK(cudaFuncSetAttribute(k_tma2<NK, T, TV, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm)); \
+            report(nm, time_ms([&] { k_tma2<NK, T, TV, S><<<148 * R, T, sm>>>(B.out, B.y0, kp, nvec); })); } } while (0)
+    TMA2(288, 256, 4, 2, "tma2 T=256+32 tile=4KB S=4 R=2");
+    TMA2(288, 256, 6, 2, "tma2 T=256+32 tile=4KB S=6 R=2");
+    TMA2(288, 256, 8, 2, "tma2 T=256+32 tile=4KB S=8 R=2");
+    TMA2(288, 512, 4, 2, "tma2 T=256+32 tile=8KB S=4 R=2");
+    TMA2(288, 512, 6, 1, "tma2 T=256+32 tile=8KB S=6 R=1");
+    TMA2(288, 512, 8, 1, "tma2 T=256+32 tile=8KB S=8 R=1");
+    TMA2(544, 512, 4, 1, "tma2 T=512+32 tile=8KB S=4 R=1");
+    TMA2(544, 1024, 4, 1, "tma2 T=512+32 tile=16KB S=4 R=1");
+    TMA2(544, 1024, 6, 1, "tma2 T=512+32 tile=16KB S=6 R=1");
+    TMA2(288, 1024, 3, 1, "tma2 T=256+32 tile=16KB S=3 R=1");
+    TMA2(288, 128, 8, 4, "tma2 T=256+32 tile=2KB S=8 R=4");
 }
 
 __global__ void k_copy(float4 *o, const float4 *i, size_t nvec) {

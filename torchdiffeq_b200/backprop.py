@@ -202,6 +202,8 @@ def adaptive_backward(p, tab, tape, t, grad_sol, params, need_t):
         s1 = s0 + dt
         dtT, t0T, t1T = _T(dt, T, dev), _T(s0, T, dev), _T(s1, T, dev)
         y0, k0 = st["y0"], st["k0"]
+        if sign != 1.0:
+            k0 = k0 * sign                               # the engine keeps RAW func outputs; F is reference-sense
         times = [_dev(_prev(t1T) if a == 1.0 else t0T + _T(a, T) * dtT, dev) for a in tab.alpha]
         coefs = [[float(_T(b, T) * dtT) for b in row] for row in tab.beta]
         Ys, ks = sa.stages(times, y0, k0, coefs)

@@ -61,14 +61,16 @@ def _combine_event_functions(event_fn, t0, y0):
     return combined_event_fn
 
 
-def _check_timelike(name, timelike, can_grad):                                         # misc.py:367-374
+def _check_timelike(name, timelike, can_grad, values=None):                            # misc.py:367-374
+    """`values`: a host copy of the tensor, so that the monotonicity test costs no device synchronisation."""
     assert isinstance(timelike, torch.Tensor), '{} must be a torch.Tensor'.format(name)
     if not torch.is_floating_point(timelike):                                          # misc.py:110-112
         raise TypeError('`{}` must be a floating point Tensor but is a {}'.format(name, timelike.type()))
     assert timelike.ndimension() == 1, "{} must be one dimensional".format(name)
     if not can_grad:
         assert not timelike.requires_grad, "{} cannot require gradient".format(name)
-    diff = timelike[1:] > timelike[:-1]
+    v = timelike if values is None else values
+    diff = v[1:] > v[:-1]
     assert diff.all() or (~diff).all(), '{} must be strictly increasing or decreasing'.format(name)
 
 
@@ -130,8 +132,8 @@ def normalise(func, y0, t, rtol, atol, method, options, event_fn, adjoint=False)
         raise _lib.TdqError("torchdiffeq_b200 runs on CUDA devices only (got %s); there is no CPU path" % p.device)
     _lib.load()                                   # fail loudly, before any work, if libtdq.so is missing
 
-    _check_timelike('t', t, True)
-    t_cpu = t.detach().to("cpu")                                                       # the one host read of t
+    t_cpu = t.detach().to("cpu") if isinstance(t, torch.Tensor) else t                 # the one host read of t
+    _check_timelike('t', t, True, values=t_cpu)
     p.t_reversed = bool(len(t_cpu) > 1 and t_cpu[0] > t_cpu[1])                        # misc.py:270-271
     p.t_sign = -1.0 if p.t_reversed else 1.0
     p.t_cpu = -t_cpu if p.t_reversed else t_cpu                                        # ascending from here on
