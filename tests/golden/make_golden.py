@@ -15,6 +15,7 @@ Outputs (committed):
                           rtol=atol in {1e-3, 1e-6, 1e-9} (+ dopri8 at 1e-12)
     options.pt            step_t / min_step / max_step / first_step / tuple-state / vector-tol cases
     fixed_extra.pt        interp='cubic' and event handling for the fixed-grid methods
+    adjoint_many.pt       odeint_adjoint on a field with 80 parameter tensors (default norm: 83 segments)
     backprop.pt           gradients of plain odeint (autograd through the reference's solver operations)
 """
 import json
@@ -350,6 +351,20 @@ def backprop():
     torch.save(out, os.path.join(HERE, "backprop.pt"))
 
 
+def adjoint_many():
+    """odeint_adjoint with the default adjoint norm on a field with 80 parameter tensors (83 norm segments)."""
+    out = {}
+    for norm in ("default", "seminorm"):
+        f = P.DeepField(dim=6, depth=40, seed=0)
+        y0 = torch.randn(16, 6, generator=torch.Generator().manual_seed(1), dtype=torch.float64).requires_grad_(True)
+        t = torch.tensor([0., 0.5, 1.0], dtype=torch.float64)
+        ao = {"norm": "seminorm"} if norm == "seminorm" else None
+        y = torchdiffeq.odeint_adjoint(f, y0, t, method="dopri5", rtol=1e-6, atol=1e-8, adjoint_options=ao)
+        (y[-1].pow(2).mean() + 0.01 * y[1].sum()).backward()
+        out[norm] = {"y": y.detach().clone(), "gy0": y0.grad.clone(), "gp": [q.grad.clone() for q in f.parameters()], "t": t}
+    torch.save(out, os.path.join(HERE, "adjoint_many.pt"))
+
+
 def dense():
     """odeint_dense (odeint.py:111-157): the dense-output closure of a dopri5 solve."""
     out = {}
@@ -380,5 +395,6 @@ if __name__ == "__main__":
     dense()
     fixed_extra()
     backprop()
+    adjoint_many()
     for fn in sorted(os.listdir(HERE)):
         print(fn, os.path.getsize(os.path.join(HERE, fn)))

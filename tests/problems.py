@@ -134,6 +134,22 @@ class MLPField(torch.nn.Module):
         return self.net(y)
 
 
+class DeepField(torch.nn.Module):
+    """A vector field with MANY parameter tensors (2*depth of them): the adjoint's default norm then has one segment
+    per tensor (adjoint.py:247-250) -- far more than any by-value descriptor holds."""
+
+    def __init__(self, dim=6, depth=40, seed=0, dtype=torch.float64):
+        super().__init__()
+        torch.manual_seed(seed)
+        self.layers = torch.nn.ModuleList([torch.nn.Linear(dim, dim) for _ in range(depth)]).to(dtype)
+
+    def forward(self, t, y):
+        h = y
+        for lin in self.layers:
+            h = h + 0.1 * torch.tanh(lin(h))
+        return h - y
+
+
 # ---- DETEST (Hull, Enright, Fellen & Sedgwick 1972), all 25 problems of tests/DETEST/detest.py:8-315 --------------
 # Written so that ONE definition serves the unbatched form the reference uses (y of shape [d], [] for class A,
 # [2, 3, 5] for C5) and BASELINE config 4's batched form with a TRAILING batch dimension (y of shape [d, B]):

@@ -69,11 +69,14 @@ struct TdqCtrl {
     alignas(16) unsigned char taux[8 * 4];
 };
 
-// Exchange buffer of one rank; double-buffered by attempt parity (a rank can be at most one attempt ahead
-// of a peer: its next controller needs that peer's next flag).
+// Exchange buffer of one rank.  Four slots: (solve epoch parity, attempt parity).  Within a solve a rank can be at
+// most one attempt ahead of a peer (its next controller needs that peer's next flag), hence the attempt parity;
+// across solves a fast rank may start solve e+1 while a slow peer is still SUMMING the last attempt of solve e
+// out of its own buffer, hence the epoch parity -- it cannot get two solves ahead, because the first
+// attempt of solve e+1 needs every peer's flag of that solve.
 struct TdqXBuf {
-    double vals[2][TDQ_MAX_RANKS][TDQ_MAX_SEGS + 2];
-    unsigned long long flags[2][TDQ_MAX_RANKS];
+    double vals[4][TDQ_MAX_RANKS][TDQ_MAX_SEGS + 2];
+    unsigned long long flags[4][TDQ_MAX_RANKS];
 };
 
 // ------------------------------------------------------------------------------------------------

@@ -349,7 +349,7 @@ k_controller(TdqCtrl *c, const double *norm_in, const int64_t *cnt, int n_seg, c
     if (sc.xworld > 1 && !sc.halt && norm_in != nullptr && ratio_dev == nullptr && n_seg <= TDQ_MAX_SEGS) {
         // Fused all-reduce over NVLink peer memory: thread t talks to rank t.
         const int R = sc.xworld, me = sc.xrank, nv = n_seg + 1;
-        const int par = (int)(sc.seq & 1ull);
+        const int par = (int)(((sc.xepoch & 1ull) << 1) | (sc.seq & 1ull));
         const unsigned long long want = (sc.xepoch << 32) | (sc.seq + 1ull);
         if (threadIdx.x == 0) xfail = 0;
         __syncthreads();
