@@ -393,7 +393,9 @@ def test_backprop_golden_mlp(key):
     loss.backward()
     tol = 1e-3 if dtype == torch.float32 else 2e-5          # adaptive: step sequences differ by the stage-sum order
     if method == "bosh3":
-        tol = max(tol, 5e-4)  # + the reference's gradient through its first step size (tests/test_backprop_cpu.py)
+        # + the reference's gradient through its first step size (tests/test_backprop_cpu.py): a derivative of the local
+        # error, so it scales with the tolerance -- 1e-4 relative at rtol 1e-6 (float64 cases), 7e-3 at rtol 1e-4 (float32)
+        tol = 2e-2 if dtype == torch.float32 else 5e-4
     if method in ("rk4", "midpoint", "euler"):
         tol = 2e-4 if dtype == torch.float32 else 1e-9      # fixed grid: the same discrete map
     assert torch.allclose(y.detach().cpu(), case["y"], rtol=1e-4, atol=1e-5 if dtype == torch.float32 else 1e-6)
