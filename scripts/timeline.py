@@ -46,6 +46,26 @@ def prof(name, fn, reps=3):
         print("    %-90s %8.3f ms  x%.0f" % (k[:90], t, c), flush=True)
 
 
+def host_profile(name, fn, n=50):
+    """Where the host time of a warm call goes (cProfile, cumulative)."""
+    import cProfile
+    import io
+    import pstats
+    for _ in range(5):
+        fn()
+    torch.cuda.synchronize()
+    pr = cProfile.Profile()
+    pr.enable()
+    for _ in range(n):
+        fn()
+    torch.cuda.synchronize()
+    pr.disable()
+    buf = io.StringIO()
+    pstats.Stats(pr, stream=buf).sort_stats("cumulative").print_stats(28)
+    print("---- host profile: %s (%d calls) ----" % (name, n))
+    print("\n".join(l for l in buf.getvalue().splitlines() if l.strip())[:6000], flush=True)
+
+
 def c3():
     f = P.MLPField(dim=64, hidden=256, seed=0).to(dev)
     y0 = torch.randn(8192, 64, generator=torch.Generator().manual_seed(1)).to(dev)
@@ -62,6 +82,8 @@ def c3():
         out[-1].pow(2).mean().backward()
     prof("C3 forward only (no_grad odeint)", fwd_only)
     prof("C3 odeint_adjoint fwd+bwd", step)
+    host_profile("C3 forward only", fwd_only)
+    host_profile("C3 odeint_adjoint fwd+bwd", step)
 
 
 def c1():
