@@ -11,3 +11,5 @@ done
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 200 --csv --log-file gpurun_out/r2f/dopri8_launches.csv python -c "
 import sys; sys.path.insert(0,'scripts'); import bench_configs as b; b.dopri8_roofline()" > gpurun_out/r2f/dopri8.log 2>&1
 ls -la gpurun_out/r2f | head -20
+timeout 600 python scripts/timeline.py > gpurun_out/r2f/timeline.txt 2> gpurun_out/r2f/timeline.err
+timeout 600 python -m pytest tests -m gpu -q --timeout 300 -k "backprop or many_parameter" > gpurun_out/r2f/pytest_sub.log 2>&1; tail -3 gpurun_out/r2f/pytest_sub.log

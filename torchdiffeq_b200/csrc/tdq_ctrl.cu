@@ -23,7 +23,9 @@ template <typename T> __device__ __forceinline__ void store_T(unsigned char *raw
 
 // rk_common.py:266-308 (+ :246-247) for the attempt that starts at rk_state.t1 with rk_state.dt,
 // then the casts and products of _runge_kutta_step (:61-79, :89) and _interp_fit's dt (:365-366).
-template <typename T> __device__ void prepare_attempt(TdqCtrl &c) {
+// Split in two: the scalar decisions (one thread) and the per-attempt tables -- stage times and the
+// coefficients fl_T(beta_ij * T(dt)) -- which are independent entries and are filled by the whole block.
+template <typename T> __device__ void prepare_scalar(TdqCtrl &c) {
     if (c.halt) return;
     if (c.n_steps_interval >= c.max_num_steps) {                     // rk_common.py:247
         c.status = TDQ_RUN_MAX_STEPS;
@@ -68,13 +70,16 @@ template <typename T> __device__ void prepare_attempt(TdqCtrl &c) {
     }
     c.att_dt = dt;
     c.att_t1 = t1;
+    c.att_dtT = (double)(T)dt;                                        // :61-65
+}
 
+template <typename T> __device__ void prepare_tables(TdqCtrl &c, int tid, int nthreads) {
+    if (c.halt) return;
     using A = Ar<T>;
-    const T t0T = (T)t0, dtT = (T)dt, t1T = (T)t1;                    // :61-65
+    const T t0T = (T)c.att_t0, dtT = (T)c.att_dt, t1T = (T)c.att_t1;  // :61-65
     const T sgn = (T)c.t_sign;
-    c.att_dtT = (double)dtT;
     const int S = c.n_stages;
-    for (int i = 0; i < S; ++i) {                                     // :72-78
+    for (int i = tid; i < S; i += nthreads) {                         // :72-78
         const T a = (T)c.alpha[i];
         T ti;
         if (a == (T)1) ti = prev_repr<T>(t1T);
@@ -82,11 +87,17 @@ template <typename T> __device__ void prepare_attempt(TdqCtrl &c) {
         store_T<T>(c.tstage, i, A::mul(sgn, ti));
     }
     const int rows = c.fsal ? S : S + 1;
-    for (int r = 0; r < rows; ++r)
-        for (int m = 0; m < c.row_nnz[r]; ++m)                        // :79 (beta_i * dt), :85 (dt * c_sol)
-            c.coef[r][m] = (double)A::mul(sgn, A::mul((T)c.beta[r][m], dtT));
-    for (int m = 0; m < c.err_nnz; ++m)                               // :89
+    for (int e = tid; e < rows * TDQ_MAX_K; e += nthreads) {          // :79 (beta_i * dt), :85 (dt * c_sol)
+        const int r = e / TDQ_MAX_K, m = e % TDQ_MAX_K;
+        if (m < c.row_nnz[r]) c.coef[r][m] = (double)A::mul(sgn, A::mul((T)c.beta[r][m], dtT));
+    }
+    for (int m = tid; m < c.err_nnz; m += nthreads)                   // :89
         c.ecoef[m] = (double)A::mul(sgn, A::mul(dtT, (T)c.c_err[m]));
+}
+
+template <typename T> __device__ void prepare_attempt(TdqCtrl &c) {
+    prepare_scalar<T>(c);
+    prepare_tables<T>(c, 0, 1);
 }
 
 // Value of the norm from per-segment sums: max over segments of sqrt(mean), each rounded to the
@@ -255,7 +266,7 @@ __device__ void controller(TdqCtrl &c, const double *norm_in, int n_seg, const v
     }
     const double fin_t0 = c.att_t0, fin_dt = c.att_dt;
     const int jumped = (accept && c.on_jump_t) ? 1 : 0;
-    prepare_attempt<T>(c);
+    prepare_scalar<T>(c);                 // the tables of the next attempt are filled by the whole block (k_controller)
     write_mailbox(c, fin_t0, fin_dt, jumped);
 }
 
@@ -390,7 +401,13 @@ k_controller(TdqCtrl *c, const double *norm_in, const int64_t *cnt, int n_seg, c
     double ratio_pre = 0.0;
     if (!sc.halt && ratio_dev == nullptr)
         ratio_pre = block_norm_from_sums<T, kCtrlThreads>(sc, norm_in, cnt, n_seg, nsm);
-    if (threadIdx.x == 0) controller<T>(sc, norm_in, n_seg, ratio_dev, ratio_pre);
+    __shared__ int was_halted;
+    if (threadIdx.x == 0) {
+        was_halted = sc.halt;
+        controller<T>(sc, norm_in, n_seg, ratio_dev, ratio_pre);
+    }
+    __syncthreads();
+    if (!was_halted) prepare_tables<T>(sc, threadIdx.x, kCtrlThreads);   // a no-op once the solve has halted
     __syncthreads();
     unsigned long long *go = reinterpret_cast<unsigned long long *>(c);
     for (int i = threadIdx.x; i < kWords; i += kCtrlThreads) go[i] = sw[i];
