@@ -391,9 +391,13 @@ def run_ours(args):
                          # committed ncu --set full capture (not re-measured by this run)
                          "traffic": TRAFFIC_STATIC["bytes"], "traffic_source": TRAFFIC_STATIC["source"],
                          "peak_source": peak_src, "algorithmic_bytes_per_attempt": comb_bytes,
+                         # what the six launches really move: the sixth (k_combine_final) also writes the prefix of the
+                         # error estimate (+1 N*s); the norm launch reads 4 and writes 2 arrays (the candidate commit)
+                         "moved_bytes_per_attempt": comb_bytes + n_elems * 4,
                          "ms_per_attempt": comb_ms, "launches_per_attempt": 6,
                          "combine_plus_error_norm": {"achieved": group, "frac": group / peak,
                                                      "bytes": comb_bytes + norm_bytes, "ms": group_ms,
+                                                     "moved_bytes": comb_bytes + n_elems * 4 + 6 * n_elems * 4,
                                                      "target": "BASELINE.md: >= 0.70 of the HBM roofline"}},
             "result_check": check,
         }

@@ -59,7 +59,8 @@ def _tape_adaptive(p, method, y0, rtol, atol):
         hi = cursor
         while hi < len(s_out) and not (float(s_out[hi]) > s + dt):
             hi += 1
-        tape.append(dict(t0=s, dt=dt, y0=y, k0=k, out_lo=cursor, out_hi=hi, first=first, jumped_into=None))
+        # the engine's tape holds RAW func outputs (the reverse-time sign lives in its coefficients)
+        tape.append(dict(t0=s, dt=dt, y0=y, k0=k * p.t_sign, out_lo=cursor, out_hi=hi, first=first, jumped_into=None))
         cursor, first = hi, False
         y, k, s = y1, ks[-1], s + dt
     assert cursor == len(s_out)
