@@ -290,6 +290,14 @@ int tdq_fixed_emit(int32_t dtype, void *y0, const void *y1, void *solution,
                    const void *slope_dev, int64_t *step_dev, const void *tstage_all_dev,
                    void *tstage_cur_dev, int64_t n_steps, size_t n, void *stream);
 
+/* The final expression of a step (which = 4 rk4, 5 euler / midpoint, 7 heun2, 9 heun3; operands as for tdq_rk4_stage)
+ * fused with tdq_fixed_emit: y1 = y0 + dy is formed in registers, the step's linear-interpolation records are written
+ * and y0 <- y1 -- one launch and 2 N*s less than tdq_rk4_stage followed by tdq_fixed_emit. */
+int tdq_fixed_final_emit(int32_t dtype, int32_t which, void *y0, const void *k1, const void *k2, const void *k3,
+                         const void *k4, const void *dt_dev, void *solution, const int32_t *rec_begin_dev,
+                         const int32_t *out_idx_dev, const int32_t *mode_dev, const void *slope_dev, int64_t *step_dev,
+                         const void *tstage_all_dev, void *tstage_cur_dev, int64_t n_steps, size_t n, void *stream);
+
 /* interp='cubic' (solvers.py:120-125, :166-173): for records r in [rec_lo, rec_hi) of one step
  * solution[out_idx[r]] = h00*y0 + (h10*dt)*f0 + h01*y1 + (h11*dt)*f1 with the four weights of record r at
  * coef_dev[4*r .. 4*r+4) (state dtype; the caller evaluates them in t's dtype like the reference and folds the

@@ -144,15 +144,23 @@ class FixedGridEngine:
         except _RetryWithCopies:                           # nothing of the step has been committed yet
             return self._step_once(step)
 
-    def _stages(self):
-        """The method's stage values and y1 (in self.y1); returns the tensors func returned (k1 first)."""
+    def _stages(self, fuse_final=False):
+        """The method's stage values and y1 (in self.y1); returns the tensors func returned (k1 first).
+        fuse_final: the last expression (y1 = y0 + dy) is fused with the emit/commit (tdq_fixed_final_emit): one launch
+        less per step and y1 never stored on its own -- for plain stepping with linear interpolation."""
         lib, dc, n, st = self.lib, self.dc, self.n, _stream()
         y0, ya, y1 = self.y0w.data_ptr(), self.ytmp.data_ptr(), self.y1.data_ptr()
         dtp, stp = self.dt_dev.data_ptr(), self.step_dev.data_ptr()
 
         def stage(which, out, k1=None, k2=None, k3=None, k4=None):
             p = lambda k: k.data_ptr() if k is not None else None
-            _lib.check(lib.tdq_rk4_stage(dc, which, out, y0, p(k1), p(k2), p(k3), p(k4), dtp, stp, n, st))
+            if fuse_final and out == y1 and which in (4, 5, 7, 9):
+                _lib.check(lib.tdq_fixed_final_emit(
+                    dc, which, y0, p(k1), p(k2), p(k3), p(k4), dtp, self.solution.data_ptr(), self.rec_begin.data_ptr(),
+                    self.out_idx.data_ptr(), self.mode.data_ptr(), self.slope.data_ptr(), stp, self.ts_all.data_ptr(),
+                    self.tcur.data_ptr(), self.n_steps, n, st))
+            else:
+                _lib.check(lib.tdq_rk4_stage(dc, which, out, y0, p(k1), p(k2), p(k3), p(k4), dtp, stp, n, st))
             self.launches += 1
         m = self.method
         self._taken = set()                                # stage outputs of this step (a func may reuse one buffer)
@@ -210,6 +218,8 @@ class FixedGridEngine:
         self.launches += 1
 
     def _step_once(self, step=None):
+        if self.interp == "linear":
+            return self._stages(fuse_final=True)
         keep = self._stages()
         if self.interp == "cubic" and step is not None:
             self._emit_cubic(step, keep[0])

@@ -15,20 +15,11 @@ constexpr int kThreads = 256;
 
 // 1/3 as Python computes it (rk_common.py:94 `_one_third = 1 / 3`), then cast to T by torch when it
 // multiplies a T tensor.
-template <typename T, int WHICH, bool VECTOR>
-__global__ void __launch_bounds__(kThreads)
-k_rk4(T *__restrict__ out, const T *__restrict__ y0, const T *__restrict__ k1, const T *__restrict__ k2,
-      const T *__restrict__ k3, const T *__restrict__ k4, const T *__restrict__ dt_arr,
-      const int64_t *__restrict__ step, size_t n) {
+template <typename T, int WHICH>
+__device__ __forceinline__ T rk_expr(T dt, T y, T a, T b, T c_, T d) {
     using A = Ar<T>;
-    // which operands the expression reads (k1,k2,k3,k4)
-    constexpr bool kA = WHICH != 8;
-    constexpr bool kB = WHICH == 2 || WHICH == 3 || WHICH == 4 || WHICH == 7 || WHICH == 8;
-    constexpr bool kC = WHICH == 3 || WHICH == 4 || WHICH == 9;
-    constexpr bool kD = WHICH == 4;
-    const T dt = dt_arr[step ? *step : 0];
     const T third = (T)(1.0 / 3.0);
-    auto f = [&](T y, T a, T b, T c_, T d) -> T {
+    {
         if (WHICH == 1) return A::add(y, A::mul(A::mul(dt, a), third));                 // y0 + dt*k1*_one_third
         if (WHICH == 2) return A::add(y, A::mul(dt, A::sub(b, A::mul(a, third))));      // y0 + dt*(k2 - k1*_one_third)
         if (WHICH == 3) return A::add(y, A::mul(dt, A::add(A::sub(a, b), c_)));         // y0 + dt*(k1 - k2 + k3)
@@ -43,7 +34,21 @@ k_rk4(T *__restrict__ out, const T *__restrict__ y0, const T *__restrict__ k1, c
         if (WHICH == 8) return A::add(y, A::mul(dt, A::mul(b, (T)(2.0 / 3.0))));        // heun3 stage 3: y0 + dt*(k1*0 + k2*2/3)
         // heun3 final: y0 + dt*(k1*1/4 + k2*0 + k3*3/4)
         return A::add(y, A::mul(dt, A::add(A::mul(a, (T)0.25), A::mul(c_, (T)0.75))));
-    };
+    }
+}
+
+template <typename T, int WHICH, bool VECTOR>
+__global__ void __launch_bounds__(kThreads)
+k_rk4(T *__restrict__ out, const T *__restrict__ y0, const T *__restrict__ k1, const T *__restrict__ k2,
+      const T *__restrict__ k3, const T *__restrict__ k4, const T *__restrict__ dt_arr,
+      const int64_t *__restrict__ step, size_t n) {
+    // which operands the expression reads (k1,k2,k3,k4)
+    constexpr bool kA = WHICH != 8;
+    constexpr bool kB = WHICH == 2 || WHICH == 3 || WHICH == 4 || WHICH == 7 || WHICH == 8;
+    constexpr bool kC = WHICH == 3 || WHICH == 4 || WHICH == 9;
+    constexpr bool kD = WHICH == 4;
+    const T dt = dt_arr[step ? *step : 0];
+    auto f = [&](T y, T a, T b, T c_, T d) -> T { return rk_expr<T, WHICH>(dt, y, a, b, c_, d); };
     if (VECTOR) {
         using V = Vec<T>;
         const size_t nvec = n / V::N;
@@ -112,6 +117,47 @@ k_fixed_emit(T *__restrict__ y0, const T *__restrict__ y1, T *__restrict__ solut
             solution[(size_t)out_idx[r] * n + i] = (md == 0) ? a : (md == 1) ? b : A::add(a, A::mul(slope[r], A::sub(b, a)));
         }
         y0[i] = b;                                            // solvers.py:126  y0 = y1
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        unsigned long long *ticket = reinterpret_cast<unsigned long long *>(step + 1);
+        const unsigned long long t = atomicAdd(ticket, 1ull);
+        if (t == gridDim.x - 1) {
+            *ticket = 0ull;
+            const int64_t nxt = s + 1;
+            step[0] = nxt;
+            if (nxt < n_steps)
+                for (int b = 0; b < 4 * (int)sizeof(T); ++b) tcur[b] = tst_all[nxt * 4 * sizeof(T) + b];
+        }
+    }
+}
+
+// The LAST expression of a step (y1 = y0 + dy) fused with k_fixed_emit: y1 never goes to memory as a separate
+// array -- it is formed in registers, the step's linear-interpolation outputs are written, and it replaces y0.
+template <typename T, int WHICH>
+__global__ void __launch_bounds__(kThreads)
+k_final_emit(T *__restrict__ y0, const T *__restrict__ k1, const T *__restrict__ k2, const T *__restrict__ k3,
+             const T *__restrict__ k4, const T *__restrict__ dt_arr, T *__restrict__ solution,
+             const int32_t *__restrict__ rec_begin, const int32_t *__restrict__ out_idx,
+             const int32_t *__restrict__ mode, const T *__restrict__ slope, int64_t *step,
+             const unsigned char *__restrict__ tst_all, unsigned char *__restrict__ tcur, int64_t n_steps, size_t n) {
+    using A = Ar<T>;
+    constexpr bool kA = WHICH != 8;
+    constexpr bool kB = WHICH == 4 || WHICH == 7;
+    constexpr bool kC = WHICH == 4 || WHICH == 9;
+    constexpr bool kD = WHICH == 4;
+    const int64_t s = step[0];
+    const T dt = dt_arr[s];
+    const int lo = rec_begin[s], hi = rec_begin[s + 1];
+    for (size_t i = (size_t)blockIdx.x * kThreads + threadIdx.x; i < n; i += (size_t)gridDim.x * kThreads) {
+        const T a = y0[i];
+        const T b = rk_expr<T, WHICH>(dt, a, kA ? k1[i] : (T)0, kB ? k2[i] : (T)0, kC ? k3[i] : (T)0, kD ? k4[i] : (T)0);
+        for (int r = lo; r < hi; ++r) {
+            const int md = mode[r];
+            solution[(size_t)out_idx[r] * n + i] = (md == 0) ? a : (md == 1) ? b : A::add(a, A::mul(slope[r], A::sub(b, a)));
+        }
+        y0[i] = b;
     }
     __syncthreads();
     if (threadIdx.x == 0) {
@@ -220,6 +266,33 @@ int tdq_fixed_emit(int32_t dtype, void *y0, const void *y1, void *solution, cons
                                (T *)y0, (const T *)y1, (T *)solution, rec_begin_dev, out_idx_dev, mode_dev,
                                (const T *)slope_dev, step_dev, (const unsigned char *)tstage_all_dev,
                                (unsigned char *)tstage_cur_dev, n_steps, n)));
+    TDQ_CHECK_CUDA(cudaGetLastError());
+    return TDQ_OK;
+}
+
+int tdq_fixed_final_emit(int32_t dtype, int32_t which, void *y0, const void *k1, const void *k2, const void *k3,
+                         const void *k4, const void *dt_dev, void *solution, const int32_t *rec_begin_dev,
+                         const int32_t *out_idx_dev, const int32_t *mode_dev, const void *slope_dev, int64_t *step_dev,
+                         const void *tstage_all_dev, void *tstage_cur_dev, int64_t n_steps, size_t n, void *stream) {
+    TDQ_REQUIRE(y0 && dt_dev && solution && rec_begin_dev && out_idx_dev && mode_dev && slope_dev && step_dev &&
+                    tstage_all_dev && tstage_cur_dev,
+                "null argument");
+    TDQ_REQUIRE(which == 4 || which == 5 || which == 7 || which == 9, "which must be a final expression (4, 5, 7, 9)");
+    TDQ_REQUIRE(k1 && (which == 5 || which == 9 || k2) && (which != 4 && which != 9 || k3) && (which != 4 || k4),
+                "missing stage slot");
+    cudaStream_t st = (cudaStream_t)stream;
+    size_t blocks = (n + kThreads - 1) / kThreads;
+    if (blocks == 0) blocks = 1;
+    if (blocks > 148 * 8) blocks = 148 * 8;
+#define TDQ_FE(W) TDQ_DISPATCH_T(dtype, (k_final_emit<T, W><<<(unsigned)blocks, kThreads, 0, st>>>(                    \
+        (T *)y0, (const T *)k1, (const T *)k2, (const T *)k3, (const T *)k4, (const T *)dt_dev, (T *)solution,              \
+        rec_begin_dev, out_idx_dev, mode_dev, (const T *)slope_dev, step_dev, (const unsigned char *)tstage_all_dev,        \
+        (unsigned char *)tstage_cur_dev, n_steps, n)))
+    if (which == 4) TDQ_FE(4);
+    else if (which == 5) TDQ_FE(5);
+    else if (which == 7) TDQ_FE(7);
+    else TDQ_FE(9);
+#undef TDQ_FE
     TDQ_CHECK_CUDA(cudaGetLastError());
     return TDQ_OK;
 }
