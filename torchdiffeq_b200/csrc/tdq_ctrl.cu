@@ -577,7 +577,7 @@ int tdq_controller(void *ctrl_dev, int32_t dtype, const double *norm_in, const i
                    int32_t n_seg, const void *ratio_dev, void *stream) {
     TDQ_REQUIRE(ctrl_dev, "null ctrl");
     TDQ_REQUIRE(norm_in || ratio_dev, "need norm sums or an explicit ratio");
-    TDQ_REQUIRE(n_seg >= 1 && n_seg <= TDQ_MAX_SEGS, "n_seg out of range");
+    TDQ_REQUIRE(n_seg >= 1, "n_seg out of range");      // any number of segments (the peer exchange: <= TDQ_MAX_SEGS)
     TDQ_DISPATCH_T(dtype, (k_controller<T><<<1, kCtrlThreads, 0, (cudaStream_t)stream>>>(
                                (TdqCtrl *)ctrl_dev, norm_in, seg_counts_dev, n_seg, ratio_dev)));
     TDQ_CHECK_CUDA(cudaGetLastError());

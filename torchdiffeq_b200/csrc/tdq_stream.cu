@@ -142,37 +142,54 @@ struct FinalMap {
     signed char epos[TDQ_MAX_K];
 };
 
+// Coefficient storage of the fused kernel.  Narrow rows keep the 2*NU coefficients in registers; wide rows
+// (NU >= 6: dopri8's last row has nine operands) would push the kernel past 128 registers and down to one block
+// per SM -- measured 128 us instead of 65 us for dopri8/float64 -- so they read them from shared memory at the
+// point of use (volatile: the compiler must not hoist 2*NU loop-invariant values back into registers).
+template <typename T> __device__ __forceinline__ T ld_shared_volatile(const T *p) { return *reinterpret_cast<const volatile T *>(p); }
+
 template <typename T, int NU, bool VECTOR>
 __global__ void __launch_bounds__(256)
 k_combine_final(const TdqCtrl *__restrict__ c, int row, T *__restrict__ out, T *__restrict__ err_out, const T *y0,
                 KPtrs kp, FinalMap fm, size_t n) {
     if (c->halt) return;
     using A = Ar<T>;
+    constexpr bool SMEMC = NU >= 6;
     constexpr int THREADS = 256, U = (NU <= 5) ? 2 : 1;     // wide rows: one vector per operand keeps two blocks per SM
-    T cr[NU], ce[NU];
-    bool ur[NU], ue[NU];
+    constexpr int NR = SMEMC ? 1 : NU;
+    __shared__ T s_cr[SMEMC ? NU : 1], s_ce[SMEMC ? NU : 1];
+    T cr[NR], ce[NR];
+    unsigned mask_r = 0, mask_e = 0;
     const T *k[NU];
     if (y0 == nullptr) y0 = reinterpret_cast<const T *>(c->y0_cur);
 #pragma unroll
     for (int m = 0; m < NU; ++m) {
-        ur[m] = fm.rpos[m] >= 0;
-        ue[m] = fm.epos[m] >= 0;
-        cr[m] = ur[m] ? (T)c->coef[row][fm.rpos[m]] : (T)0;
-        ce[m] = ue[m] ? (T)c->ecoef[fm.epos[m]] : (T)0;
+        const bool ur = fm.rpos[m] >= 0, ue = fm.epos[m] >= 0;
+        if (ur) mask_r |= 1u << m;
+        if (ue) mask_e |= 1u << m;
+        const T vr = ur ? (T)c->coef[row][fm.rpos[m]] : (T)0;
+        const T ve = ue ? (T)c->ecoef[fm.epos[m]] : (T)0;
+        if (SMEMC) {
+            if (threadIdx.x == 0) { s_cr[m] = vr; s_ce[m] = ve; }
+        } else {
+            cr[m] = vr;
+            ce[m] = ve;
+        }
         k[m] = reinterpret_cast<const T *>(kp.p[m] ? kp.p[m] : c->k0_cur);
     }
+    if (SMEMC) __syncthreads();
     auto element = [&](T y, const T *kv, T &yo, T &eo) {
         T ar = (T)0, ae = (T)0;
         bool fr = true, fe = true;
 #pragma unroll
         for (int m = 0; m < NU; ++m) {
-            if (ur[m]) {
-                const T p = A::mul(kv[m], cr[m]);
+            if ((mask_r >> m) & 1u) {
+                const T p = A::mul(kv[m], SMEMC ? ld_shared_volatile(&s_cr[m]) : cr[SMEMC ? 0 : m]);
                 ar = fr ? p : A::add(ar, p);
                 fr = false;
             }
-            if (ue[m]) {
-                const T p = A::mul(kv[m], ce[m]);
+            if ((mask_e >> m) & 1u) {
+                const T p = A::mul(kv[m], SMEMC ? ld_shared_volatile(&s_ce[m]) : ce[SMEMC ? 0 : m]);
                 ae = fe ? p : A::add(ae, p);
                 fe = false;
             }
