@@ -31,6 +31,7 @@ FIXED_METHODS = ("euler", "midpoint", "heun2", "heun3", "rk4")
 
 class FixedGridEngine:
     """Explicit fixed-step methods of fixed_grid.py:6-60 on one captured step graph."""
+    FUSE_FINAL = True       # last expression of a step fused with the emit/commit kernel (tdq_fixed_final_emit)
 
     def __init__(self, fn, n, dtype, device, *, method="rk4", t_sign=1.0, perturb=False, graph="auto",
                  callbacks=None, pieces=None, interp="linear"):
@@ -218,7 +219,7 @@ class FixedGridEngine:
         self.launches += 1
 
     def _step_once(self, step=None):
-        if self.interp == "linear":
+        if self.interp == "linear" and self.FUSE_FINAL:
             return self._stages(fuse_final=True)
         keep = self._stages()
         if self.interp == "cubic" and step is not None:

@@ -155,7 +155,9 @@ k_combine_final(const TdqCtrl *__restrict__ c, int row, T *__restrict__ out, T *
     if (c->halt) return;
     using A = Ar<T>;
     constexpr bool SMEMC = NU >= 6;
-    constexpr int THREADS = 256, U = (NU <= 5) ? 2 : 1;     // wide rows: one vector per operand keeps two blocks per SM
+    // two vectors per operand per thread for every row width: measured on dopri8/float64 (NU = 9), one vector per
+    // operand halves the bandwidth (126 us vs 75 us) even at twice the occupancy -- bytes in flight per thread matter
+    constexpr int THREADS = 256, U = 2;
     constexpr int NR = SMEMC ? 1 : NU;
     __shared__ T s_cr[SMEMC ? NU : 1], s_ce[SMEMC ? NU : 1];
     T cr[NR], ce[NR];
@@ -251,7 +253,7 @@ k_combine_final(const TdqCtrl *__restrict__ c, int row, T *__restrict__ out, T *
 template <typename T, int NU>
 int launch_final(const TdqCtrl *c, int row, void *out, void *err_out, const void *y0, const KPtrs &kp,
                  const FinalMap &fm, size_t n, bool vec, cudaStream_t st) {
-    constexpr int THREADS = 256, U = (NU <= 5) ? 2 : 1;
+    constexpr int THREADS = 256, U = 2;
     if (vec) {
         const size_t nvec = n / Vec<T>::N;
         size_t blocks = (nvec + (size_t)THREADS * U - 1) / ((size_t)THREADS * U);
