@@ -96,7 +96,9 @@ class ClockSampler:
 
 
 # DRAM traffic of the six stage-combine launches of one attempt, from the committed ncu capture; a literal, labelled as such
-TRAFFIC_STATIC = {"bytes": 921.6e6, "source": "static, from profiles/r1_ncu_full_summary.csv (ncu --set full; not measured by this run)"}
+TRAFFIC_STATIC = {"bytes": 928.4e6, "source": "static: dram__bytes_read+write of the six launches from ncu --set full captures "
+                                                "(profiles/r2_ncu_full_summary.csv for k_combine<5> 209.3 MB and k_combine_final 216.5 MB, "
+                                                "profiles/r1_ncu_full_summary.csv for rows NK=1..4); not measured by this run"}
 FULL_ATTEMPTS = 74         # step attempts of the full workload (reference, oracle and CUDA path agree)
 CPU_SAMPLE_T_END = 1.0     # the CPU sample integrates the FULL batch over t in [0, 1] (9 of the 74 attempts, + the start-up work)
 REF_DIR = os.path.join(ROOT, "baseline", "_ref")      # the unmodified reference, `pip install --target`

@@ -1,0 +1,24 @@
+#!/bin/bash
+# The commands behind profiles/r2_* (run on a B200 box from the repo root, e.g. `gpurun -- 'bash scripts/profile_recipes.sh'`).
+# Numbers printed under ncu are never bench values.
+set +e
+OUT=${OUT:-gpurun_out/profile}
+mkdir -p $OUT
+# kernels inside the device-side while loop are invisible to ncu's kernel-level profiling: profile the host-replay mode
+B="python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-device-loop"
+# 1. launch list (per-kernel durations of a warm solve)
+ncu --metrics gpu__time_duration.sum --clock-control none -c 4000 --csv --log-file $OUT/launches.csv $B > $OUT/ncu_bench.log 2>&1
+# 2. full captures of the three dominant kernels
+ncu --set full --clock-control none --import-source on --kernel-name-base demangled -k "regex:k_combine_final<float" --launch-skip 20 -c 1 -o $OUT/k_combine_final -f $B
+ncu --set full --clock-control none --import-source on -k regex:k_norm --launch-skip 20 -c 1 -o $OUT/k_norm -f $B
+ncu --set full --clock-control none --import-source on --kernel-name-base demangled -k "regex:k_combine<float, \(int\)5" --launch-skip 20 -c 1 -o $OUT/k_combine5 -f $B
+for k in k_combine_final k_norm k_combine5; do
+  ncu -i $OUT/$k.ncu-rep --page details > $OUT/${k}_details.txt
+  ncu -i $OUT/$k.ncu-rep --page raw --csv > $OUT/${k}_raw.csv
+done
+# 3. the other configs, the small-state timelines, the DETEST sweep, the TMA experiment
+python scripts/bench_configs.py > $OUT/configs.jsonl
+python scripts/timeline.py > $OUT/timeline.txt
+python scripts/detest_sweep.py > $OUT/detest_sweep.jsonl
+nvcc -gencode arch=compute_100a,code=sm_100a -O3 --fmad=false -o $OUT/exp_combine scripts/exp_combine.cu && $OUT/exp_combine > $OUT/tma_sweep.txt
+# 4. multi-GPU (N = 2, 4, 8):  torchrun --nproc-per-node N scripts/dist_check.py ;  bench.py --gpus N [--scaling strong]

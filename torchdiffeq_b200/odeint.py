@@ -531,12 +531,6 @@ def _unflatten(p, sol):
     return sol.view(sol.shape[0], *p.shape)
 
 
-def _func_requires_grad(func):
-    if isinstance(func, torch.nn.Module):
-        return any(q.requires_grad for q in func.parameters())
-    return False
-
-
 class _ImplicitFnGradientRerouting(torch.autograd.Function):
     """odeint.py:197-231: gradient of the event time and of the state at the event through the implicit function
     theorem, event_fn(t*, y(t*)) = 0  =>  dt*/dy = -(dc/dy) / (dc/dt + dc/dy . f)."""
