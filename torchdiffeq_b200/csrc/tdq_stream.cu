@@ -142,10 +142,10 @@ struct FinalMap {
     signed char epos[TDQ_MAX_K];
 };
 
-// Coefficient storage of the fused kernel.  Narrow rows keep the 2*NU coefficients in registers; wide rows
-// (NU >= 6: dopri8's last row has nine operands) would push the kernel past 128 registers and down to one block
-// per SM -- measured 128 us instead of 65 us for dopri8/float64 -- so they read them from shared memory at the
-// point of use (volatile: the compiler must not hoist 2*NU loop-invariant values back into registers).
+// Coefficient storage of the fused kernel.  Narrow rows keep the 2*NU coefficients in registers; with five and more
+// operands (dopri5's last row: 5, dopri8's: 9) that costs ~45 registers and a block per SM of occupancy (126 vs 80
+// registers for float/NU=5), so those rows read the coefficients from shared memory at the point of use (volatile:
+// the compiler must not hoist 2*NU loop-invariant values back into registers).
 template <typename T> __device__ __forceinline__ T ld_shared_volatile(const T *p) { return *reinterpret_cast<const volatile T *>(p); }
 
 template <typename T, int NU, bool VECTOR>
@@ -154,7 +154,7 @@ k_combine_final(const TdqCtrl *__restrict__ c, int row, T *__restrict__ out, T *
                 KPtrs kp, FinalMap fm, size_t n) {
     if (c->halt) return;
     using A = Ar<T>;
-    constexpr bool SMEMC = NU >= 6;
+    constexpr bool SMEMC = NU >= 5;
     // two vectors per operand per thread for every row width: measured on dopri8/float64 (NU = 9), one vector per
     // operand halves the bandwidth (126 us vs 75 us) even at twice the occupancy -- bytes in flight per thread matter
     constexpr int THREADS = 256, U = 2;
