@@ -298,6 +298,13 @@ int tdq_fixed_final_emit(int32_t dtype, int32_t which, void *y0, const void *k1,
                          const int32_t *out_idx_dev, const int32_t *mode_dev, const void *slope_dev, int64_t *step_dev,
                          const void *tstage_all_dev, void *tstage_cur_dev, int64_t n_steps, size_t n, void *stream);
 
+/* Multistep (Adams) predictor / corrector sums (fixed_adams.py:198-215): out = [base +] sum_m x_m * T(coefs[m]), products
+ * and sums rounded separately, ascending m, first product initialising the sum (Python's sum()).  x, coefs: HOST
+ * arrays of n_terms <= TDQ_MAX_K entries; coefficients are float64 values the kernel casts to the state dtype (what torch
+ * does with a 0-dim float64 tensor times a state tensor); base may be NULL. */
+int tdq_lincomb(int32_t dtype, void *out, const void *base, const void *const *x, const double *coefs, int32_t n_terms,
+                size_t n, void *stream);
+
 /* interp='cubic' (solvers.py:120-125, :166-173): for records r in [rec_lo, rec_hi) of one step
  * solution[out_idx[r]] = h00*y0 + (h10*dt)*f0 + h01*y1 + (h11*dt)*f1 with the four weights of record r at
  * coef_dev[4*r .. 4*r+4) (state dtype; the caller evaluates them in t's dtype like the reference and folds the

@@ -490,6 +490,118 @@ def odeint_rk4(func, y0, t, grid=None, perturb=False, method="rk4", interp="line
 
 
 # ------------------------------------------------------------------------------------------------
+# fixed-step Adams-Bashforth(-Moulton) (fixed_adams.py:164-228)
+# ------------------------------------------------------------------------------------------------
+_ADAMS = None
+
+
+def adams_tables():
+    """Float64 weight tables of the reference (fixed_adams.py:10-141), not restated: dumped from the reference into
+    tests/golden/adams.json by make_golden.py.  Index k: the k weights of order k."""
+    global _ADAMS
+    if _ADAMS is None:
+        import json
+        import os
+        with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "tests", "golden", "adams.json")) as f:
+            _ADAMS = json.load(f)
+    return _ADAMS
+
+
+class AdamsStepper:
+    """AdamsBashforthMoulton (fixed_adams.py:164-222): history deque, RK4 bootstrap, predictor, functional iteration."""
+
+    def __init__(self, func, y0, rtol, atol, implicit=True, max_iters=4, max_order=12, perturb=False):
+        import collections
+        tabs = adams_tables()
+        self.bash = [torch.tensor(b, dtype=torch.float64) for b in tabs["bashforth"]]
+        self.moul = [torch.tensor(m, dtype=torch.float64) for m in tabs["moulton"]]
+        self.func, self.perturb, self.implicit, self.max_iters, self.max_order = func, perturb, implicit, max_iters, max_order
+        self.rtol, self.atol = torch.as_tensor(rtol, dtype=y0.dtype), torch.as_tensor(atol, dtype=y0.dtype)
+        self.prev_f, self.prev_t = collections.deque(maxlen=max_order - 1), None
+        self.T = _real_dtype(y0)
+
+    def _update(self, t, f):
+        if self.prev_t is None or self.prev_t != t:
+            self.prev_f.appendleft(f)
+            self.prev_t = t
+
+    def call(self, tt, yy, perturb=0):
+        """_PerturbFunc (misc.py:174-197): t is cast to the real dtype of the y it is called with -- for a 0-dim float32
+        state the stage values `y0 + dt * k` are float64 (two 0-dim tensors promote), and so is t then."""
+        tt = torch.as_tensor(tt).to(yy.abs().dtype)
+        if perturb > 0:
+            tt = _next(tt)
+        elif perturb < 0:
+            tt = _prev(tt)
+        return self.func(tt, yy)
+
+    def step(self, t0, dt, t1, y0):
+        """Returns (dy, f0)."""
+        p = 1 if self.perturb else 0
+        f0 = self.call(t0, y0, p)
+        self._update(t0, f0)
+        order = min(len(self.prev_f), self.max_order - 1)
+        if order < 3:
+            k1 = self.prev_f[0]
+            k2 = self.call(t0 + dt * _ONE_THIRD, y0 + dt * k1 * _ONE_THIRD)
+            k3 = self.call(t0 + dt * _TWO_THIRDS, y0 + dt * (k2 - k1 * _ONE_THIRD))
+            k4 = self.call(t1, y0 + dt * (k1 - k2 + k3), -p)
+            return (k1 + 3 * (k2 + k3) + k4) * dt * 0.125, f0
+        dot = lambda xs, ys: sum(xi * yi for xi, yi in zip(xs, ys))
+        dy = dot(dt * self.bash[order], self.prev_f).type_as(y0)
+        if self.implicit:
+            mc = self.moul[order + 1]
+            delta = dt * dot(mc[1:], self.prev_f).type_as(y0)
+            converged = False
+            for _ in range(self.max_iters):
+                dy_old = dy
+                f = self.call(t1, y0 + dy, -p)
+                dy = (dt * (mc[0]) * f).type_as(y0) + delta
+                err = torch.abs(dy_old - dy)
+                tol = self.atol + self.rtol * torch.max(dy_old.abs(), dy.abs())
+                converged = bool((err / tol).abs().max() < 1)
+                if converged:
+                    break
+            if not converged:
+                self.prev_f.pop()
+            self._update(t0, f)
+        return dy, f0
+
+
+def odeint_adams(func, y0, t, implicit=True, rtol=1e-7, atol=1e-9, grid=None, perturb=False, interp="linear",
+                 max_iters=4, max_order=12):
+    """odeint(..., method='implicit_adams' | 'explicit_adams') = FixedGridODESolver.integrate (solvers.py:102-128) around
+    AdamsBashforthMoulton._step_func.  odeint passes ITS rtol/atol to the solver (odeint.py:92)."""
+    sign = 1.0
+    if len(t) > 1 and t[0] > t[1]:
+        sign = -1.0
+        t = -t
+        if grid is not None:
+            grid = -grid
+    user = func
+    if sign < 0:
+        func = lambda tt, yy: -1.0 * user(-tt, yy)
+    grid = t if grid is None else grid
+    st = AdamsStepper(func, y0, rtol, atol, implicit, max_iters, max_order, perturb)
+    solution = torch.empty(len(t), *y0.shape, dtype=y0.dtype)
+    solution[0] = y0
+    j, y = 1, y0
+    for t0, t1 in zip(grid[:-1], grid[1:]):
+        dt = t1 - t0
+        dy, f0 = st.step(t0, dt, t1, y)
+        y1 = y + dy
+        while j < len(t) and t1 >= t[j]:
+            if interp == "cubic":
+                f1 = st.call(t1, y1)
+                solution[j] = cubic_hermite(t0, y, f0, t1, y1, f1, t[j])
+            else:
+                solution[j] = linear_interp(t0, t1, y, y1, t[j])
+            j += 1
+        y = y1
+    return solution
+
+
+# ------------------------------------------------------------------------------------------------
 # adjoint backward (adjoint.py:36-153) for a tensor state
 # ------------------------------------------------------------------------------------------------
 def adjoint_gradients(func, params, y0, t, grad_y, method="dopri5", rtol=1e-7, atol=1e-9,

@@ -6,3 +6,6 @@ cut -c1-200 gpurun_out/r2i/configs.jsonl
 timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 200 --csv --log-file gpurun_out/r2i/dopri8_launches.csv python -c "
 import sys; sys.path.insert(0,'scripts'); import bench_configs as b; b.dopri8_roofline()" > gpurun_out/r2i/dopri8.log 2>&1
 grep "k_combine_final" gpurun_out/r2i/dopri8_launches.csv | head -3 | cut -c1-60,200-
+timeout 120 ./scripts/exp_gemm.bin > gpurun_out/r2i/exp_gemm.txt 2>&1; cat gpurun_out/r2i/exp_gemm.txt
+timeout 300 python bench.py --steps 10 --warmup 3 --no-cpu-baseline > gpurun_out/r2i/bench.json 2> gpurun_out/r2i/bench.err; python -c "
+import json; d=json.loads(open('gpurun_out/r2i/bench.json').read()); print(d['value'], d['ms_per_step'], d['roofline']['frac'], d['roofline']['combine_plus_error_norm']['frac'])"

@@ -16,6 +16,7 @@ Outputs (committed):
     options.pt            step_t / min_step / max_step / first_step / tuple-state / vector-tol cases
     fixed_extra.pt        interp='cubic' and event handling for the fixed-grid methods
     adjoint_many.pt       odeint_adjoint on a field with 80 parameter tensors (default norm: 83 segments)
+    adams.json, adams.pt  Adams-Bashforth(-Moulton) weight tables and explicit_adams / implicit_adams solutions, events
     backprop.pt           gradients of plain odeint (autograd through the reference's solver operations)
 """
 import json
@@ -365,6 +366,60 @@ def adjoint_many():
     torch.save(out, os.path.join(HERE, "adjoint_many.pt"))
 
 
+def adams():
+    """explicit_adams / implicit_adams (fixed_adams.py:164-228): weight tables and solutions."""
+    from torchdiffeq._impl import fixed_adams as fa
+    with open(os.path.join(HERE, "adams.json"), "w") as f:
+        json.dump({"bashforth": [b.tolist() for b in fa._BASHFORTH_DIVISOR[:13]],
+                   "moulton": [m.tolist() for m in fa._MOULTON_DIVISOR[:13]]}, f)
+    out = {}
+    for ode in ("constant", "sine", "linear"):
+        for method in ("explicit_adams", "implicit_adams"):
+            for dtype in (torch.float32, torch.float64):
+                for reverse in (False, True):
+                    f, y0, t, sol = P.construct_problem("cpu", ode=ode, reverse=reverse, dtype=dtype)
+                    for name, opts in (("grid", None), ("step", {"step_size": 0.02}), ("cubic", {"step_size": 0.05, "interp": "cubic"})):
+                        rec = Rec(f)
+                        with torch.no_grad(), warnings_off():
+                            y = torchdiffeq.odeint(rec, y0, t, method=method, options=opts)
+                        out["%s/%s/%s/%s/%s" % (ode, method, str(dtype).split(".")[1], "rev" if reverse else "fwd", name)] = {
+                            "y": y, "nfe": rec.nfe, "opts": opts, "exact": sol}
+    # batched: the spiral, loose tolerances of the corrector exercised through odeint's rtol/atol
+    fs = P.Spiral()
+    g = torch.Generator().manual_seed(0)
+    y0 = (torch.tensor([[2., 0.]]) * (1 + 0.1 * torch.rand(64, 1, generator=g)))
+    t2 = torch.linspace(0., 5., 7)
+    for method in ("explicit_adams", "implicit_adams"):
+        for kw in ({}, {"rtol": 1e-3, "atol": 1e-4}):
+            rec = Rec(fs)
+            with torch.no_grad(), warnings_off():
+                y = torchdiffeq.odeint(rec, y0, t2, method=method, options={"step_size": 0.01, "max_order": 6}, **kw)
+            out["spiral/%s/%s" % (method, "loose" if kw else "tight")] = {"y": y, "nfe": rec.nfe, "kw": kw}
+    # event handling (event_tests.py:14-49: every fixed method with step_size 0.01 and cubic interpolation)
+    for ode in ("constant", "sine"):
+        for method in ("explicit_adams", "implicit_adams"):
+            for reverse in (False, True):
+                fe, ye, te, sol = P.construct_problem("cpu", ode=ode, reverse=reverse, dtype=torch.float64)
+                target = sol[2]
+                rec = Rec(fe)
+                with torch.no_grad(), warnings_off():
+                    et, ys = torchdiffeq.odeint(rec, ye, te[0:2], event_fn=lambda t_, y_: torch.sum(y_ - target).real,
+                                                method=method, options={"step_size": 0.01, "interp": "cubic"})
+                out["event/%s/%s/%s" % (ode, method, "rev" if reverse else "fwd")] = {"event_t": et, "y": ys, "nfe": rec.nfe}
+    torch.save(out, os.path.join(HERE, "adams.pt"))
+
+
+class warnings_off:
+    def __enter__(self):
+        import warnings
+        self.c = warnings.catch_warnings()
+        self.c.__enter__()
+        warnings.simplefilter("ignore")
+
+    def __exit__(self, *a):
+        return self.c.__exit__(*a)
+
+
 def dense():
     """odeint_dense (odeint.py:111-157): the dense-output closure of a dopri5 solve."""
     out = {}
@@ -396,5 +451,6 @@ if __name__ == "__main__":
     fixed_extra()
     backprop()
     adjoint_many()
+    adams()
     for fn in sorted(os.listdir(HERE)):
         print(fn, os.path.getsize(os.path.join(HERE, fn)))

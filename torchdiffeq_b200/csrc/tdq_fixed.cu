@@ -193,6 +193,25 @@ k_fixed_emit_cubic(const T *__restrict__ y0, const T *__restrict__ y1, const T *
     }
 }
 
+// Generic linear combination for the multistep (Adams) predictor / corrector of fixed_adams.py:198-215:
+//   out = [base +] ((x_0*c_0 + x_1*c_1) + x_2*c_2) + ...      products and sums rounded separately, ascending order,
+// the first product initialises the sum (Python's sum() starts from 0 + x_0*c_0 = x_0*c_0 exactly).
+struct LinArgs {
+    const void *x[TDQ_MAX_K];
+    double c[TDQ_MAX_K];
+};
+
+template <typename T>
+__global__ void __launch_bounds__(kThreads)
+k_lincomb(T *__restrict__ out, const T *base, LinArgs a, int n_terms, size_t n) {
+    using A = Ar<T>;
+    for (size_t i = (size_t)blockIdx.x * kThreads + threadIdx.x; i < n; i += (size_t)gridDim.x * kThreads) {
+        T acc = A::mul(reinterpret_cast<const T *>(a.x[0])[i], (T)a.c[0]);
+        for (int m = 1; m < n_terms; ++m) acc = A::add(acc, A::mul(reinterpret_cast<const T *>(a.x[m])[i], (T)a.c[m]));
+        out[i] = base ? A::add(base[i], acc) : acc;
+    }
+}
+
 struct PackArgs {
     const void *src[TDQ_MAX_SEGS];
     int64_t off[TDQ_MAX_SEGS];
@@ -293,6 +312,26 @@ int tdq_fixed_final_emit(int32_t dtype, int32_t which, void *y0, const void *k1,
     else if (which == 7) TDQ_FE(7);
     else TDQ_FE(9);
 #undef TDQ_FE
+    TDQ_CHECK_CUDA(cudaGetLastError());
+    return TDQ_OK;
+}
+
+int tdq_lincomb(int32_t dtype, void *out, const void *base, const void *const *x, const double *coefs, int32_t n_terms,
+                size_t n, void *stream) {
+    TDQ_REQUIRE(out && x && coefs, "null argument");
+    TDQ_REQUIRE(n_terms >= 1 && n_terms <= TDQ_MAX_K, "n_terms out of range");
+    LinArgs a;
+    memset(&a, 0, sizeof(a));
+    for (int m = 0; m < n_terms; ++m) {
+        TDQ_REQUIRE(x[m] != nullptr, "null term");
+        a.x[m] = x[m];
+        a.c[m] = coefs[m];
+    }
+    if (n == 0) return TDQ_OK;
+    size_t blocks = (n + kThreads - 1) / kThreads;
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    TDQ_DISPATCH_T(dtype, (k_lincomb<T><<<(unsigned)blocks, kThreads, 0, (cudaStream_t)stream>>>(
+                               (T *)out, (const T *)base, a, n_terms, n)));
     TDQ_CHECK_CUDA(cudaGetLastError());
     return TDQ_OK;
 }

@@ -18,6 +18,7 @@ from ._fixed import FixedGridEngine, grid_from_step_size
 
 ADAPTIVE_METHODS = ("dopri5", "dopri8", "tsit5", "bosh3", "fehlberg2", "adaptive_heun")
 FIXED_METHODS = ("euler", "midpoint", "heun2", "heun3", "rk4")
+ADAMS_METHODS = {"explicit_adams": False, "implicit_adams": True, "fixed_adams": True}     # name -> implicit (odeint.py:31-42)
 # Every name the reference registers (odeint.py:19-46); the ones outside SURVEY.md section 8 are
 # recognised and rejected explicitly rather than reported as "invalid".
 REFERENCE_METHODS = (
@@ -30,6 +31,7 @@ _ADJOINT_CALLBACK_NAMES = [name + "_adjoint" for name in _CALLBACK_NAMES]       
 _ADAPTIVE_OPTIONS = {"min_step", "max_step", "first_step", "step_t", "jump_t", "safety", "ifactor", "dfactor",
                      "max_num_steps", "dtype", "norm"}
 _FIXED_OPTIONS = {"step_size", "grid_constructor", "interp", "perturb", "norm"}
+_ADAMS_OPTIONS = _FIXED_OPTIONS | {"max_iters", "max_order"}
 _OUR_OPTIONS = {"graph", "run_ahead", "process_group", "cache", "exchange", "device_loop"}
 
 
@@ -124,9 +126,9 @@ def normalise(func, y0, t, rtol, atol, method, options, event_fn, adjoint=False)
     if method not in REFERENCE_METHODS:                                               # misc.py:232-234
         raise ValueError('Invalid method "{}". Must be one of {}'.format(
             method, '{"' + '", "'.join(REFERENCE_METHODS) + '"}.'))
-    if method not in ADAPTIVE_METHODS + FIXED_METHODS:
+    if method not in ADAPTIVE_METHODS + FIXED_METHODS + tuple(ADAMS_METHODS):
         raise NotImplementedError('method "{}" is not part of the B200 hot path; implemented: {}'.format(
-            method, ADAPTIVE_METHODS + FIXED_METHODS))
+            method, ADAPTIVE_METHODS + FIXED_METHODS + tuple(ADAMS_METHODS)))
     p.method, p.options = method, options
     if p.device.type != "cuda":
         raise _lib.TdqError("torchdiffeq_b200 runs on CUDA devices only (got %s); there is no CPU path" % p.device)
@@ -168,7 +170,7 @@ def normalise(func, y0, t, rtol, atol, method, options, event_fn, adjoint=False)
         cb = getattr(func, name, None)
         if cb is not None:
             p.callbacks[name] = cb
-    valid = set(_CALLBACK_NAMES) if method in ADAPTIVE_METHODS else {"callback_step"}
+    valid = set(_CALLBACK_NAMES) if method in ADAPTIVE_METHODS else {"callback_step"}     # solvers.py:81-83
     invalid = set(p.callbacks) - valid
     if invalid:
         warnings.warn("Solver '{}' does not support callbacks {}".format(method, invalid))
@@ -460,9 +462,7 @@ def _solve(p):
     o = p.options
     y0_view = p.layout.views(p.y0_flat) if p.is_tuple else p.y0_flat.view(p.shape)
     grid = fixed_grid(p.method, o, p.original_func, y0_view, p.t_cpu)
-    eng = FixedGridEngine(p.fn, p.n, p.dtype, p.device, method=p.method, t_sign=p.t_sign,
-                          perturb=o.get("perturb", False), graph=_resolve_graph(o.get("graph", "auto"), p.original_func),
-                          callbacks=p.callbacks, pieces=p.pieces, interp=o.get("interp", "linear"))
+    eng = _fixed_engine(p)
     sol = eng.solve(p.y0_flat, grid, p.t_cpu)
     return sol, eng
 
@@ -478,13 +478,31 @@ def fixed_event_solve(eng, y0_flat, t0, step_size, event_fn, atol):
     return eng.solve_until_event(y0_flat, t0, step_size, event_fn, atol)
 
 
-_FIXED_NAMES = {"euler": "Euler", "midpoint": "Midpoint", "heun2": "Heun2", "heun3": "Heun3", "rk4": "RK4"}
+_FIXED_NAMES = {"euler": "Euler", "midpoint": "Midpoint", "heun2": "Heun2", "heun3": "Heun3", "rk4": "RK4",
+                "explicit_adams": "AdamsBashforth", "implicit_adams": "AdamsBashforthMoulton",
+                "fixed_adams": "AdamsBashforthMoulton"}
+
+
+def _fixed_engine(p, graph=None, interp=None):
+    """The fixed-grid engine of a normalised problem: explicit RK step kernels, or the Adams multistep driver."""
+    o = p.options
+    interp = _cubic_or_linear(o.get("interp", "linear")) if interp is None else interp
+    if p.method in ADAMS_METHODS:
+        from ._adams import AdamsEngine
+        if p.rtol is None or p.atol is None:
+            raise NotImplementedError("per-element tolerances are not implemented for the Adams methods")
+        return AdamsEngine(p.fn, p.n, p.dtype, p.device, implicit=ADAMS_METHODS[p.method], rtol=p.rtol, atol=p.atol,
+                           max_iters=o.get("max_iters", 4), max_order=o.get("max_order", 12), t_sign=p.t_sign,
+                           perturb=o.get("perturb", False), callbacks=p.callbacks, pieces=p.pieces, interp=interp)
+    g = _resolve_graph(o.get("graph", "auto"), p.original_func) if graph is None else graph
+    return FixedGridEngine(p.fn, p.n, p.dtype, p.device, method=p.method, t_sign=p.t_sign,
+                           perturb=o.get("perturb", False), graph=g, callbacks=p.callbacks, pieces=p.pieces, interp=interp)
 
 
 def fixed_grid(method, o, func, y0_view, t_cpu, keep_graph=False):
     """Option handling and time grid of FixedGridODESolver (solvers.py:55-79, :85-96, :103-104) for an
     ascending CPU `t_cpu`; the caller has already wrapped a user grid_constructor for reversed time."""
-    _warn_unused(_FIXED_NAMES[method], o, _FIXED_OPTIONS)
+    _warn_unused(_FIXED_NAMES[method], o, _ADAMS_OPTIONS if method in ADAMS_METHODS else _FIXED_OPTIONS)
     step_size, gc = o.get("step_size"), o.get("grid_constructor")
     if step_size is None:
         grid_constructor = gc if gc is not None else (lambda f, y0, t: t)
@@ -501,17 +519,15 @@ def fixed_grid(method, o, func, y0_view, t_cpu, keep_graph=False):
 
 def _solve_event(p):
     """odeint.py:97-100 + solvers.py:41-49: integrate until the event; returns (event_t tensor like t, [2, n])."""
-    if p.method in FIXED_METHODS:                                                      # solvers.py:130-164
+    if p.method in FIXED_METHODS or p.method in ADAMS_METHODS:                         # solvers.py:130-164
         o = p.options
-        _warn_unused(_FIXED_NAMES[p.method], o, _FIXED_OPTIONS)
+        _warn_unused(_FIXED_NAMES[p.method], o, _ADAMS_OPTIONS if p.method in ADAMS_METHODS else _FIXED_OPTIONS)
         if o.get("step_size") is None:
             raise AssertionError("Event handling for fixed step solvers currently requires `step_size` to be provided "
                                  "in options.")
         if o.get("grid_constructor") is not None:
             raise ValueError("step_size and grid_constructor are mutually exclusive arguments.")
-        eng = FixedGridEngine(p.fn, p.n, p.dtype, p.device, method=p.method, t_sign=p.t_sign,
-                              perturb=o.get("perturb", False), graph=False, pieces=p.pieces,
-                              interp=_cubic_or_linear(o.get("interp", "linear")))
+        eng = _fixed_engine(p, graph=False)
         tol = p.atol if p.atol is not None else float(p.atol_vec.min())
         event_t, y_event = fixed_event_solve(eng, p.y0_flat, p.t_cpu[0], o["step_size"], p.event_fn, tol)
         sol = torch.stack([p.y0_flat.to(p.dtype), y_event], dim=0)
@@ -647,6 +663,9 @@ def _odeint_backprop(p, func, y0, t, params, _stats):
             holder["eng"] = eng
             return sol.clone(), {"kind": "adaptive", "tape": tape, "tab": adaptive_tableau(p.method)}
         o = p.options
+        if p.method in ADAMS_METHODS:
+            raise NotImplementedError("gradients of the discrete solve are implemented for the explicit Runge-Kutta "
+                                      "methods; use odeint_adjoint with the Adams methods")
         if o.get("interp", "linear") != "linear":
             raise NotImplementedError("gradients through interp='cubic' are not implemented (use the default linear "
                                       "interpolation, or odeint_adjoint)")
