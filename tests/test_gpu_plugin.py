@@ -222,3 +222,18 @@ def test_seam_graph_mode_opt_in(front):
         a = odeint(f, y0, t, method="dopri5", rtol=1e-5, atol=1e-7)
         b = odeint(f, y0, t, method="dopri5", rtol=1e-5, atol=1e-7, options={"graph": True})
     assert torch.equal(a, b)
+
+
+@pytest.mark.parametrize("method", ["explicit_adams", "implicit_adams"])
+def test_seam_adams(front, method):
+    """The Adams methods through the seam (odeint.py:31-42 registers AdamsBashforth / AdamsBashforthMoulton; the
+    constructor receives odeint's rtol/atol, fixed_adams.py:167-175)."""
+    odeint, _, _ = front
+    AD = ld("adams.pt")
+    for direction in ("fwd", "rev"):
+        case = AD["linear/%s/float64/%s/step" % (method, direction)]
+        f, y0, t, _ = P.construct_problem(DEV, ode="linear", reverse=direction == "rev", dtype=torch.float64)
+        with torch.no_grad():
+            y = odeint(f, y0, t, method=method, options=case["opts"])
+        assert torch.allclose(y.cpu(), case["y"], rtol=1e-9, atol=1e-9)
+        assert f.nfe == case["nfe"]

@@ -37,6 +37,7 @@ from ._fixed import FixedGridEngine, grid_from_step_size
 
 ADAPTIVE = ("dopri5", "dopri8", "tsit5", "bosh3", "fehlberg2", "adaptive_heun")
 FIXED = ("euler", "midpoint", "heun2", "heun3", "rk4")
+ADAMS = {"explicit_adams": False, "implicit_adams": True, "fixed_adams": True}
 _CB = ("callback_step", "callback_accept_step", "callback_reject_step")
 _ADAPTIVE_KEYS = ("min_step", "max_step", "first_step", "step_t", "jump_t", "safety", "ifactor", "dfactor", "max_num_steps")
 _OUR_KEYS = ("graph", "run_ahead", "device_loop")
@@ -170,7 +171,9 @@ def make_adaptive(method, **defaults):
 
 
 def make_fixed(method, **defaults):
-    """Class with the interface of FixedGridODESolver (solvers.py:52-128) for one explicit fixed-step method."""
+    """Class with the interface of FixedGridODESolver (solvers.py:52-128) for one explicit fixed-step method, or of
+    AdamsBashforth / AdamsBashforthMoulton (fixed_adams.py:164-228) for the Adams names."""
+    adams = method in ADAMS
 
     class B200FixedSolver:
         name = method
@@ -180,7 +183,8 @@ def make_fixed(method, **defaults):
             if not y0.is_cuda:
                 raise _lib.TdqError("torchdiffeq_b200.plugin solvers take CUDA tensors (got %s)" % y0.device)
             self.atol = unused_kwargs.pop("atol", None)                        # solvers.py:58-61
-            unused_kwargs.pop("rtol", None)
+            self.rtol = unused_kwargs.pop("rtol", None)
+            self.adams_kw = {k: unused_kwargs.pop(k) for k in ("max_iters", "max_order") if adams and k in unused_kwargs}
             unused_kwargs.pop("norm", None)
             self.our = {k: unused_kwargs.pop(k) for k in _OUR_KEYS if k in unused_kwargs}
             for k, v in defaults.items():
@@ -202,19 +206,28 @@ def make_fixed(method, **defaults):
         def valid_callbacks(cls):                                              # solvers.py:81-83
             return {"callback_step"}
 
+        def _make_engine(self, interp, graph):
+            shape, base = self.shape, self.base
+            fn = lambda t_, yf: base(t_, yf.view(shape))
+            if adams:
+                from ._adams import AdamsEngine
+                return AdamsEngine(fn, self.y0.numel(), self.y0.dtype, self.y0.device, implicit=ADAMS[method],
+                                   rtol=self.rtol if self.rtol is not None else 1e-3,
+                                   atol=self.atol if self.atol is not None else 1e-4, perturb=self.perturb,
+                                   callbacks=self.callbacks, interp=interp, **self.adams_kw)
+            return FixedGridEngine(fn, self.y0.numel(), self.y0.dtype, self.y0.device, method=method, perturb=self.perturb,
+                                   graph=graph, callbacks=self.callbacks, interp=interp)
+
         def integrate(self, t):                                                # solvers.py:102-128
             from .odeint import _cubic_or_linear
             interp = _cubic_or_linear(self.interp)
-            shape, base = self.shape, self.base
+            shape = self.shape
             t_cpu = t.detach().to("cpu")
             grid = self.grid_constructor(self.func, self.y0, t_cpu).detach().to("cpu")
             assert grid[0] == t_cpu[0] and grid[-1] == t_cpu[-1]
             lock = "graph" not in self.our
             with torch.no_grad(), on_solver_stream(self.y0.device) as ss:
-                eng = FixedGridEngine(lambda t_, yf: base(t_, yf.view(shape)), self.y0.numel(), self.y0.dtype,
-                                      self.y0.device, method=method, perturb=self.perturb,
-                                      graph=False if lock else self.our.get("graph", False), callbacks=self.callbacks,
-                                      interp=interp)
+                eng = self._make_engine(interp, False if lock else self.our.get("graph", False))
                 sol = eng.solve(self.y0.detach().reshape(-1), grid, t_cpu).view(len(t), *shape)
                 ss.publish(sol)
             return sol
@@ -223,11 +236,9 @@ def make_fixed(method, **defaults):
             from .odeint import _cubic_or_linear, fixed_event_solve
             assert self.step_size is not None, ("Event handling for fixed step solvers currently requires `step_size` "
                                                 "to be provided in options.")
-            shape, base = self.shape, self.base
+            shape = self.shape
             with torch.no_grad(), on_solver_stream(self.y0.device) as ss:
-                eng = FixedGridEngine(lambda t_, yf: base(t_, yf.view(shape)), self.y0.numel(), self.y0.dtype,
-                                      self.y0.device, method=method, perturb=self.perturb, graph=False,
-                                      interp=_cubic_or_linear(self.interp))
+                eng = self._make_engine(_cubic_or_linear(self.interp), False)
                 ev = lambda t_, yf: event_fn(t_, yf.view(shape))
                 event_t, y1 = fixed_event_solve(eng, self.y0.detach().reshape(-1), t0, self.step_size, ev, float(self.atol))
                 sol = torch.stack([self.y0.detach(), y1.view(shape)], dim=0)
@@ -256,7 +267,7 @@ class _Dispatch:
         return self.gpu_cls.valid_callbacks()
 
 
-def register(solvers=None, methods=ADAPTIVE + FIXED, **defaults):
+def register(solvers=None, methods=ADAPTIVE + FIXED + tuple(ADAMS), **defaults):
     """Put the libtdq-backed solvers into a SOLVERS dict (default: the reference's, found through
     importlib.import_module('torchdiffeq._impl.odeint') -- the attribute torchdiffeq._impl.odeint is shadowed by the
     function of the same name).  In place, so torchdiffeq._impl.adjoint sees it too.  Returns the dict of replaced
