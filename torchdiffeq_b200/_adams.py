@@ -156,10 +156,12 @@ class AdamsEngine(FixedGridEngine):
             self._lincomb(delta, None, [(S, dt_T)])                              # dt * (...) with dt cast to T
             converged = False
             c0 = sgn * (dt64 * moul[0])
+            alive = []           # keep every output of this step allocated: a recycled address would look like aliasing
             for _ in range(self.max_iters):
                 dy_old = dy
                 self._lincomb(self.ytmp, self.y0w, [(dy, 1.0)])                  # y0 + dy
                 f = self._call_fn(self.tcur[3], self.ytmp, None)                 # t1 (Perturb.PREV in tcur)
+                alive.append(f)
                 dy = torch.empty(self.n, dtype=T, device=dev)
                 self._lincomb(dy, delta, [(f, c0)])                              # (dt*m0*f) + delta
                 # fixed_adams.py:188-191: max |(|dy_old - dy|) / (atol + rtol*max(|dy_old|, |dy|))| < 1 -- a host decision

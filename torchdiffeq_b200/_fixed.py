@@ -211,8 +211,10 @@ class FixedGridEngine:
         lo, hi = int(self._rec_begin_cpu[step]), int(self._rec_begin_cpu[step + 1])
         if hi <= lo:
             return
+        alive = []               # keep the evaluations allocated until the step is over (see _call_fn's aliasing test)
         for _ in range(hi - lo):
             f1 = self._call_fn(self.t1_dev[step], self.y1, None)
+            alive.append(f1)
         _lib.check(self.lib.tdq_fixed_emit_cubic(self.dc, self.y0w.data_ptr(), self.y1.data_ptr(), k1.data_ptr(),
                                                  f1.data_ptr(), self.solution.data_ptr(), self.out_idx.data_ptr(),
                                                  self.cubic_dev.data_ptr(), lo, hi, self.n, _stream()))

@@ -142,25 +142,19 @@ struct FinalMap {
     signed char epos[TDQ_MAX_K];
 };
 
-// Coefficient storage of the fused kernel.  Narrow rows keep the 2*NU coefficients in registers; with five and more
-// operands (dopri5's last row: 5, dopri8's: 9) that costs ~45 registers and a block per SM of occupancy (126 vs 80
-// registers for float/NU=5), so those rows read the coefficients from shared memory at the point of use (volatile:
-// the compiler must not hoist 2*NU loop-invariant values back into registers).
-template <typename T> __device__ __forceinline__ T ld_shared_volatile(const T *p) { return *reinterpret_cast<const volatile T *>(p); }
-
+// Coefficients live in registers.  A shared-memory variant (volatile reads at the point of use, ~45 registers and one
+// block per SM of occupancy saved) was measured on B200 and is slower: dopri5's last row 0.063 vs 0.038 ms, dopri8/float64
+// no better than registers (83 vs 80 us) -- the extra LDS traffic in the inner loop costs more than the occupancy buys.
 template <typename T, int NU, bool VECTOR>
 __global__ void __launch_bounds__(256)
 k_combine_final(const TdqCtrl *__restrict__ c, int row, T *__restrict__ out, T *__restrict__ err_out, const T *y0,
                 KPtrs kp, FinalMap fm, size_t n) {
     if (c->halt) return;
     using A = Ar<T>;
-    constexpr bool SMEMC = NU >= 5;
     // two vectors per operand per thread for every row width: measured on dopri8/float64 (NU = 9), one vector per
     // operand halves the bandwidth (126 us vs 75 us) even at twice the occupancy -- bytes in flight per thread matter
     constexpr int THREADS = 256, U = 2;
-    constexpr int NR = SMEMC ? 1 : NU;
-    __shared__ T s_cr[SMEMC ? NU : 1], s_ce[SMEMC ? NU : 1];
-    T cr[NR], ce[NR];
+    T cr[NU], ce[NU];
     unsigned mask_r = 0, mask_e = 0;
     const T *k[NU];
     if (y0 == nullptr) y0 = reinterpret_cast<const T *>(c->y0_cur);
@@ -171,27 +165,22 @@ k_combine_final(const TdqCtrl *__restrict__ c, int row, T *__restrict__ out, T *
         if (ue) mask_e |= 1u << m;
         const T vr = ur ? (T)c->coef[row][fm.rpos[m]] : (T)0;
         const T ve = ue ? (T)c->ecoef[fm.epos[m]] : (T)0;
-        if (SMEMC) {
-            if (threadIdx.x == 0) { s_cr[m] = vr; s_ce[m] = ve; }
-        } else {
-            cr[m] = vr;
-            ce[m] = ve;
-        }
+        cr[m] = vr;
+        ce[m] = ve;
         k[m] = reinterpret_cast<const T *>(kp.p[m] ? kp.p[m] : c->k0_cur);
     }
-    if (SMEMC) __syncthreads();
     auto element = [&](T y, const T *kv, T &yo, T &eo) {
         T ar = (T)0, ae = (T)0;
         bool fr = true, fe = true;
 #pragma unroll
         for (int m = 0; m < NU; ++m) {
             if ((mask_r >> m) & 1u) {
-                const T p = A::mul(kv[m], SMEMC ? ld_shared_volatile(&s_cr[m]) : cr[SMEMC ? 0 : m]);
+                const T p = A::mul(kv[m], cr[m]);
                 ar = fr ? p : A::add(ar, p);
                 fr = false;
             }
             if ((mask_e >> m) & 1u) {
-                const T p = A::mul(kv[m], SMEMC ? ld_shared_volatile(&s_ce[m]) : ce[SMEMC ? 0 : m]);
+                const T p = A::mul(kv[m], ce[m]);
                 ae = fe ? p : A::add(ae, p);
                 fe = false;
             }
