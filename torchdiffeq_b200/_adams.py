@@ -121,6 +121,9 @@ class AdamsEngine(FixedGridEngine):
         sgn = self.t_sign
         # func outputs of earlier steps are kept: a func that reuses one output buffer must be copied
         self._taken = {h.data_ptr() for h in self.prev_f}
+        # ... and the entry the deque drops in this step stays allocated until the next one: a recycled address would
+        # look like a func that reuses its output buffer (_call_fn's aliasing test), also to the cubic emit's f1
+        self._hist_alive = list(self.prev_f)
         f0 = self._call_fn(self.tcur[0], self.y0w, None)                         # fixed_adams.py:194 (Perturb.NEXT in tcur)
         self._update_history(t0, f0)
         order = min(len(self.prev_f), self.max_order - 1)
