@@ -17,3 +17,4 @@ for f in sorted(glob.glob('gpurun_out/r2g/bench_n${N}*.json')):
         d=json.loads([l for l in open(f).read().splitlines() if l.startswith('{')][-1]); print(f, round(d['value']), round(d['ms_per_step'],3), d['scaling'], round(d['e2e']['value']), d['result_check'])
     except Exception as e: print(f,'ERR',e)
 PY
+timeout 300 python -m pytest tests -m gpu -x -q -k "adams" > gpurun_out/r2g/pytest_adams.log 2>&1; tail -2 gpurun_out/r2g/pytest_adams.log

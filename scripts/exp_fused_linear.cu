@@ -1,0 +1,316 @@
+// Experiment (not part of libtdq): a Runge-Kutta stage fused with a LINEAR vector field on the 5th-generation tensor cores.
+//
+//   y_i = y0 + sum_j cf_j * k_j          (the stage combination of tdq_stream.cu, same expression order)
+//   k_i = y_i @ A^T                      (the field of BASELINE.json configs[1]: 65536 x 128 states, A 128 x 128)
+//
+// The float32 product is computed as a BF16x9 emulation (each float32 operand = hi + mid + lo bfloat16 planes, exact to 24 bits;
+// nine bf16 products accumulated in float32 in tensor memory), the scheme cuBLAS 12.9 offers as
+// CUBLAS_COMPUTE_32F_EMULATED_16BFX9.  y_i never goes to HBM: it is split in registers and stored as three bf16 operand planes
+// in shared memory (128-byte swizzle, K-major), tcgen05.mma reads them, tcgen05.ld brings the accumulator tile back.
+//
+// build:  nvcc -gencode arch=compute_100a,code=sm_100a -O3 --fmad=false -lineinfo -o /tmp/exp_fused_linear scripts/exp_fused_linear.cu
+// run:    /tmp/exp_fused_linear [rows]
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#include <cmath>
+#include <vector>
+
+#define CK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { printf("CUDA error %s at %s:%d\n", cudaGetErrorString(e_), __FILE__, __LINE__); exit(1); } } while (0)
+
+constexpr int D = 128;                 // state width = GEMM N = GEMM K
+constexpr int TM = 128;                // rows per tile = GEMM M
+constexpr int ATOM_BYTES = 128 * 128;  // one swizzle atom column: 128 rows x 128 bytes (64 bf16 of K)
+constexpr int PLANE_BYTES = 2 * ATOM_BYTES;   // K = 128 bf16 = two atoms
+constexpr int MAXK = 7;
+
+struct KP { const float *p[MAXK]; };
+struct CF { float c[MAXK]; };
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+// ---- float32 -> three bf16 planes, two elements at a time (packed: element 0 in the low half) --------------------------------
+__device__ __forceinline__ void split2(float a, float b, uint32_t &h, uint32_t &m, uint32_t &l) {
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(h) : "f"(b), "f"(a));
+    const float ra = a - __uint_as_float(h << 16), rb = b - __uint_as_float(h & 0xffff0000u);       // exact
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(m) : "f"(rb), "f"(ra));
+    const float sa = ra - __uint_as_float(m << 16), sb = rb - __uint_as_float(m & 0xffff0000u);     // exact
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(l) : "f"(sb), "f"(sa));
+}
+
+// byte offset, inside one plane, of the 8-byte group holding elements [4*q, 4*q+4) of row r (q = 0..31):
+// K-major, 128-byte swizzle: atoms of 8 rows x 128 bytes, 16-byte chunk index XOR (row mod 8); rows 128 B apart,
+// the second 64 elements of K one ATOM (16 KB) further
+__device__ __forceinline__ uint32_t plane_offset(int r, int q) {
+    const int katom = q >> 4, chunk = (q & 15) >> 1, half = q & 1;
+    return katom * ATOM_BYTES + r * 128 + ((chunk ^ (r & 7)) << 4) + half * 8;
+}
+
+template <typename P>
+__device__ __forceinline__ void store_split(P *base, int r, int q, float4 v) {
+    uint32_t h0, m0, l0, h1, m1, l1;
+    split2(v.x, v.y, h0, m0, l0);
+    split2(v.z, v.w, h1, m1, l1);
+    const uint32_t off = plane_offset(r, q);
+    *reinterpret_cast<uint2 *>(base + off) = make_uint2(h0, h1);
+    *reinterpret_cast<uint2 *>(base + PLANE_BYTES + off) = make_uint2(m0, m1);
+    *reinterpret_cast<uint2 *>(base + 2 * PLANE_BYTES + off) = make_uint2(l0, l1);
+}
+
+// A (128 x 128 float32, row n = output column n, K contiguous) -> three pre-swizzled bf16 planes in global memory
+__global__ void k_split_weights(const float *__restrict__ A, uint8_t *__restrict__ planes) {
+    const int r = blockIdx.x, q = threadIdx.x;          // 128 blocks x 32 threads
+    const float4 v = *reinterpret_cast<const float4 *>(A + (size_t)r * D + q * 4);
+    store_split(planes, r, q, v);
+}
+
+// ---- tcgen05 / mbarrier wrappers ----------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr) {
+    // UMMA shared-memory descriptor (cute/arch/mma_sm100_desc.hpp SmemDescriptor): start address >> 4 in [0,14), leading byte
+    // offset >> 4 in [16,30) (unused for swizzled K-major), stride byte offset >> 4 in [32,46) = 1024 B between 8-row groups,
+    // version 1 in [46,48), layout type SWIZZLE_128B = 2 in [61,64)
+    return (uint64_t)((saddr & 0x3FFFFu) >> 4) | (1ull << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
+}
+// instruction descriptor (InstrDescriptor): D = F32 (1 at [4,6)), A = B = BF16 (1 at [7,10), [10,13)), both K-major,
+// N >> 3 at [17,23), M >> 4 at [24,29)
+constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(D >> 3) << 17) | ((uint32_t)(TM >> 4) << 24);
+
+__device__ __forceinline__ void mma_bf16(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t accumulate) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                 "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}\n"
+                 :: "r"(tmem_d), "l"(da), "l"(db), "r"(IDESC), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void mma_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" :: "r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    asm volatile("{\n\t.reg .pred p;\n\tWAIT_%=:\n\t"
+                 "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+                 "@p bra DONE_%=;\n\tbra WAIT_%=;\n\tDONE_%=:\n\t}\n" :: "r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+                 "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+                   "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+                   "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+                   "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+                 : "r"(taddr) : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// ---- the fused stage ----------------------------------------------------------------------------------------------------------
+constexpr int THREADS = 256;
+constexpr int TMEM_COLS = 128;
+constexpr int SMEM_BYTES = 6 * PLANE_BYTES + 1024 + 64;
+
+template <int NK>
+__global__ void __launch_bounds__(THREADS, 1)
+k_linear_stage(const float *__restrict__ y0, KP kp, CF cf, const uint8_t *__restrict__ wplanes, float *__restrict__ kout,
+               int ntiles) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint8_t *sB = smem, *sA = smem + 3 * PLANE_BYTES;
+    uint64_t *bar = reinterpret_cast<uint64_t *>(smem + 6 * PLANE_BYTES);
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + 6 * PLANE_BYTES + 16);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(smem_u32(tmem_slot)), "n"(TMEM_COLS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    if (tid == 32) {
+        mbar_init(smem_u32(bar), 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    for (int i = tid; i < 3 * PLANE_BYTES / 16; i += THREADS)
+        reinterpret_cast<uint4 *>(sB)[i] = reinterpret_cast<const uint4 *>(wplanes)[i];
+    fence_async_smem();
+    fence_before();
+    __syncthreads();
+    fence_after();
+    const uint32_t tmem_d = *tmem_slot;
+    const uint32_t a_base = smem_u32(sA), b_base = smem_u32(sB), bar_a = smem_u32(bar);
+
+    uint32_t it = 0;
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+        const size_t row0 = (size_t)tile * TM;
+        // ---- stage combination, split, operand planes ----
+#pragma unroll 1
+        for (int i = 0; i < 4; ++i) {
+            float4 a[4], kv[4][NK > 0 ? NK : 1];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int r = warp + 8 * (4 * i + u);
+                const size_t off = (row0 + r) * D + lane * 4;
+                a[u] = __ldcs(reinterpret_cast<const float4 *>(y0 + off));
+#pragma unroll
+                for (int m = 0; m < NK; ++m) kv[u][m] = __ldcs(reinterpret_cast<const float4 *>(kp.p[m] + off));
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int r = warp + 8 * (4 * i + u);
+                float4 y = a[u];
+                if (NK > 0) {
+                    float4 acc = make_float4(kv[u][0].x * cf.c[0], kv[u][0].y * cf.c[0], kv[u][0].z * cf.c[0], kv[u][0].w * cf.c[0]);
+#pragma unroll
+                    for (int m = 1; m < NK; ++m) {
+                        acc.x = acc.x + kv[u][m].x * cf.c[m];
+                        acc.y = acc.y + kv[u][m].y * cf.c[m];
+                        acc.z = acc.z + kv[u][m].z * cf.c[m];
+                        acc.w = acc.w + kv[u][m].w * cf.c[m];
+                    }
+                    y = make_float4(y.x + acc.x, y.y + acc.y, y.z + acc.z, y.w + acc.w);
+                }
+                store_split(sA, r, lane, y);
+            }
+        }
+        fence_async_smem();
+        fence_before();
+        __syncthreads();
+        // ---- nine bf16 products, smallest first, accumulated in tensor memory ----
+        if (tid == 0) {
+            fence_after();
+            constexpr int PA[9] = {2, 2, 1, 2, 0, 1, 1, 0, 0};
+            constexpr int PB[9] = {2, 1, 2, 0, 2, 1, 0, 1, 0};
+            uint32_t acc = 0;
+#pragma unroll
+            for (int p = 0; p < 9; ++p) {
+#pragma unroll
+                for (int ks = 0; ks < 8; ++ks) {
+                    const uint32_t koff = (ks >> 2) * ATOM_BYTES + (ks & 3) * 32;
+                    mma_bf16(tmem_d, make_desc(a_base + PA[p] * PLANE_BYTES + koff), make_desc(b_base + PB[p] * PLANE_BYTES + koff), acc);
+                    acc = 1;
+                }
+            }
+            mma_commit(bar_a);
+        }
+        mbar_wait(bar_a, it & 1);
+        fence_after();
+        // ---- accumulator tile -> k_i ----
+        {
+            const int q = warp & 3, h = warp >> 2;
+            float *dst = kout + (row0 + q * 32 + lane) * D + h * 64;
+#pragma unroll
+            for (int cc = 0; cc < 2; ++cc) {
+                uint32_t r[32];
+                tmem_ld32(tmem_d + ((uint32_t)(q * 32) << 16) + h * 64 + cc * 32, r);
+#pragma unroll
+                for (int j = 0; j < 8; ++j)
+                    *reinterpret_cast<float4 *>(dst + cc * 32 + j * 4) =
+                        make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]), __uint_as_float(r[4 * j + 2]), __uint_as_float(r[4 * j + 3]));
+            }
+        }
+        fence_before();
+        __syncthreads();
+    }
+    if (warp == 0) {
+        fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem_d), "n"(TMEM_COLS) : "memory");
+    }
+}
+
+// ---- host ---------------------------------------------------------------------------------------------------------------------
+static float frand(uint64_t &s) {
+    s = s * 6364136223846793005ull + 1442695040888963407ull;
+    return (float)((s >> 40) & 0xFFFFFF) / 16777216.0f * 2.0f - 1.0f;
+}
+
+template <int NK>
+static void run(int rows, const float *d_y0, float *const *d_k, const float *cfh, const uint8_t *d_planes, float *d_out,
+                const std::vector<float> &h_y0, const std::vector<std::vector<float>> &h_k, const std::vector<float> &h_A,
+                int sms) {
+    KP kp{};
+    CF cf{};
+    for (int m = 0; m < NK; ++m) { kp.p[m] = d_k[m]; cf.c[m] = cfh[m]; }
+    const int ntiles = rows / TM;
+    CK(cudaFuncSetAttribute(k_linear_stage<NK>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    const int grid = ntiles < sms ? ntiles : sms;
+    CK(cudaMemset(d_out, 0xff, (size_t)rows * D * 4));
+    k_linear_stage<NK><<<grid, THREADS, SMEM_BYTES>>>(d_y0, kp, cf, d_planes, d_out, ntiles);
+    CK(cudaGetLastError());
+    CK(cudaDeviceSynchronize());
+    std::vector<float> out((size_t)rows * D);
+    CK(cudaMemcpy(out.data(), d_out, out.size() * 4, cudaMemcpyDeviceToHost));
+    // reference in double from the float32 stage value (same expression order, no fma)
+    double max_err = 0, sum_sq = 0, ref_sq = 0;
+    size_t bad = 0;
+    const int check_rows[] = {0, 1, 7, 8, 31, 32, 63, 64, 127, 128, 129, 255, rows / 2 + 5, rows - 129, rows - 128, rows - 1};
+    std::vector<int> rr(check_rows, check_rows + 16);
+    for (int r = 300; r < rows; r += 997) rr.push_back(r);
+    for (int r : rr) {
+        float y[D];
+        for (int c = 0; c < D; ++c) {
+            float v = h_y0[(size_t)r * D + c];
+            if (NK > 0) {
+                volatile float acc = h_k[0][(size_t)r * D + c] * cfh[0];
+                for (int m = 1; m < NK; ++m) { volatile float p = h_k[m][(size_t)r * D + c] * cfh[m]; acc = acc + p; }
+                v = v + acc;
+            }
+            y[c] = v;
+        }
+        for (int n = 0; n < D; ++n) {
+            double s = 0;
+            for (int c = 0; c < D; ++c) s += (double)y[c] * (double)h_A[(size_t)n * D + c];
+            const double e = fabs((double)out[(size_t)r * D + n] - s);
+            if (!(e < 1e-3)) ++bad;
+            if (e > max_err) max_err = e;
+            sum_sq += e * e;
+            ref_sq += s * s;
+        }
+    }
+    // timing
+    cudaEvent_t e0, e1;
+    CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+    for (int i = 0; i < 3; ++i) k_linear_stage<NK><<<grid, THREADS, SMEM_BYTES>>>(d_y0, kp, cf, d_planes, d_out, ntiles);
+    CK(cudaEventRecord(e0));
+    const int reps = 20;
+    for (int i = 0; i < reps; ++i) k_linear_stage<NK><<<grid, THREADS, SMEM_BYTES>>>(d_y0, kp, cf, d_planes, d_out, ntiles);
+    CK(cudaEventRecord(e1));
+    CK(cudaEventSynchronize(e1));
+    float ms;
+    CK(cudaEventElapsedTime(&ms, e0, e1));
+    const double us = ms * 1e3 / reps, bytes = (double)rows * D * 4 * (NK + 2);
+    printf("NK=%d rows=%d grid=%d: %.2f us  (%.0f GB/s on %d arrays)  rel rms err %.3e  max abs err %.3e  bad %zu of %zu\n", NK, rows,
+           grid, us, bytes / us * 1e-3, NK + 2, sqrt(sum_sq / ref_sq), max_err, bad, rr.size() * D);
+}
+
+int main(int argc, char **argv) {
+    const int rows = argc > 1 ? atoi(argv[1]) : 65536;
+    int sms;
+    CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0));
+    uint64_t seed = 12345;
+    std::vector<float> h_A((size_t)D * D), h_y0((size_t)rows * D);
+    for (auto &v : h_A) v = frand(seed) * 0.09f;
+    for (auto &v : h_y0) v = frand(seed);
+    std::vector<std::vector<float>> h_k(MAXK, std::vector<float>((size_t)rows * D));
+    for (auto &k : h_k) for (auto &v : k) v = frand(seed);
+    const float cfh[MAXK] = {0.0123f, -0.031f, 0.027f, 0.0451f, -0.0083f, 0.019f, 0.0071f};
+    float *d_A, *d_y0, *d_out, *d_k[MAXK];
+    uint8_t *d_planes;
+    CK(cudaMalloc(&d_A, h_A.size() * 4)); CK(cudaMalloc(&d_y0, h_y0.size() * 4)); CK(cudaMalloc(&d_out, h_y0.size() * 4));
+    CK(cudaMalloc(&d_planes, 3 * PLANE_BYTES));
+    CK(cudaMemcpy(d_A, h_A.data(), h_A.size() * 4, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(d_y0, h_y0.data(), h_y0.size() * 4, cudaMemcpyHostToDevice));
+    for (int m = 0; m < MAXK; ++m) {
+        CK(cudaMalloc(&d_k[m], h_y0.size() * 4));
+        CK(cudaMemcpy(d_k[m], h_k[m].data(), h_y0.size() * 4, cudaMemcpyHostToDevice));
+    }
+    k_split_weights<<<D, 32>>>(d_A, d_planes);
+    CK(cudaGetLastError());
+    CK(cudaDeviceSynchronize());
+    run<0>(rows, d_y0, d_k, cfh, d_planes, d_out, h_y0, h_k, h_A, sms);
+    run<1>(rows, d_y0, d_k, cfh, d_planes, d_out, h_y0, h_k, h_A, sms);
+    run<3>(rows, d_y0, d_k, cfh, d_planes, d_out, h_y0, h_k, h_A, sms);
+    run<5>(rows, d_y0, d_k, cfh, d_planes, d_out, h_y0, h_k, h_A, sms);
+    printf("done\n");
+    return 0;
+}
