@@ -305,6 +305,27 @@ int tdq_fixed_final_emit(int32_t dtype, int32_t which, void *y0, const void *k1,
 int tdq_lincomb(int32_t dtype, void *out, const void *base, const void *const *x, const double *coefs, int32_t n_terms,
                 size_t n, void *stream);
 
+/* ---- Stage fused with a LINEAR vector field f(t, y) = y W^T on the tensor cores (tdq_linear.cu) ----------------------------
+ * What rk_common.py:79-81 does with two kernels and a round trip of y_i through memory -- y_i = y0 + sum_j coef_ij k_j, then
+ * k_i = func(t_i, y_i) -- in one launch when func is `torchdiffeq_b200.LinearField` (float32 states [..., 128], W 128 x 128):
+ * y_i is formed in registers (same products, same order as tdq_stage_combine), split into three bfloat16 planes and multiplied
+ * on tcgen05 with float32 accumulation in tensor memory (BF16x9: float32-grade, rel. rms error 1e-7 against float64).
+ * tdq_linear_supported: 1 if (dtype, width) has a fused kernel.  tdq_linear_weights_bytes: size of the split weights.
+ * tdq_linear_prepare: W (row-major [width][width], W[n][k] = d k_n / d y_k, i.e. func = y @ W^T) -> split planes (once per solve).
+ * tdq_linear_apply: k_out = y W^T for n_rows rows, no control block (f0, tests).
+ * tdq_linear_stage: row `row` (0 .. S-1) of the tableau as tdq_stage_combine evaluates it, k_out = k_{row+1}; for the row
+ * that yields y1 of an FSAL tableau (row S-1) y1_out and err_out are written as tdq_stage_combine_final writes them
+ * (bitwise), otherwise they must be NULL.  y0 NULL / k[0] NULL: the control block's pointer table.  Rows of more than 8
+ * terms are rejected (the caller keeps the unfused pair for them).  No-op after halt, like every attempt kernel. */
+int tdq_linear_supported(int32_t dtype, int32_t width);
+size_t tdq_linear_weights_bytes(int32_t width);
+int tdq_linear_prepare(int32_t dtype, const void *weight, int32_t width, void *planes, void *stream);
+int tdq_linear_apply(int32_t dtype, const void *y, const void *planes, int32_t width, size_t n_rows, void *k_out,
+                     void *stream);
+int tdq_linear_stage(void *ctrl_dev, const tdq_tableau *tab, int32_t dtype, int32_t row, void *k_out, void *y1_out,
+                     void *err_out, const void *y0, const void *const *k, const void *planes, int32_t width, size_t n,
+                     void *stream);
+
 /* interp='cubic' (solvers.py:120-125, :166-173): for records r in [rec_lo, rec_hi) of one step
  * solution[out_idx[r]] = h00*y0 + (h10*dt)*f0 + h01*y1 + (h11*dt)*f1 with the four weights of record r at
  * coef_dev[4*r .. 4*r+4) (state dtype; the caller evaluates them in t's dtype like the reference and folds the

@@ -107,6 +107,15 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
+__device__ __forceinline__ void tmem_ld16_nowait(uint32_t taddr, uint32_t (&r)[16]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+                 "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+                   "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+                 : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
 // ---- the fused stage ----------------------------------------------------------------------------------------------------------
 constexpr int THREADS = 256;
 constexpr int TMEM_COLS = 128;
@@ -218,6 +227,375 @@ k_linear_stage(const float *__restrict__ y0, KP kp, CF cf, const uint8_t *__rest
     }
 }
 
+// ---- version 2: balanced 64-row units, K-atom split MMA issue, register double buffering with prefetch across tiles,
+//      accumulator tile transposed through shared memory for coalesced stores, optional last-row outputs (y1, error prefix) ----
+constexpr int SCRATCH_ROW = 272;                       // 64 floats + 16 bytes: conflict-free 128-bit writes down a column
+constexpr int SCRATCH_WARP = 32 * SCRATCH_ROW;
+
+template <int NK, int NPROD, bool FINAL>
+__global__ void __launch_bounds__(THREADS, 1)
+k_linear_stage2(const float *__restrict__ y0, KP kp, CF cr, CF ce, const uint8_t *__restrict__ wplanes,
+                float *__restrict__ kout, float *__restrict__ yout, float *__restrict__ eout, int n_rows) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint8_t *sB = smem, *sA = smem + 3 * PLANE_BYTES;
+    uint64_t *bar = reinterpret_cast<uint64_t *>(smem + 6 * PLANE_BYTES);
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + 6 * PLANE_BYTES + 16);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, half = lane >> 4, q = lane & 15;
+    constexpr int NKK = NK > 0 ? NK : 1;
+
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(smem_u32(tmem_slot)), "n"(TMEM_COLS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    if (tid == 32) {
+        mbar_init(smem_u32(bar), 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    for (int i = tid; i < 3 * PLANE_BYTES / 16; i += THREADS)
+        reinterpret_cast<uint4 *>(sB)[i] = reinterpret_cast<const uint4 *>(wplanes)[i];
+    fence_async_smem();
+    fence_before();
+    __syncthreads();
+    fence_after();
+    const uint32_t tmem_d = *tmem_slot;
+    const uint32_t a_base = smem_u32(sA), b_base = smem_u32(sB), bar_a = smem_u32(bar);
+
+    struct Regs { float4 a[2]; float4 k[2][NKK]; };
+    Regs R[2];
+    // batch b (0..3) of K-atom `atom`: rows (2b+u)*16 + 2*warp + half, u = 0,1; 16 lanes cover the 64 columns of the atom
+    auto load = [&](Regs &r, int row0, int rows_here, int atom, int b) {
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+            const int rr = (b * 2 + u) * 16 + warp * 2 + half;
+            if (rr < rows_here) {
+                const size_t off = (size_t)(row0 + rr) * D + atom * 64 + q * 4;
+                r.a[u] = __ldcs(reinterpret_cast<const float4 *>(y0 + off));
+#pragma unroll
+                for (int m = 0; m < NK; ++m) r.k[u][m] = __ldcs(reinterpret_cast<const float4 *>(kp.p[m] + off));
+            }
+        }
+    };
+    auto process = [&](Regs &r, int row0, int rows_here, int atom, int b) {
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+            const int rr = (b * 2 + u) * 16 + warp * 2 + half;
+            if (rr < rows_here) {
+                float4 y = r.a[u];
+                if (NK > 0) {
+                    float4 acc = make_float4(r.k[u][0].x * cr.c[0], r.k[u][0].y * cr.c[0], r.k[u][0].z * cr.c[0], r.k[u][0].w * cr.c[0]);
+#pragma unroll
+                    for (int m = 1; m < NK; ++m) {
+                        acc.x = acc.x + r.k[u][m].x * cr.c[m];
+                        acc.y = acc.y + r.k[u][m].y * cr.c[m];
+                        acc.z = acc.z + r.k[u][m].z * cr.c[m];
+                        acc.w = acc.w + r.k[u][m].w * cr.c[m];
+                    }
+                    y = make_float4(y.x + acc.x, y.y + acc.y, y.z + acc.z, y.w + acc.w);
+                    if (FINAL) {
+                        float4 e = make_float4(r.k[u][0].x * ce.c[0], r.k[u][0].y * ce.c[0], r.k[u][0].z * ce.c[0], r.k[u][0].w * ce.c[0]);
+#pragma unroll
+                        for (int m = 1; m < NK; ++m) {
+                            e.x = e.x + r.k[u][m].x * ce.c[m];
+                            e.y = e.y + r.k[u][m].y * ce.c[m];
+                            e.z = e.z + r.k[u][m].z * ce.c[m];
+                            e.w = e.w + r.k[u][m].w * ce.c[m];
+                        }
+                        const size_t off = (size_t)(row0 + rr) * D + atom * 64 + q * 4;
+                        *reinterpret_cast<float4 *>(yout + off) = y;
+                        *reinterpret_cast<float4 *>(eout + off) = e;
+                    }
+                }
+                store_split(sA, rr, atom * 16 + q, y);
+            }
+        }
+    };
+    auto issue = [&](int atom, bool first) {
+        constexpr int PA9[9] = {2, 2, 1, 2, 0, 1, 1, 0, 0}, PB9[9] = {2, 1, 2, 0, 2, 1, 0, 1, 0};
+        constexpr int PA6[6] = {2, 0, 1, 1, 0, 0}, PB6[6] = {0, 2, 1, 0, 1, 0};
+        uint32_t acc = first ? 0u : 1u;
+#pragma unroll
+        for (int p = 0; p < NPROD; ++p) {
+            const int pa = NPROD == 9 ? PA9[p] : PA6[p], pb = NPROD == 9 ? PB9[p] : PB6[p];
+#pragma unroll
+            for (int ks = 0; ks < 4; ++ks) {
+                const uint32_t koff = atom * ATOM_BYTES + ks * 32;
+                mma_bf16(tmem_d, make_desc(a_base + pa * PLANE_BYTES + koff), make_desc(b_base + pb * PLANE_BYTES + koff), acc);
+                acc = 1;
+            }
+        }
+    };
+
+    const int units = (n_rows + 63) / 64;
+    int u = (int)((long long)blockIdx.x * units / gridDim.x);
+    const int u_end = (int)((long long)(blockIdx.x + 1) * units / gridDim.x);
+    uint32_t it = 0;
+    if (u < u_end) {
+        const int nu = u_end - u < 2 ? u_end - u : 2;
+        const int rows_here = min(nu * 64, n_rows - u * 64);
+        load(R[0], u * 64, rows_here, 0, 0);
+    }
+    while (u < u_end) {
+        const int nu = u_end - u < 2 ? u_end - u : 2;
+        const int row0 = u * 64, rows_here = min(nu * 64, n_rows - row0);
+        const int un = u + nu;
+        const bool has_next = un < u_end;
+        const int nnu = u_end - un < 2 ? u_end - un : 2;
+        const int nrow0 = un * 64, nrows_here = has_next ? min(nnu * 64, n_rows - nrow0) : 0;
+#pragma unroll
+        for (int s = 0; s < 8; ++s) {
+            if (s < 7) load(R[(s + 1) & 1], row0, rows_here, (s + 1) >> 2, (s + 1) & 3);
+            else if (has_next) load(R[0], nrow0, nrows_here, 0, 0);
+            process(R[s & 1], row0, rows_here, s >> 2, s & 3);
+            if (s == 3 || s == 7) {
+                fence_async_smem();
+                fence_before();
+                __syncthreads();
+                if (tid == 0) {
+                    fence_after();
+                    issue(s >> 2, s == 3);
+                    if (s == 7) mma_commit(bar_a);
+                }
+            }
+        }
+        mbar_wait(bar_a, it & 1);
+        fence_after();
+        {
+            const int qw = warp & 3, h = warp >> 2;
+            if (qw * 32 < rows_here) {
+                uint8_t *scratch = sA + warp * SCRATCH_WARP;
+#pragma unroll
+                for (int cc = 0; cc < 2; ++cc) {
+                    uint32_t r[32];
+                    tmem_ld32(tmem_d + ((uint32_t)(qw * 32) << 16) + h * 64 + cc * 32, r);
+#pragma unroll
+                    for (int j = 0; j < 8; ++j)
+                        *reinterpret_cast<uint4 *>(scratch + lane * SCRATCH_ROW + (cc * 32 + j * 4) * 4) =
+                            make_uint4(r[4 * j], r[4 * j + 1], r[4 * j + 2], r[4 * j + 3]);
+                }
+                __syncwarp();
+#pragma unroll
+                for (int i = 0; i < 16; ++i) {
+                    const int rr = 2 * i + half, grow = qw * 32 + rr;
+                    const uint4 v = *reinterpret_cast<const uint4 *>(scratch + rr * SCRATCH_ROW + q * 16);
+                    if (grow < rows_here) *reinterpret_cast<uint4 *>(kout + (size_t)(row0 + grow) * D + h * 64 + q * 4) = v;
+                }
+            }
+        }
+        fence_before();
+        __syncthreads();
+        u = un;
+        ++it;
+    }
+    if (warp == 0) {
+        fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem_d), "n"(TMEM_COLS) : "memory");
+    }
+}
+
+// ---- version 3: warp specialised; the WEIGHTS are the stationary A operand in tensor memory (M = 128 output features),
+//      the stage values are the B operand (N = 128 rows) in a two-deep shared-memory ring; the accumulator comes out
+//      transposed (lane = feature, column = row), so the epilogue stores are 128-byte coalesced without staging. ----
+constexpr int V3_THREADS = 384;
+constexpr int STAGE_BYTES = 3 * PLANE_BYTES;
+constexpr int V3_SMEM = 2 * STAGE_BYTES + 1024 + 128;
+constexpr int V3_TMEM_COLS = 512;
+constexpr int COL_BIG = 0, COL_SMALL = 128, COL_W = 256;      // tensor-memory columns
+
+// weights -> [plane][feature n][64 x u32] (bf16 pairs along K): what thread n stores into its tensor-memory lane
+__global__ void k_split_weights_t(const float *__restrict__ A, uint32_t *__restrict__ wt) {
+    const int n = blockIdx.x, c = threadIdx.x;            // 128 blocks x 64 threads
+    uint32_t h, m, l;
+    split2(A[(size_t)n * D + 2 * c], A[(size_t)n * D + 2 * c + 1], h, m, l);
+    wt[(0 * D + n) * 64 + c] = h;
+    wt[(1 * D + n) * 64 + c] = m;
+    wt[(2 * D + n) * 64 + c] = l;
+}
+
+__device__ __forceinline__ void mma_bf16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t db, uint32_t accumulate) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                 "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}\n"
+                 :: "r"(tmem_d), "r"(tmem_a), "l"(db), "r"(IDESC), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.shared::cta.b64 st, [%0];\n\t}\n" :: "r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&r)[32]) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+                 "{%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31,%32};"
+                 :: "r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]),
+                    "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]),
+                    "r"(r[16]), "r"(r[17]), "r"(r[18]), "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]),
+                    "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31]) : "memory");
+}
+
+template <int NK, bool FINAL>
+__global__ void __launch_bounds__(V3_THREADS, 1)
+k_linear_stage3(const float *__restrict__ y0, KP kp, CF cr, CF ce, const uint32_t *__restrict__ wt,
+                float *__restrict__ kout, float *__restrict__ yout, float *__restrict__ eout, int n_rows) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint64_t *bars = reinterpret_cast<uint64_t *>(smem + 2 * STAGE_BYTES);   // full[2], empty[2], accf, acce, wready
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + 2 * STAGE_BYTES + 64);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, wg = warp >> 2;
+    const uint32_t bar0 = smem_u32(bars);
+    const uint32_t b_full[2] = {bar0, bar0 + 8}, b_empty[2] = {bar0 + 16, bar0 + 24};
+    const uint32_t b_accf = bar0 + 32, b_acce = bar0 + 40, b_wready = bar0 + 48;
+
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(smem_u32(tmem_slot)), "n"(V3_TMEM_COLS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    if (tid == 32) {
+        mbar_init(b_full[0], 256); mbar_init(b_full[1], 256);
+        mbar_init(b_empty[0], 1); mbar_init(b_empty[1], 1);
+        mbar_init(b_accf, 1); mbar_init(b_acce, 128); mbar_init(b_wready, 128);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    fence_before();
+    __syncthreads();
+    fence_after();
+    const uint32_t tmem = *tmem_slot;
+
+    const int units = (n_rows + 63) / 64;
+    const int u_begin = (int)((long long)blockIdx.x * units / gridDim.x);
+    const int u_end = (int)((long long)(blockIdx.x + 1) * units / gridDim.x);
+
+    if (wg < 2) {
+        // ================= producers: stage combination, split, operand planes =================
+        constexpr int NKK = NK > 0 ? NK : 1;
+        uint32_t it = 0;
+        for (int u = u_begin; u < u_end; ++it) {
+            const int nu = u_end - u < 2 ? u_end - u : 2;
+            const int row0 = u * 64, rows_here = min(nu * 64, n_rows - row0);
+            u += nu;
+            const int s = it & 1;
+            uint8_t *sY = smem + s * STAGE_BYTES;
+            mbar_wait(b_empty[s], ((it >> 1) & 1) ^ 1);
+#pragma unroll 1
+            for (int i = 0; i < 4; ++i) {
+                if ((4 * i) * 8 >= rows_here) break;
+                float4 a[4], kv[4][NKK];
+#pragma unroll
+                for (int uu = 0; uu < 4; ++uu) {
+                    const int r = warp + 8 * (4 * i + uu);
+                    if (r < rows_here) {
+                        const size_t off = (size_t)(row0 + r) * D + lane * 4;
+                        a[uu] = __ldcs(reinterpret_cast<const float4 *>(y0 + off));
+#pragma unroll
+                        for (int m = 0; m < NK; ++m) kv[uu][m] = __ldcs(reinterpret_cast<const float4 *>(kp.p[m] + off));
+                    }
+                }
+#pragma unroll
+                for (int uu = 0; uu < 4; ++uu) {
+                    const int r = warp + 8 * (4 * i + uu);
+                    if (r < rows_here) {
+                        float4 y = a[uu];
+                        if (NK > 0) {
+                            float4 acc = make_float4(kv[uu][0].x * cr.c[0], kv[uu][0].y * cr.c[0], kv[uu][0].z * cr.c[0], kv[uu][0].w * cr.c[0]);
+#pragma unroll
+                            for (int m = 1; m < NK; ++m) {
+                                acc.x = acc.x + kv[uu][m].x * cr.c[m];
+                                acc.y = acc.y + kv[uu][m].y * cr.c[m];
+                                acc.z = acc.z + kv[uu][m].z * cr.c[m];
+                                acc.w = acc.w + kv[uu][m].w * cr.c[m];
+                            }
+                            y = make_float4(y.x + acc.x, y.y + acc.y, y.z + acc.z, y.w + acc.w);
+                            if (FINAL) {
+                                float4 e = make_float4(kv[uu][0].x * ce.c[0], kv[uu][0].y * ce.c[0], kv[uu][0].z * ce.c[0], kv[uu][0].w * ce.c[0]);
+#pragma unroll
+                                for (int m = 1; m < NK; ++m) {
+                                    e.x = e.x + kv[uu][m].x * ce.c[m];
+                                    e.y = e.y + kv[uu][m].y * ce.c[m];
+                                    e.z = e.z + kv[uu][m].z * ce.c[m];
+                                    e.w = e.w + kv[uu][m].w * ce.c[m];
+                                }
+                                const size_t off = (size_t)(row0 + r) * D + lane * 4;
+                                *reinterpret_cast<float4 *>(yout + off) = y;
+                                *reinterpret_cast<float4 *>(eout + off) = e;
+                            }
+                        }
+                        store_split(sY, r, lane, y);
+                    }
+                }
+            }
+            fence_async_smem();
+            mbar_arrive(b_full[s]);
+        }
+    } else if (wg == 2) {
+        // ================= epilogue warps: weights into tensor memory once, then accumulator tiles -> k =================
+        const int e = warp & 3, f = e * 32 + lane;                // this thread's tensor-memory lane = output feature
+        const uint32_t lane_base = tmem + ((uint32_t)(e * 32) << 16);
+#pragma unroll 1
+        for (int pl = 0; pl < 3; ++pl) {
+#pragma unroll 1
+            for (int c0 = 0; c0 < 64; c0 += 32) {
+                uint32_t r[32];
+                const uint4 *src = reinterpret_cast<const uint4 *>(wt + ((size_t)pl * D + f) * 64 + c0);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const uint4 v = src[j];
+                    r[4 * j] = v.x; r[4 * j + 1] = v.y; r[4 * j + 2] = v.z; r[4 * j + 3] = v.w;
+                }
+                tmem_st32(lane_base + COL_W + pl * 64 + c0, r);
+            }
+        }
+        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+        uint32_t it = 0;
+        for (int u = u_begin; u < u_end; ++it) {
+            const int nu = u_end - u < 2 ? u_end - u : 2;
+            const int row0 = u * 64, rows_here = min(nu * 64, n_rows - row0);
+            u += nu;
+            // the previous tile's accumulators are drained (and, the first time, the weights are in tensor memory)
+            fence_before();
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+            if (warp == 8 && lane == 0) {
+                // ---- MMA issue: one thread ----
+                const int s = it & 1;
+                const uint32_t y_base = smem_u32(smem + s * STAGE_BYTES);
+                mbar_wait(b_full[s], (it >> 1) & 1);
+                fence_after();
+                // weights plane pw (A, tensor memory) x stage-value plane py (B, shared memory); eight small products
+                // in ascending magnitude into one accumulator, hi x hi into the other
+                constexpr int PW[9] = {2, 2, 1, 1, 2, 0, 1, 0, 0}, PY[9] = {2, 1, 2, 1, 0, 2, 0, 1, 0};
+#pragma unroll
+                for (int p = 0; p < 9; ++p) {
+                    const uint32_t dcol = tmem + (p == 8 ? COL_BIG : COL_SMALL);
+#pragma unroll
+                    for (int ks = 0; ks < 8; ++ks) {
+                        const uint32_t koff = (ks >> 2) * ATOM_BYTES + (ks & 3) * 32;
+                        mma_bf16_ts(dcol, tmem + COL_W + PW[p] * 64 + ks * 8, make_desc(y_base + PY[p] * PLANE_BYTES + koff),
+                                    (p == 0 || p == 8) && ks == 0 ? 0u : 1u);
+                    }
+                }
+                mma_commit(b_empty[s]);
+                mma_commit(b_accf);
+            }
+            __syncwarp();
+            mbar_wait(b_accf, it & 1);
+            fence_after();
+#pragma unroll 1
+            for (int cc = 0; cc < 8; ++cc) {
+                if (cc * 16 >= rows_here) break;
+                uint32_t big[16], small[16];
+                tmem_ld16_nowait(lane_base + COL_SMALL + cc * 16, small);
+                tmem_ld16_nowait(lane_base + COL_BIG + cc * 16, big);
+                tmem_ld_wait();
+                float *dst = kout + (size_t)(row0 + cc * 16) * D + f;
+#pragma unroll
+                for (int j = 0; j < 16; ++j)
+                    if (cc * 16 + j < rows_here) dst[(size_t)j * D] = __uint_as_float(small[j]) + __uint_as_float(big[j]);
+            }
+        }
+    }
+    fence_before();
+    __syncthreads();
+    if (warp == 0) {
+        fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem), "n"(V3_TMEM_COLS) : "memory");
+    }
+}
+
 // ---- host ---------------------------------------------------------------------------------------------------------------------
 static float frand(uint64_t &s) {
     s = s * 6364136223846793005ull + 1442695040888963407ull;
@@ -283,6 +661,81 @@ static void run(int rows, const float *d_y0, float *const *d_k, const float *cfh
            grid, us, bytes / us * 1e-3, NK + 2, sqrt(sum_sq / ref_sq), max_err, bad, rr.size() * D);
 }
 
+static const uint32_t *g_wt = nullptr;
+template <int NK, int NPROD, bool FINAL, int VER = 2>
+static void run2(int rows, const float *d_y0, float *const *d_k, const float *cfh, const float *ceh, const uint8_t *d_planes,
+                 float *d_out, float *d_yout, float *d_eout, const std::vector<float> &h_y0,
+                 const std::vector<std::vector<float>> &h_k, const std::vector<float> &h_A, int sms) {
+    KP kp{};
+    CF cr{}, ce{};
+    for (int m = 0; m < NK; ++m) { kp.p[m] = d_k[m]; cr.c[m] = cfh[m]; ce.c[m] = ceh[m]; }
+    const int units = (rows + 63) / 64;
+    const int grid = units / 2 < sms ? (units + 1) / 2 : sms;
+    if (VER == 2) CK(cudaFuncSetAttribute(k_linear_stage2<NK, NPROD, FINAL>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    else CK(cudaFuncSetAttribute(k_linear_stage3<NK, FINAL>, cudaFuncAttributeMaxDynamicSharedMemorySize, V3_SMEM));
+    const uint32_t *wt = g_wt;
+    auto launch = [&]() {
+        if (VER == 2) k_linear_stage2<NK, NPROD, FINAL><<<grid, THREADS, SMEM_BYTES>>>(d_y0, kp, cr, ce, d_planes, d_out, d_yout, d_eout, rows);
+        else k_linear_stage3<NK, FINAL><<<grid, V3_THREADS, V3_SMEM>>>(d_y0, kp, cr, ce, wt, d_out, d_yout, d_eout, rows);
+    };
+    CK(cudaMemset(d_out, 0xff, (size_t)rows * D * 4));
+    CK(cudaMemset(d_yout, 0xff, (size_t)rows * D * 4));
+    CK(cudaMemset(d_eout, 0xff, (size_t)rows * D * 4));
+    launch();
+    CK(cudaGetLastError());
+    CK(cudaDeviceSynchronize());
+    std::vector<float> out((size_t)rows * D), yo((size_t)rows * D), eo((size_t)rows * D);
+    CK(cudaMemcpy(out.data(), d_out, out.size() * 4, cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(yo.data(), d_yout, out.size() * 4, cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(eo.data(), d_eout, out.size() * 4, cudaMemcpyDeviceToHost));
+    double max_err = 0, sum_sq = 0, ref_sq = 0;
+    size_t bad = 0, ybad = 0;
+    std::vector<int> rr = {0, 1, 7, 8, 31, 32, 63, 64, 65, 127, 128, 129, 255, rows / 2 + 5, rows - 129, rows - 128, rows - 65, rows - 64, rows - 1};
+    for (int r = 300; r < rows; r += 499) rr.push_back(r);
+    for (int r : rr) {
+        if (r < 0 || r >= rows) continue;
+        float y[D];
+        for (int c = 0; c < D; ++c) {
+            float v = h_y0[(size_t)r * D + c];
+            if (NK > 0) {
+                volatile float acc = h_k[0][(size_t)r * D + c] * cfh[0];
+                volatile float ee = h_k[0][(size_t)r * D + c] * ceh[0];
+                for (int m = 1; m < NK; ++m) {
+                    volatile float p = h_k[m][(size_t)r * D + c] * cfh[m]; acc = acc + p;
+                    volatile float pe = h_k[m][(size_t)r * D + c] * ceh[m]; ee = ee + pe;
+                }
+                v = v + acc;
+                if (FINAL && (yo[(size_t)r * D + c] != v || eo[(size_t)r * D + c] != ee)) ++ybad;
+            }
+            y[c] = v;
+        }
+        for (int n = 0; n < D; ++n) {
+            double s = 0;
+            for (int c = 0; c < D; ++c) s += (double)y[c] * (double)h_A[(size_t)n * D + c];
+            const double e = fabs((double)out[(size_t)r * D + n] - s);
+            if (!(e < 1e-3)) ++bad;
+            if (e > max_err) max_err = e;
+            sum_sq += e * e;
+            ref_sq += s * s;
+        }
+    }
+    cudaEvent_t e0, e1;
+    CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+    for (int i = 0; i < 3; ++i) launch();
+    CK(cudaEventRecord(e0));
+    const int reps = 20;
+    for (int i = 0; i < reps; ++i) launch();
+    CK(cudaEventRecord(e1));
+    CK(cudaEventSynchronize(e1));
+    CK(cudaGetLastError());
+    float ms;
+    CK(cudaEventElapsedTime(&ms, e0, e1));
+    const int arrays = NK + 2 + (FINAL ? 2 : 0);
+    const double us = ms * 1e3 / reps, bytes = (double)rows * D * 4 * arrays;
+    printf("v%d NK=%d NPROD=%d FINAL=%d rows=%d grid=%d: %.2f us  (%.0f GB/s on %d arrays)  rel rms err %.3e  max abs err %.3e  bad %zu  y/err mismatches %zu\n",
+           VER, NK, NPROD, (int)FINAL, rows, grid, us, bytes / us * 1e-3, arrays, sqrt(sum_sq / ref_sq), max_err, bad, ybad);
+}
+
 int main(int argc, char **argv) {
     const int rows = argc > 1 ? atoi(argv[1]) : 65536;
     int sms;
@@ -311,6 +764,28 @@ int main(int argc, char **argv) {
     run<1>(rows, d_y0, d_k, cfh, d_planes, d_out, h_y0, h_k, h_A, sms);
     run<3>(rows, d_y0, d_k, cfh, d_planes, d_out, h_y0, h_k, h_A, sms);
     run<5>(rows, d_y0, d_k, cfh, d_planes, d_out, h_y0, h_k, h_A, sms);
+    float *d_yout, *d_eout;
+    CK(cudaMalloc(&d_yout, h_y0.size() * 4)); CK(cudaMalloc(&d_eout, h_y0.size() * 4));
+    const float ceh[MAXK] = {0.0012f, 0.0005f, -0.0034f, 0.0021f, -0.0018f, 0.0041f, -0.0009f};
+    uint32_t *d_wt;
+    CK(cudaMalloc(&d_wt, 3 * D * 64 * 4));
+    k_split_weights_t<<<D, 64>>>(d_A, d_wt);
+    CK(cudaGetLastError());
+    CK(cudaDeviceSynchronize());
+    g_wt = d_wt;
+#define R3(NK, F) run2<NK, 9, F, 3>(rows, d_y0, d_k, cfh, ceh, d_planes, d_out, d_yout, d_eout, h_y0, h_k, h_A, sms)
+    if (argc > 2) {
+        R3(0, false); R3(1, false); R3(2, false); R3(3, false); R3(4, false); R3(5, false); R3(5, true);
+        run2<5, 9, true, 3>(rows - 40, d_y0, d_k, cfh, ceh, d_planes, d_out, d_yout, d_eout, h_y0, h_k, h_A, sms);
+        run2<3, 9, false, 3>(1000, d_y0, d_k, cfh, ceh, d_planes, d_out, d_yout, d_eout, h_y0, h_k, h_A, sms);
+        printf("done v3\n");
+        return 0;
+    }
+#define R2(NK, NP, F) run2<NK, NP, F>(rows, d_y0, d_k, cfh, ceh, d_planes, d_out, d_yout, d_eout, h_y0, h_k, h_A, sms)
+    R2(0, 9, false); R2(1, 9, false); R2(2, 9, false); R2(3, 9, false); R2(4, 9, false); R2(5, 9, false); R2(5, 9, true);
+    R2(0, 6, false); R2(3, 6, false); R2(5, 6, false); R2(5, 6, true);
+    run2<5, 9, true>(rows - 40, d_y0, d_k, cfh, ceh, d_planes, d_out, d_yout, d_eout, h_y0, h_k, h_A, sms);
+    run2<3, 9, false>(1000, d_y0, d_k, cfh, ceh, d_planes, d_out, d_yout, d_eout, h_y0, h_k, h_A, sms);
     printf("done\n");
     return 0;
 }

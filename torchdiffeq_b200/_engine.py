@@ -273,6 +273,7 @@ class AdaptiveEngine:
         self._loop_handle = 0
         self._loop_failed = False
         self._always_copy = False        # set when func is seen to reuse its output buffer (see _call_fn)
+        self.linear = None               # set_linear(): every stage fused with a linear field (csrc/tdq_linear.cu)
         self.capture_in_solve = True     # False: only a prime()d graph is used (solves run inside autograd backward)
         self.n_attempts = 0              # attempts that did work (from the mailbox counters)
         self.nfe = 0                     # func evaluations issued by the host
@@ -321,6 +322,38 @@ class AdaptiveEngine:
         if self.post_fn is not None:
             self.post_fn(buf)
         return buf
+
+    def set_linear(self, weight):
+        """Fuse the stage combination with func = y @ weight^T (torchdiffeq_b200.LinearField): tdq_linear_stage replaces
+        tdq_stage_combine + the torch call for every row (rk_common.py:79-81 in one launch; csrc/tdq_linear.cu).
+        Returns False (and changes nothing) if a row of the tableau has more terms than the fused kernel takes."""
+        width, S = int(weight.shape[0]), self.S
+        if self.pieces is not None or self.post_fn is not None or self.n % width:
+            return False
+        beta, c_err = self.tab.beta, self.tab.c_err
+        for i in range(S):
+            used = {j for j in range(i + 1) if beta[i][j] != 0.0}
+            if self.fsal and i == S - 1:
+                used |= {j for j in range(S) if c_err[j] != 0.0}
+            if not 1 <= len(used) <= 8:
+                return False
+        planes = torch.empty(int(self.lib.tdq_linear_weights_bytes(width)), dtype=torch.uint8, device=self.device)
+        self.linear = dict(weight=weight, width=width, planes=planes,
+                           k=[torch.zeros(self.n, dtype=self.dtype, device=self.device) for _ in range(S)])
+        self._drop_graph()
+        return True
+
+    def _eval(self, t, y, slot, dst=None):
+        """func(t, y) before the first attempt (f0, the initial step's probe): the fused field's own kernel when there is
+        one, so that a solve uses one arithmetic for every evaluation."""
+        if self.linear is None:
+            return self._call_fn(t, y, slot, dst=dst)
+        self.nfe += 1
+        out = dst if dst is not None else self._slot(slot)
+        L = self.linear
+        self._launch(self.lib.tdq_linear_apply(self.dt_code, y.data_ptr(), L["planes"].data_ptr(), L["width"],
+                                               self.n // L["width"], out.data_ptr(), _stream()))
+        return out
 
     @property
     def y0w(self):
@@ -382,7 +415,20 @@ class AdaptiveEngine:
         S = self.S
         k = [None] * (S + 1)             # k[0] = NULL: the kernels read k_0 (and y0) through the pointer table
         keep = []
-        for i in range(S):
+        if self.linear is not None:
+            # combination + evaluation of every row in one tcgen05 launch (csrc/tdq_linear.cu); the FSAL row also writes
+            # y1 and the error-sum prefix exactly as tdq_stage_combine_final does
+            L = self.linear
+            for i in range(S):
+                last = i == S - 1 and self.fsal
+                out = L["k"][i]
+                self._launch(lib.tdq_linear_stage(ctrl, tab, dc, i, out.data_ptr(),
+                                                  self.y1.data_ptr() if last else None,
+                                                  self.errp.data_ptr() if last else None, None, _lib.ptr_array(k),
+                                                  L["planes"].data_ptr(), L["width"], self.n, st))
+                self.nfe += 1
+                k[i + 1] = out.data_ptr()
+        for i in range(S if self.linear is None else 0):
             if i == S - 1 and self.fsal:
                 # the row that yields y1, fused with the available prefix of the error estimate (rk_common.py:83-89)
                 out = self.y1
@@ -538,9 +584,12 @@ class AdaptiveEngine:
             self._launch(lib.tdq_ctrl_set_step_t(self.ctrl.data_ptr(), self.step_t.data_ptr(),
                                                int(self.step_t.numel()), st))
         dc, ctrl = self.dt_code, self.ctrl.data_ptr()
+        if self.linear is not None:                                   # the weight may have changed since the last solve
+            L = self.linear
+            self._launch(lib.tdq_linear_prepare(dc, L["weight"].data_ptr(), L["width"], L["planes"].data_ptr(), st))
 
         # _before_integrate: f0 and the initial step (rk_common.py:213-221, misc.py:36-77)
-        f0 = self._call_fn(self.taux[0], self.ybuf[0], 0, dst=self.kbuf[0])
+        f0 = self._eval(self.taux[0], self.ybuf[0], 0, dst=self.kbuf[0])
         if f0.data_ptr() != self.kbuf[0].data_ptr():
             self.kbuf[0].copy_(f0)
         del f0
@@ -555,7 +604,7 @@ class AdaptiveEngine:
                 self._launch(lib.tdq_initial_step_h0(ctrl, dc, self.dsum[0].data_ptr(), self.dsum[1].data_ptr(),
                                                    self.seg_counts.data_ptr(), self.n_seg, st))
                 self._launch(lib.tdq_initial_step_probe(ctrl, dc, self.ytmp.data_ptr(), None, None, self.n, st))
-                f1 = self._call_fn(self.taux[1], self.ytmp, 1)
+                f1 = self._eval(self.taux[1], self.ytmp, 1)
                 self._sumsq(f1, self.kbuf[0], self.dsum[2])
                 del f1
                 self._launch(lib.tdq_initial_step_finish(ctrl, dc, self.dsum[2].data_ptr(),

@@ -32,7 +32,7 @@ _ADAPTIVE_OPTIONS = {"min_step", "max_step", "first_step", "step_t", "jump_t", "
                      "max_num_steps", "dtype", "norm"}
 _FIXED_OPTIONS = {"step_size", "grid_constructor", "interp", "perturb", "norm"}
 _ADAMS_OPTIONS = _FIXED_OPTIONS | {"max_iters", "max_order"}
-_OUR_OPTIONS = {"graph", "run_ahead", "process_group", "cache", "exchange", "device_loop"}
+_OUR_OPTIONS = {"graph", "run_ahead", "process_group", "cache", "exchange", "device_loop", "fused_linear"}
 
 
 def _rms_norm(tensor):
@@ -281,7 +281,7 @@ def _make_adaptive_engine(p, method, rtol, atol, rtol_vec, atol_vec, options, fn
             except Exception as e:      # e.g. CUDA IPC not permitted in this container: keep the NCCL all-reduce
                 warnings.warn("torchdiffeq_b200: NVLink peer exchange unavailable (%s: %s); using the process "
                               "group's all-reduce" % (type(e).__name__, e))
-    return AdaptiveEngine(
+    eng = AdaptiveEngine(
         fn if fn is not None else p.fn, n if n is not None else p.n, p.dtype, p.device, method,
         rtol=rtol, atol=atol, rtol_vec=rtol_vec, atol_vec=atol_vec,
         segs=segs, t_sign=p.t_sign, pieces=pieces,
@@ -293,6 +293,13 @@ def _make_adaptive_engine(p, method, rtol, atol, rtol_vec, atol_vec, options, fn
         reduce_fn=reduce_fn, n_global=n_global, seg_counts_global=seg_counts_global, agree_fn=agree_fn,
         exchange=exchange, callbacks=callbacks, keep_interp=keep_interp, device_loop=o.get("device_loop", "auto"),
         post_fn=post_fn)
+    if fn is None and not p.is_tuple and o.get("fused_linear", True):
+        # func is a torchdiffeq_b200.LinearField on a float32 [..., 128] state: stages run as one tcgen05 kernel each
+        from .fields import fusable
+        w = fusable(getattr(p, "original_func", None), tuple(p.shape), p.dtype, p.device, eng.lib)
+        if w is not None:
+            eng.set_linear(w)
+    return eng
 
 
 # ---- engine cache -------------------------------------------------------------------------------
@@ -686,7 +693,8 @@ def _odeint_backprop(p, func, y0, t, params, _stats):
     if eng is not None:
         _LAST_STATS.clear()
         _LAST_STATS.update(nfe=eng.nfe, launches=getattr(eng, "launches", 0), attempts=getattr(eng, "n_attempts", None),
-                           n_accept=getattr(eng, "n_accept", None), n_reject=getattr(eng, "n_reject", None))
+                           n_accept=getattr(eng, "n_accept", None), n_reject=getattr(eng, "n_reject", None),
+                       fused_linear=getattr(eng, "linear", None) is not None)
         if _stats is not None:
             _stats.update(_LAST_STATS)
     return _unflatten(p, sol)
@@ -728,7 +736,8 @@ def odeint(func, y0, t, *, rtol=1e-7, atol=1e-9, method=None, options=None, even
         ss.publish(sol)
     _LAST_STATS.clear()
     _LAST_STATS.update(nfe=eng.nfe, launches=getattr(eng, "launches", 0), attempts=getattr(eng, "n_attempts", None),
-                       n_accept=getattr(eng, "n_accept", None), n_reject=getattr(eng, "n_reject", None))
+                       n_accept=getattr(eng, "n_accept", None), n_reject=getattr(eng, "n_reject", None),
+                       fused_linear=getattr(eng, "linear", None) is not None)
     if _stats is not None:               # private: solver counters for bench.py and the tests
         _stats["nfe"] = eng.nfe
         _stats["launches"] = _stats.get("launches", 0) + getattr(eng, "launches", 0)
