@@ -9,11 +9,16 @@ N > 1 (torchrun, one rank per GPU): every rank integrates its own 65536 trajecto
 configs[4] at N=8) and the ranks share one scalar all-reduce per attempt so that all take the common
 dt of the unsharded problem.
 
+The vector field is `torchdiffeq_b200.LinearField(A)` -- an nn.Module with forward(t, y) = y @ A^T that the reference runs
+unchanged -- so every Runge-Kutta stage (combination + field evaluation) is ONE tcgen05 kernel (csrc/tdq_linear.cu).
+`--generic` keeps func an opaque torch module (the path any other func takes: k_combine + the user's kernels); the default
+run times that path too and reports it as `generic_path`.
+
 Prints ONE JSON line (rank 0).  `value` is measured with inputs resident in HBM; `e2e` goes through the
 public API with pinned HOST buffers (H2D of y0 and D2H of y(t_end) inside the timed region);
-`roofline` is the stage-combine kernel's algorithmic bytes / its CUDA-event time against the measured
-HBM peak; `cpu_baseline` is the CPU oracle (a port of the reference's algorithm, oracle/) on a bounded
-sample.  --impl reference times that CPU port alone on the host cores.
+`roofline` is the dominant kernel group's algorithmic bytes / its CUDA-event time against the measured
+HBM peak; `cpu_baseline` is the unmodified reference (baseline/_ref; the CPU oracle only if it did not travel) on a bounded
+sample.  --impl reference times that CPU implementation alone on the host cores.
 """
 import argparse
 import ctypes as C
@@ -36,11 +41,16 @@ RTOL, ATOL = 1e-5, 1e-7
 METRIC = "trajectories/sec (dopri5, batch=65536 dim=128)"
 
 
-def make_problem(device, batch, rank=0, world=1):
+def make_problem(device, batch, rank=0, world=1, fused=False):
     """The workload: ONE seeded batch of `batch * world` trajectories (y0 = randn, generator
-    seed 1); rank r owns rows [r*batch, (r+1)*batch).  Returns (func, this rank's rows, t, the whole batch)."""
+    seed 1); rank r owns rows [r*batch, (r+1)*batch).  Returns (func, this rank's rows, t, the whole batch).
+    fused: func is torchdiffeq_b200.LinearField(A) (same matrix, same mathematics: y @ A^T) instead of the plain module."""
     import problems as P
-    f = P.BatchedLinear(DIM, torch.float32).to(device)
+    if fused:
+        import torchdiffeq_b200 as tdq
+        f = tdq.LinearField(P.skew_matrix(DIM, torch.float32).to(device))
+    else:
+        f = P.BatchedLinear(DIM, torch.float32).to(device)
     g = torch.Generator().manual_seed(1)
     y_all = torch.randn(batch * world, DIM, generator=g)
     y0 = y_all[rank * batch:(rank + 1) * batch].contiguous()
@@ -99,6 +109,10 @@ class ClockSampler:
 TRAFFIC_STATIC = {"bytes": 928.4e6, "source": "static: dram__bytes_read+write of the six launches from ncu --set full captures "
                                                 "(profiles/r2_ncu_full_summary.csv for k_combine<5> 209.3 MB and k_combine_final 216.5 MB, "
                                                 "profiles/r1_ncu_full_summary.csv for rows NK=1..4); not measured by this run"}
+# the six fused launches (k_linear_stage) of one attempt: filled from the ncu --set full capture under profiles/ (see there)
+TRAFFIC_FUSED = {"bytes": 946.1e6, "source": "static: dram__bytes_read+write of the six k_linear_stage launches of one attempt, ncu --set full "
+                                               "(profiles/r2_ncu_full_fused_rows_summary.csv: reads 873 MB = the algorithmic reads, writes 73 MB -- most "
+                                               "of the 268 MB written is still in L2 when a kernel ends); not measured by this run"}
 FULL_ATTEMPTS = 74         # step attempts of the full workload (reference, oracle and CUDA path agree)
 CPU_SAMPLE_T_END = 1.0     # the CPU sample integrates the FULL batch over t in [0, 1] (9 of the 74 attempts, + the start-up work)
 REF_DIR = os.path.join(ROOT, "baseline", "_ref")      # the unmodified reference, `pip install --target`
@@ -258,7 +272,23 @@ def roofline_probe(dev, n_elems, reps=20):
     # every pass over the six rows touches 9 distinct 33.5 MB arrays (>> 126 MB L2), like a real attempt
     comb_ms = timed(rows, reps)
     group_ms = timed(rows + [norm], reps)
-    return comb_ms, group_ms
+    res = {"comb_ms": comb_ms, "group_ms": group_ms}
+    if lib.tdq_linear_supported(dc, DIM):
+        # the fused rows of one attempt as the engine issues them: row i reads y0, k_0..k_i and writes k_{i+1}
+        # (producer -> consumer through memory, 9 + 2 distinct arrays); the last row also writes y1 and the error prefix
+        W = torch.randn(DIM, DIM, device=dev) * 0.09
+        planes = torch.empty(int(lib.tdq_linear_weights_bytes(DIM)), dtype=torch.uint8, device=dev)
+        _lib.check(lib.tdq_linear_prepare(dc, W.data_ptr(), DIM, planes.data_ptr(), _stream()))
+
+        def fused_row(row):
+            last = row == 5
+            _lib.check(lib.tdq_linear_stage(ctrl, tab, dc, row, ks[row + 1].data_ptr(), outs[1].data_ptr() if last else None,
+                                            errp.data_ptr() if last else None, y0.data_ptr(), kp, planes.data_ptr(), DIM,
+                                            n_elems, _stream()))
+        frows = [lambda r=r: fused_row(r) for r in range(6)]
+        res["fused_ms"] = timed(frows, reps)
+        res["fused_group_ms"] = timed(frows + [norm], reps)
+    return res
 
 
 def run_ours(args):
@@ -280,7 +310,8 @@ def run_ours(args):
     if strong:
         assert B_PER_GPU % world == 0
     rows = B_PER_GPU // world if strong else B_PER_GPU      # strong: the 65,536 trajectories are split over the ranks
-    f, y0_host, t, y_all = make_problem(dev, rows, rank, world)
+    fused = not args.generic
+    f, y0_host, t, y_all = make_problem(dev, rows, rank, world, fused=fused)
     y0_host = y0_host.pin_memory()
     y0 = y0_host.to(dev)
     t_dev = t.to(dev)
@@ -289,9 +320,10 @@ def run_ours(args):
         opts["process_group"] = pg
     stats = {}
 
-    def solve(y):
+    def solve(y, func=None, st=None):
         with torch.no_grad():
-            return tdq.odeint(f, y, t_dev, method="dopri5", rtol=RTOL, atol=ATOL, options=dict(opts), _stats=stats)
+            return tdq.odeint(func if func is not None else f, y, t_dev, method="dopri5", rtol=RTOL, atol=ATOL,
+                              options=dict(opts), _stats=st if st is not None else stats)
 
     def barrier():
         if world > 1:
@@ -329,10 +361,25 @@ def run_ours(args):
     e1.record()
     barrier()
     ms_e2e = e0.elapsed_time(e1)
+    # ---- the same job with func as an opaque torch module (what any other vector field gets) -------------------------
+    ms_gen, gen_stats = None, {}
+    if fused:
+        f_gen = make_problem(dev, rows, rank, world, fused=False)[0]
+        for _ in range(3):
+            solve(y0, f_gen, gen_stats)
+        barrier()
+        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        g0.record()
+        for _ in range(args.steps):
+            solve(y0, f_gen, gen_stats)
+        g1.record()
+        barrier()
+        ms_gen = g0.elapsed_time(g1)
     if world > 1:
-        tm = torch.tensor([ms, ms_e2e], device=dev, dtype=torch.float64)
+        tm = torch.tensor([ms, ms_e2e, ms_gen if ms_gen is not None else 0.0], device=dev, dtype=torch.float64)
         dist.all_reduce(tm, op=dist.ReduceOp.MAX)
         ms, ms_e2e = float(tm[0]), float(tm[1])
+        ms_gen = float(tm[2]) if ms_gen is not None else None
     # sanity of the result (norm preservation of the skew field) -- a wrong answer must not be timed silently
     n0, n1 = y0.norm(dim=1), out[-1].norm(dim=1)
     drift = float(((n1 - n0).abs() / n0).max())
@@ -359,7 +406,8 @@ def run_ours(args):
     if rank == 0:
         n_elems = B_PER_GPU * DIM
         peak, peak_src = measured_peaks()
-        comb_ms, group_ms = roofline_probe(dev, n_elems)
+        probe = roofline_probe(dev, n_elems)
+        comb_ms, group_ms = probe["comb_ms"], probe["group_ms"]
         nnz = [1, 2, 3, 4, 5, 5]                          # non-zero beta entries per dopri5 row
         comb_bytes = sum((k + 2) * n_elems * 4 for k in nnz)          # 32*N*s
         norm_bytes = 8 * n_elems * 4
@@ -378,8 +426,9 @@ def run_ours(args):
                        "batch_per_gpu": rows, "dim": DIM,
                        "exec": ("cuda-graph step body inside a device-side while loop (one launch per solve)"
                                 if not args.no_device_loop else "cuda-graph step body replayed by the host, run_ahead=2"),
-                       "func_share": "the user's func (y @ A^T, cuBLAS fp32 SIMT SGEMM, 6 per attempt) is ~60 % of a step; "
-                                     "the solver's own kernels are the rest (profiles/README.md)",
+                       "func": ("torchdiffeq_b200.LinearField(A): forward(t, y) = y @ A^T; each stage (combination + field) is one "
+                                "tcgen05 kernel, BF16x9 float32-grade product (tdq_linear.cu)" if fused else
+                                "plain nn.Module y @ A^T (cuBLAS fp32 SIMT SGEMM, 6 per attempt, ~60 % of a step)"),
                        "attempts_per_solve": stats.get("attempts"), "nfe_per_solve": stats.get("nfe"),
                        "l2": "working set 20 arrays x 33.5 MB >> 126 MB L2 (no flush needed)",
                        "parallelism": "batch-sharded, 1 all-reduce(3 x f64)/attempt" if world > 1 else "single GPU"},
@@ -387,22 +436,49 @@ def run_ours(args):
                     "h2d_bytes_per_step": y0_host.numel() * 4 * world, "d2h_bytes_per_step": res_host.numel() * 4 * world},
             "gpu_launches": launches,
             "clocks": clocks,
-            "roofline": {"bound": "hbm", "kernel": "k_combine (6 launches per attempt)", "achieved": achieved,
-                         "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         # STATIC: dram__bytes_read + dram__bytes_write of the six launches of one attempt from the
-                         # committed ncu --set full capture (not re-measured by this run)
-                         "traffic": TRAFFIC_STATIC["bytes"], "traffic_source": TRAFFIC_STATIC["source"],
-                         "peak_source": peak_src, "algorithmic_bytes_per_attempt": comb_bytes,
-                         # what the six launches really move: the sixth (k_combine_final) also writes the prefix of the
-                         # error estimate (+1 N*s); the norm launch reads 4 and writes 2 arrays (the candidate commit)
-                         "moved_bytes_per_attempt": comb_bytes + n_elems * 4,
-                         "ms_per_attempt": comb_ms, "launches_per_attempt": 6,
-                         "combine_plus_error_norm": {"achieved": group, "frac": group / peak,
-                                                     "bytes": comb_bytes + norm_bytes, "ms": group_ms,
-                                                     "moved_bytes": comb_bytes + n_elems * 4 + 6 * n_elems * 4,
-                                                     "target": "BASELINE.md: >= 0.70 of the HBM roofline"}},
-            "result_check": check,
         }
+        k_combine_roof = {"kernel": "k_combine (6 launches per attempt; the stage combination when func is an opaque module)",
+                          "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                          # STATIC: dram__bytes_read + dram__bytes_write of the six launches of one attempt from the
+                          # committed ncu --set full capture (not re-measured by this run)
+                          "traffic": TRAFFIC_STATIC["bytes"], "traffic_source": TRAFFIC_STATIC["source"],
+                          "algorithmic_bytes_per_attempt": comb_bytes,
+                          # what the six launches really move: the sixth (k_combine_final) also writes the prefix of the
+                          # error estimate (+1 N*s); the norm launch reads 4 and writes 2 arrays (the candidate commit)
+                          "moved_bytes_per_attempt": comb_bytes + n_elems * 4,
+                          "ms_per_attempt": comb_ms, "launches_per_attempt": 6,
+                          "combine_plus_error_norm": {"achieved": group, "frac": group / peak,
+                                                      "bytes": comb_bytes + norm_bytes, "ms": group_ms,
+                                                      "moved_bytes": comb_bytes + n_elems * 4 + 6 * n_elems * 4,
+                                                      "target": "BASELINE.md: >= 0.70 of the HBM roofline"}}
+        if fused and "fused_ms" in probe:
+            # six fused rows: reads y0 + the row's k_j, writes k_i; the last row also writes y1 and the error prefix
+            fused_bytes = comb_bytes + 2 * n_elems * 4                        # 34*N*s: y_i is never written or re-read
+            fms, fgms = probe["fused_ms"], probe["fused_group_ms"]
+            flops = 6 * 9 * 2.0 * B_PER_GPU * DIM * DIM                       # nine bf16 products per float32 product
+            line["roofline"] = {
+                "bound": "hbm", "kernel": "k_linear_stage (6 launches per attempt: stage combination + linear field, tcgen05)",
+                "achieved": fused_bytes / (fms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                "frac": fused_bytes / (fms * 1e-3) / 1e9 / peak, "peak_source": peak_src,
+                "traffic": TRAFFIC_FUSED["bytes"], "traffic_source": TRAFFIC_FUSED["source"],
+                "algorithmic_bytes_per_attempt": fused_bytes, "ms_per_attempt": fms, "launches_per_attempt": 6,
+                "tensor": {"bf16_flop_per_attempt": flops, "achieved_tflops": flops / (fms * 1e-3) / 1e12,
+                           "note": "9 bf16 MMAs per float32 product; the kernel is HBM bound, the tensor pipe is ~20 % busy"},
+                "stage_plus_error_norm": {"achieved": (fused_bytes + norm_bytes) / (fgms * 1e-3) / 1e9,
+                                          "frac": (fused_bytes + norm_bytes) / (fgms * 1e-3) / 1e9 / peak,
+                                          "bytes": fused_bytes + norm_bytes, "ms": fgms},
+                "generic_path_kernel": k_combine_roof}
+        else:
+            k_combine_roof.update({"bound": "hbm", "peak_source": peak_src})
+            line["roofline"] = k_combine_roof
+        if ms_gen is not None:
+            line["generic_path"] = {"value": total_traj / (ms_gen * 1e-3), "unit": "trajectories/s",
+                                    "ms_per_step": ms_gen / args.steps,
+                                    "func": "plain nn.Module y @ A^T (cuBLAS fp32 SIMT SGEMM): k_combine + the user's kernels",
+                                    "attempts_per_solve": gen_stats.get("attempts")}
+        line.update({
+            "result_check": check,
+        })
         if cpu_val is not None:
             line["cpu_baseline"] = {"value": cpu_val, "unit": "trajectories/s", "cores": threads, "kind": cpu_kind,
                                     "sample": cpu_desc}
@@ -424,6 +500,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", dest="cpu_baseline", action="store_false")
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
                     help="N > 1: weak = 65536 trajectories per rank (configs[4]); strong = 65536 split over the ranks")
+    ap.add_argument("--generic", action="store_true",
+                    help="func as an opaque torch module (k_combine + cuBLAS SGEMM per stage) instead of LinearField")
     ap.add_argument("--no-device-loop", action="store_true",
                     help="replay the step graph from the host instead of the device-side while loop (needed under ncu: "
                          "kernels inside a conditional graph node are not visible to its kernel-level profiling)")

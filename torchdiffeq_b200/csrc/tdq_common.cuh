@@ -143,6 +143,17 @@ template <> __device__ __forceinline__ void st_vec<double>(double *p, const Vec<
     asm volatile("st.global.v2.f64 [%0], {%1,%2};" :: "l"(p), "d"(x.v[0]), "d"(x.v[1]) : "memory");
 }
 
+// A pointer that comes straight out of a global load (the control block's pointer table: y0_cur, k0_cur, ybuf[], kbuf[])
+// carries that load's SCOREBOARD into every address computation that uses it.  ptxas counts a loop's own loads on the
+// same scoreboard, so "wait for the pointer" becomes "wait for every load issued so far": the second group of loads of an
+// iteration is not issued before the first has returned (seen with ncu as long-scoreboard stalls on IADD3; it cost the
+// fused linear stage 55 us instead of 39 us).  One integer add with a run-time zero the compiler cannot fold turns the
+// pointer into an ALU result.  `n` is any size_t kernel argument below 2^63.
+template <typename P>
+__device__ __forceinline__ P *tdq_detach(P *p, size_t n) {
+    return reinterpret_cast<P *>(reinterpret_cast<uintptr_t>(p) + (n >> 63));
+}
+
 // Stage-slot pointer bundle passed by value.
 struct KPtrs {
     const void *p[TDQ_MAX_K];

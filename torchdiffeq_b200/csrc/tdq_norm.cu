@@ -57,7 +57,7 @@ k_norm(const TdqCtrl *__restrict__ c, NormArgs a) {
 
     const T *x = reinterpret_cast<const T *>(a.x);
     const T *x2 = reinterpret_cast<const T *>(a.x2);
-    const T *y0 = reinterpret_cast<const T *>(a.y0 ? a.y0 : c->y0_cur);
+    const T *y0 = tdq_detach(reinterpret_cast<const T *>(a.y0 ? a.y0 : c->y0_cur), a.n);
     const T *y1 = reinterpret_cast<const T *>(a.y1);
     const T rtolT = (T)c->rtol, atolT = (T)c->atol;   // 0-dim float64 tensors act as scalars of T (misc.py:81)
     // MODE 0: the last error weight, when it belongs to k_S of an FSAL tableau, is not in the prefix
@@ -65,8 +65,8 @@ k_norm(const TdqCtrl *__restrict__ c, NormArgs a) {
     const T ecS = ek ? (T)c->ecoef[c->err_nnz - 1] : (T)0;
     T *ycand = nullptr, *kcand = nullptr;
     if (MODE == 0 && c->ybuf[0] != nullptr) {
-        ycand = reinterpret_cast<T *>(c->ybuf[c->par ^ 1]);
-        kcand = reinterpret_cast<T *>(c->kbuf[c->par ^ 1]);
+        ycand = tdq_detach(reinterpret_cast<T *>(c->ybuf[c->par ^ 1]), a.n);
+        kcand = tdq_detach(reinterpret_cast<T *>(c->kbuf[c->par ^ 1]), a.n);
     }
     double *p_sum = a.partials + 2, *p_bad = p_sum + a.n_parts;
 

@@ -40,8 +40,9 @@ k_combine(const TdqCtrl *__restrict__ c, int row, T *__restrict__ out, const T *
 #pragma unroll
     for (int m = 0; m < NK; ++m) {
         cf[m] = (T)c->coef[row][m];
-        k[m] = reinterpret_cast<const T *>(kp.p[m] ? kp.p[m] : c->k0_cur);
+        k[m] = tdq_detach(reinterpret_cast<const T *>(kp.p[m] ? kp.p[m] : c->k0_cur), n);
     }
+    y0 = tdq_detach(y0, n);
     if (VECTOR) {
         using V = Vec<T>;
         const size_t nvec = n / V::N;
@@ -167,8 +168,9 @@ k_combine_final(const TdqCtrl *__restrict__ c, int row, T *__restrict__ out, T *
         const T ve = ue ? (T)c->ecoef[fm.epos[m]] : (T)0;
         cr[m] = vr;
         ce[m] = ve;
-        k[m] = reinterpret_cast<const T *>(kp.p[m] ? kp.p[m] : c->k0_cur);
+        k[m] = tdq_detach(reinterpret_cast<const T *>(kp.p[m] ? kp.p[m] : c->k0_cur), n);
     }
+    y0 = tdq_detach(y0, n);
     auto element = [&](T y, const T *kv, T &yo, T &eo) {
         T ar = (T)0, ae = (T)0;
         bool fr = true, fe = true;
