@@ -429,7 +429,7 @@ __device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&r)[32
                     "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31]) : "memory");
 }
 
-template <int NK, bool FINAL, int PF = 0>
+template <int NK, bool FINAL, int PF = 0, int SCHED = 0, int PIPE = 0>
 __global__ void __launch_bounds__(V3_THREADS, 1)
 k_linear_stage3(const float *__restrict__ y0, KP kp, CF cr, CF ce, const uint32_t *__restrict__ wt,
                 float *__restrict__ kout, float *__restrict__ yout, float *__restrict__ eout, int n_rows) {
@@ -449,7 +449,7 @@ k_linear_stage3(const float *__restrict__ y0, KP kp, CF cr, CF ce, const uint32_
     if (tid == 32) {
         mbar_init(b_full[0], 256); mbar_init(b_full[1], 256);
         mbar_init(b_empty[0], 1); mbar_init(b_empty[1], 1);
-        mbar_init(b_accf, 1); mbar_init(b_acce, 128); mbar_init(b_wready, 128);
+        mbar_init(b_accf, 1); mbar_init(b_acce, 128); mbar_init(b_wready, 128); mbar_init(bar0 + 56, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     fence_before();
@@ -460,17 +460,30 @@ k_linear_stage3(const float *__restrict__ y0, KP kp, CF cr, CF ce, const uint32_
     const int units = (n_rows + 63) / 64;
     const int u_begin = (int)((long long)blockIdx.x * units / gridDim.x);
     const int u_end = (int)((long long)(blockIdx.x + 1) * units / gridDim.x);
+    // SCHED 1: round robin -- W full waves of 128-row tiles (tile it * G + b), then the remaining 64-row units one per CTA and
+    // wave: at any time the CTAs read ONE contiguous window of every array (like a grid-stride streaming kernel)
+    const int G = gridDim.x, W_full = (units / 2) / G, u_tail = 2 * W_full * G;
+    const int n_tail = units - u_tail > (int)blockIdx.x ? (units - u_tail - (int)blockIdx.x + G - 1) / G : 0;
+    const int n_tiles = SCHED == 0 ? (u_end - u_begin + 1) / 2 : W_full + n_tail;
+    auto tile_of = [&](int it, int &row0, int &rows_here) {
+        if (SCHED == 0) {
+            const int u = u_begin + 2 * it;
+            row0 = u * 64;
+            rows_here = min(min(128, (u_end - u) * 64), n_rows - row0);
+        } else if (it < W_full) {
+            row0 = (it * G + (int)blockIdx.x) * 128;
+            rows_here = min(128, n_rows - row0);
+        } else {
+            row0 = (u_tail + (it - W_full) * G + (int)blockIdx.x) * 64;
+            rows_here = min(64, n_rows - row0);
+        }
+    };
 
     if (wg < 2) {
         // ================= producers: stage combination, split, operand planes =================
         constexpr int NKK = NK > 0 ? NK : 1;
         constexpr int BPT = 4;                                   // batches of 4 rows per warp and tile
-        const int n_tiles = (u_end - u_begin + 1) / 2, nb = n_tiles * BPT;
-        auto tile_of = [&](int it, int &row0, int &rows_here) {
-            const int u = u_begin + 2 * it;
-            row0 = u * 64;
-            rows_here = min(min(128, (u_end - u) * 64), n_rows - row0);
-        };
+        const int nb = n_tiles * BPT;
         // L2 prefetch of a later batch: lane l < 4 * (NK + 1) fetches the 512-byte row uu = l / (NK + 1) of array l % (NK + 1)
         auto prefetch = [&](int b) {
             int row0, rows_here;
@@ -563,11 +576,62 @@ k_linear_stage3(const float *__restrict__ y0, KP kp, CF cr, CF ce, const uint32_
             }
         }
         asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
-        uint32_t it = 0;
-        for (int u = u_begin; u < u_end; ++it) {
-            const int nu = u_end - u < 2 ? u_end - u : 2;
-            const int row0 = u * 64, rows_here = min(nu * 64, n_rows - row0);
-            u += nu;
+        if (PIPE) {
+            // ---- version 4: one accumulator per tile, two of them: the MMAs of tile t+1 run while tile t is drained ----
+            const uint32_t b_acc2[2] = {b_accf, bar0 + 56};
+            const bool leader = warp == 8 && lane == 0;
+            auto issue = [&](int t) {
+                const int s = t & 1;
+                const uint32_t y_base = smem_u32(smem + s * STAGE_BYTES);
+                mbar_wait(b_full[s], (t >> 1) & 1);
+                fence_after();
+                constexpr int PW[9] = {2, 2, 1, 1, 2, 0, 1, 0, 0}, PY[9] = {2, 1, 2, 1, 0, 2, 0, 1, 0};
+#pragma unroll
+                for (int p = 0; p < 9; ++p) {
+#pragma unroll
+                    for (int ks = 0; ks < 8; ++ks) {
+                        const uint32_t koff = (ks >> 2) * ATOM_BYTES + (ks & 3) * 32;
+                        mma_bf16_ts(tmem + s * 128, tmem + COL_W + PW[p] * 64 + ks * 8, make_desc(y_base + PY[p] * PLANE_BYTES + koff),
+                                    p == 0 && ks == 0 ? 0u : 1u);
+                    }
+                }
+                mma_commit(b_empty[s]);
+                mma_commit(b_acc2[s]);
+            };
+            fence_before();
+            asm volatile("bar.sync 1, 128;" ::: "memory");          // the weights are in tensor memory
+            if (leader && n_tiles > 0) issue(0);
+            for (int t = 0; t < n_tiles; ++t) {
+                int row0, rows_here;
+                tile_of(t, row0, rows_here);
+                if (t > 0) {
+                    fence_before();
+                    asm volatile("bar.sync 1, 128;" ::: "memory");  // tile t-1 is drained: its accumulator is free for t+1
+                }
+                if (leader && t + 1 < n_tiles) issue(t + 1);
+                __syncwarp();
+                mbar_wait(b_acc2[t & 1], (t >> 1) & 1);
+                fence_after();
+                const uint32_t acc = lane_base + (t & 1) * 128;
+                const int nch = (rows_here + 15) >> 4;
+                uint32_t buf[2][16];
+                tmem_ld16_nowait(acc, buf[0]);
+#pragma unroll
+                for (int cc = 0; cc < 8; ++cc) {
+                    if (cc < nch) {
+                        tmem_ld_wait();
+                        if (cc + 1 < nch) tmem_ld16_nowait(acc + (cc + 1) * 16, buf[(cc + 1) & 1]);
+                        float *dst = kout + (size_t)(row0 + cc * 16) * D + f;
+#pragma unroll
+                        for (int j = 0; j < 16; ++j)
+                            if (cc * 16 + j < rows_here) dst[(size_t)j * D] = __uint_as_float(buf[cc & 1][j]);
+                    }
+                }
+            }
+        } else
+        for (uint32_t it = 0; it < (uint32_t)n_tiles; ++it) {
+            int row0, rows_here;
+            tile_of((int)it, row0, rows_here);
             // the previous tile's accumulators are drained (and, the first time, the weights are in tensor memory)
             fence_before();
             asm volatile("bar.sync 1, 128;" ::: "memory");
@@ -688,7 +752,7 @@ constexpr int NSETS = 3;                       // distinct copies of the inputs,
 static float *g_set_y0[NSETS];
 static float *g_set_k[NSETS][MAXK];
 static float *g_set_out[NSETS][3];
-template <int NK, int NPROD, bool FINAL, int VER = 2, int PF = 0>
+template <int NK, int NPROD, bool FINAL, int VER = 2, int PF = 0, int SCHED = 0, int PIPE = 0>
 static void run2(int rows, const float *d_y0, float *const *d_k, const float *cfh, const float *ceh, const uint8_t *d_planes,
                  float *d_out, float *d_yout, float *d_eout, const std::vector<float> &h_y0,
                  const std::vector<std::vector<float>> &h_k, const std::vector<float> &h_A, int sms) {
@@ -698,7 +762,7 @@ static void run2(int rows, const float *d_y0, float *const *d_k, const float *cf
     const int units = (rows + 63) / 64;
     const int grid = units / 2 < sms ? (units + 1) / 2 : sms;
     if (VER == 2) CK(cudaFuncSetAttribute(k_linear_stage2<NK, NPROD, FINAL>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-    else CK(cudaFuncSetAttribute(k_linear_stage3<NK, FINAL, PF>, cudaFuncAttributeMaxDynamicSharedMemorySize, V3_SMEM));
+    else CK(cudaFuncSetAttribute(k_linear_stage3<NK, FINAL, PF, SCHED, PIPE>, cudaFuncAttributeMaxDynamicSharedMemorySize, V3_SMEM));
     const uint32_t *wt = g_wt;
     int set = -1;
     auto launch = [&]() {
@@ -712,7 +776,7 @@ static void run2(int rows, const float *d_y0, float *const *d_k, const float *cf
         float *o0 = d_out, *o1 = d_yout, *o2 = d_eout;
         if (set > 0 && g_set_out[0][0]) { o0 = g_set_out[set % NSETS][0]; o1 = g_set_out[set % NSETS][1]; o2 = g_set_out[set % NSETS][2]; }
         if (VER == 2) k_linear_stage2<NK, NPROD, FINAL><<<grid, THREADS, SMEM_BYTES>>>(yy, kq, cr, ce, d_planes, o0, o1, o2, rows);
-        else k_linear_stage3<NK, FINAL, PF><<<grid, V3_THREADS, V3_SMEM>>>(yy, kq, cr, ce, wt, o0, o1, o2, rows);
+        else k_linear_stage3<NK, FINAL, PF, SCHED, PIPE><<<grid, V3_THREADS, V3_SMEM>>>(yy, kq, cr, ce, wt, o0, o1, o2, rows);
     };
     CK(cudaMemset(d_out, 0xff, (size_t)rows * D * 4));
     CK(cudaMemset(d_yout, 0xff, (size_t)rows * D * 4));
@@ -769,8 +833,8 @@ static void run2(int rows, const float *d_y0, float *const *d_k, const float *cf
     CK(cudaEventElapsedTime(&ms, e0, e1));
     const int arrays = NK + 2 + (FINAL ? 2 : 0);
     const double us = ms * 1e3 / reps, bytes = (double)rows * D * 4 * arrays;
-    printf("v%d PF=%d NK=%d NPROD=%d FINAL=%d rows=%d grid=%d: %.2f us  (%.0f GB/s on %d arrays)  rel rms err %.3e  max abs err %.3e  bad %zu  y/err mismatches %zu\n",
-           VER, PF, NK, NPROD, (int)FINAL, rows, grid, us, bytes / us * 1e-3, arrays, sqrt(sum_sq / ref_sq), max_err, bad, ybad);
+    printf("v%d PIPE=%d SCHED=%d PF=%d NK=%d NPROD=%d FINAL=%d rows=%d grid=%d: %.2f us  (%.0f GB/s on %d arrays)  rel rms err %.3e  max abs err %.3e  bad %zu  y/err mismatches %zu\n",
+           VER, PIPE, SCHED, PF, NK, NPROD, (int)FINAL, rows, grid, us, bytes / us * 1e-3, arrays, sqrt(sum_sq / ref_sq), max_err, bad, ybad);
 }
 
 int main(int argc, char **argv) {
@@ -833,8 +897,12 @@ int main(int argc, char **argv) {
             for (int j = 0; j < 3; ++j) CK(cudaMalloc(&g_set_out[st][j], h_y0.size() * 4));
         printf("cold inputs and outputs (3 rotating copies), arrays %zu bytes apart:\n", stride);
         R3(0, false); R3(1, false); R3(2, false); R3(3, false); R3(4, false); R3(5, false); R3(5, true);
-        R4(3, false, 1); R4(5, false, 1); R4(5, true, 1);
-        R4(3, false, 2); R4(5, false, 2); R4(5, true, 2);
+#define R5(NK, F) run2<NK, 9, F, 3, 0, 0, 1>(rows, d_y0, d_k, cfh, ceh, d_planes, d_out, d_yout, d_eout, h_y0, h_k, h_A, sms)
+        R5(0, false); R5(1, false); R5(2, false); R5(3, false); R5(4, false); R5(5, false); R5(5, true);
+        run2<5, 9, true, 3, 0, 0, 1>(rows - 40, d_y0, d_k, cfh, ceh, d_planes, d_out, d_yout, d_eout, h_y0, h_k, h_A, sms);
+        run2<3, 9, false, 3, 0, 0, 1>(1000, d_y0, d_k, cfh, ceh, d_planes, d_out, d_yout, d_eout, h_y0, h_k, h_A, sms);
+        run2<3, 9, false, 3, 0, 0, 1>(64, d_y0, d_k, cfh, ceh, d_planes, d_out, d_yout, d_eout, h_y0, h_k, h_A, sms);
+        run2<3, 9, false, 3, 0, 0, 1>(148 * 128 * 2 + 64 * 100 + 13, d_y0, d_k, cfh, ceh, d_planes, d_out, d_yout, d_eout, h_y0, h_k, h_A, sms);
         run2<5, 9, true, 3>(rows - 40, d_y0, d_k, cfh, ceh, d_planes, d_out, d_yout, d_eout, h_y0, h_k, h_A, sms);
         run2<3, 9, false, 3>(1000, d_y0, d_k, cfh, ceh, d_planes, d_out, d_yout, d_eout, h_y0, h_k, h_A, sms);
         printf("done v3\n");
