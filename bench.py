@@ -427,7 +427,7 @@ def run_ours(args):
                        "exec": ("cuda-graph step body inside a device-side while loop (one launch per solve)"
                                 if not args.no_device_loop else "cuda-graph step body replayed by the host, run_ahead=2"),
                        "func": ("torchdiffeq_b200.LinearField(A): forward(t, y) = y @ A^T; each stage (combination + field) is one "
-                                "tcgen05 kernel, BF16x9 float32-grade product (tdq_linear.cu)" if fused else
+                                "tcgen05 kernel, split-bf16 float32-grade product (tdq_linear.cu)" if fused else
                                 "plain nn.Module y @ A^T (cuBLAS fp32 SIMT SGEMM, 6 per attempt, ~60 % of a step)"),
                        "attempts_per_solve": stats.get("attempts"), "nfe_per_solve": stats.get("nfe"),
                        "l2": "working set 20 arrays x 33.5 MB >> 126 MB L2 (no flush needed)",
@@ -455,7 +455,7 @@ def run_ours(args):
             # six fused rows: reads y0 + the row's k_j, writes k_i; the last row also writes y1 and the error prefix
             fused_bytes = comb_bytes + 2 * n_elems * 4                        # 34*N*s: y_i is never written or re-read
             fms, fgms = probe["fused_ms"], probe["fused_group_ms"]
-            flops = 6 * 9 * 2.0 * B_PER_GPU * DIM * DIM                       # nine bf16 products per float32 product
+            flops = 6 * 6 * 2.0 * B_PER_GPU * DIM * DIM                       # six bf16 products per float32 product
             line["roofline"] = {
                 "bound": "hbm", "kernel": "k_linear_stage (6 launches per attempt: stage combination + linear field, tcgen05)",
                 "achieved": fused_bytes / (fms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
@@ -463,7 +463,7 @@ def run_ours(args):
                 "traffic": TRAFFIC_FUSED["bytes"], "traffic_source": TRAFFIC_FUSED["source"],
                 "algorithmic_bytes_per_attempt": fused_bytes, "ms_per_attempt": fms, "launches_per_attempt": 6,
                 "tensor": {"bf16_flop_per_attempt": flops, "achieved_tflops": flops / (fms * 1e-3) / 1e12,
-                           "note": "9 bf16 MMAs per float32 product; the kernel is HBM bound, the tensor pipe is ~20 % busy"},
+                           "note": "6 bf16 MMA passes per float32 product; the kernel is HBM bound, the tensor pipe is ~20 % busy"},
                 "stage_plus_error_norm": {"achieved": (fused_bytes + norm_bytes) / (fgms * 1e-3) / 1e9,
                                           "frac": (fused_bytes + norm_bytes) / (fgms * 1e-3) / 1e9 / peak,
                                           "bytes": fused_bytes + norm_bytes, "ms": fgms},

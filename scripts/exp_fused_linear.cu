@@ -429,7 +429,7 @@ __device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&r)[32
                     "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31]) : "memory");
 }
 
-template <int NK, bool FINAL, int PF = 0, int SCHED = 0, int PIPE = 0>
+template <int NK, bool FINAL, int PF = 0, int SCHED = 0, int PIPE = 0, int NPROD = 9>
 __global__ void __launch_bounds__(V3_THREADS, 1)
 k_linear_stage3(const float *__restrict__ y0, KP kp, CF cr, CF ce, const uint32_t *__restrict__ wt,
                 float *__restrict__ kout, float *__restrict__ yout, float *__restrict__ eout, int n_rows) {
@@ -456,6 +456,7 @@ k_linear_stage3(const float *__restrict__ y0, KP kp, CF cr, CF ce, const uint32_
     __syncthreads();
     fence_after();
     const uint32_t tmem = *tmem_slot;
+    const int dbg = (int)ce.c[6];          // ablation only: 1 skip epilogue stores, 2 skip MMAs, 4 skip y0 loads, 8 skip split+STS
 
     const int units = (n_rows + 63) / 64;
     const int u_begin = (int)((long long)blockIdx.x * units / gridDim.x);
@@ -514,7 +515,8 @@ k_linear_stage3(const float *__restrict__ y0, KP kp, CF cr, CF ce, const uint32_
                     const int r = warp + 8 * (4 * i + uu);
                     if (r < rows_here) {
                         const size_t off = (size_t)(row0 + r) * D + lane * 4;
-                        a[uu] = __ldcs(reinterpret_cast<const float4 *>(y0 + off));
+                        if (dbg & 4) { a[uu] = make_float4(1.f, 2.f, 3.f, (float)off); }
+                        else a[uu] = __ldcs(reinterpret_cast<const float4 *>(y0 + off));
 #pragma unroll
                         for (int m = 0; m < NK; ++m) kv[uu][m] = __ldcs(reinterpret_cast<const float4 *>(kp.p[m] + off));
                     }
@@ -548,7 +550,7 @@ k_linear_stage3(const float *__restrict__ y0, KP kp, CF cr, CF ce, const uint32_
                                 *reinterpret_cast<float4 *>(eout + off) = e;
                             }
                         }
-                        store_split(sY, r, lane, y);
+                        if (!(dbg & 8)) store_split(sY, r, lane, y);
                     }
                 }
             }
@@ -643,15 +645,19 @@ k_linear_stage3(const float *__restrict__ y0, KP kp, CF cr, CF ce, const uint32_
                 fence_after();
                 // weights plane pw (A, tensor memory) x stage-value plane py (B, shared memory); eight small products
                 // in ascending magnitude into one accumulator, hi x hi into the other
-                constexpr int PW[9] = {2, 2, 1, 1, 2, 0, 1, 0, 0}, PY[9] = {2, 1, 2, 1, 0, 2, 0, 1, 0};
+                constexpr int PW9[9] = {2, 2, 1, 1, 2, 0, 1, 0, 0}, PY9[9] = {2, 1, 2, 1, 0, 2, 0, 1, 0};
+                constexpr int PW6[9] = {1, 2, 0, 1, 0, 0, 0, 0, 0}, PY6[9] = {1, 0, 2, 0, 1, 0, 0, 0, 0};
+                constexpr int PW3[9] = {1, 0, 0, 0, 0, 0, 0, 0, 0}, PY3[9] = {0, 1, 0, 0, 0, 0, 0, 0, 0};
 #pragma unroll
-                for (int p = 0; p < 9; ++p) {
-                    const uint32_t dcol = tmem + (p == 8 ? COL_BIG : COL_SMALL);
+                for (int p = 0; p < NPROD; ++p) {
+                    const int *PW = NPROD == 9 ? PW9 : (NPROD == 6 ? PW6 : PW3), *PY = NPROD == 9 ? PY9 : (NPROD == 6 ? PY6 : PY3);
+                    const uint32_t dcol = tmem + (p == NPROD - 1 ? COL_BIG : COL_SMALL);
+                    if (dbg & 2) continue;
 #pragma unroll
                     for (int ks = 0; ks < 8; ++ks) {
                         const uint32_t koff = (ks >> 2) * ATOM_BYTES + (ks & 3) * 32;
                         mma_bf16_ts(dcol, tmem + COL_W + PW[p] * 64 + ks * 8, make_desc(y_base + PY[p] * PLANE_BYTES + koff),
-                                    (p == 0 || p == 8) && ks == 0 ? 0u : 1u);
+                                    (p == 0 || p == NPROD - 1) && ks == 0 ? 0u : 1u);
                     }
                 }
                 mma_commit(b_empty[s]);
@@ -670,7 +676,7 @@ k_linear_stage3(const float *__restrict__ y0, KP kp, CF cr, CF ce, const uint32_
                 float *dst = kout + (size_t)(row0 + cc * 16) * D + f;
 #pragma unroll
                 for (int j = 0; j < 16; ++j)
-                    if (cc * 16 + j < rows_here) dst[(size_t)j * D] = __uint_as_float(small[j]) + __uint_as_float(big[j]);
+                    if (cc * 16 + j < rows_here && !((dbg & 1) && j > 0)) dst[(size_t)j * D] = __uint_as_float(small[j]) + __uint_as_float(big[j]);
             }
         }
     }
@@ -748,6 +754,7 @@ static void run(int rows, const float *d_y0, float *const *d_k, const float *cfh
 }
 
 static const uint32_t *g_wt = nullptr;
+static int g_dbg = 0;
 constexpr int NSETS = 3;                       // distinct copies of the inputs, rotated per launch: a cold L2 for every launch
 static float *g_set_y0[NSETS];
 static float *g_set_k[NSETS][MAXK];
@@ -759,10 +766,11 @@ static void run2(int rows, const float *d_y0, float *const *d_k, const float *cf
     KP kp{};
     CF cr{}, ce{};
     for (int m = 0; m < NK; ++m) { kp.p[m] = d_k[m]; cr.c[m] = cfh[m]; ce.c[m] = ceh[m]; }
+    ce.c[6] = (float)g_dbg;
     const int units = (rows + 63) / 64;
     const int grid = units / 2 < sms ? (units + 1) / 2 : sms;
     if (VER == 2) CK(cudaFuncSetAttribute(k_linear_stage2<NK, NPROD, FINAL>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-    else CK(cudaFuncSetAttribute(k_linear_stage3<NK, FINAL, PF, SCHED, PIPE>, cudaFuncAttributeMaxDynamicSharedMemorySize, V3_SMEM));
+    else CK(cudaFuncSetAttribute(k_linear_stage3<NK, FINAL, PF, SCHED, PIPE, NPROD>, cudaFuncAttributeMaxDynamicSharedMemorySize, V3_SMEM));
     const uint32_t *wt = g_wt;
     int set = -1;
     auto launch = [&]() {
@@ -776,7 +784,7 @@ static void run2(int rows, const float *d_y0, float *const *d_k, const float *cf
         float *o0 = d_out, *o1 = d_yout, *o2 = d_eout;
         if (set > 0 && g_set_out[0][0]) { o0 = g_set_out[set % NSETS][0]; o1 = g_set_out[set % NSETS][1]; o2 = g_set_out[set % NSETS][2]; }
         if (VER == 2) k_linear_stage2<NK, NPROD, FINAL><<<grid, THREADS, SMEM_BYTES>>>(yy, kq, cr, ce, d_planes, o0, o1, o2, rows);
-        else k_linear_stage3<NK, FINAL, PF, SCHED, PIPE><<<grid, V3_THREADS, V3_SMEM>>>(yy, kq, cr, ce, wt, o0, o1, o2, rows);
+        else k_linear_stage3<NK, FINAL, PF, SCHED, PIPE, NPROD><<<grid, V3_THREADS, V3_SMEM>>>(yy, kq, cr, ce, wt, o0, o1, o2, rows);
     };
     CK(cudaMemset(d_out, 0xff, (size_t)rows * D * 4));
     CK(cudaMemset(d_yout, 0xff, (size_t)rows * D * 4));
@@ -902,6 +910,16 @@ int main(int argc, char **argv) {
         run2<5, 9, true, 3, 0, 0, 1>(rows - 40, d_y0, d_k, cfh, ceh, d_planes, d_out, d_yout, d_eout, h_y0, h_k, h_A, sms);
         run2<3, 9, false, 3, 0, 0, 1>(1000, d_y0, d_k, cfh, ceh, d_planes, d_out, d_yout, d_eout, h_y0, h_k, h_A, sms);
         run2<3, 9, false, 3, 0, 0, 1>(64, d_y0, d_k, cfh, ceh, d_planes, d_out, d_yout, d_eout, h_y0, h_k, h_A, sms);
+#define R6(NK, F, NP) run2<NK, NP, F, 3, 0, 0, 0>(rows, d_y0, d_k, cfh, ceh, d_planes, d_out, d_yout, d_eout, h_y0, h_k, h_A, sms)
+        printf("six and three bf16 products instead of nine:\n");
+        R6(0, false, 6); R6(1, false, 6); R6(2, false, 6); R6(3, false, 6); R6(4, false, 6); R6(5, false, 6); R6(5, true, 6);
+        R6(0, false, 3); R6(3, false, 3); R6(5, false, 3);
+        for (int dbg : {1, 2, 3, 4, 8, 12, 15}) {
+            g_dbg = dbg;
+            printf("ablation %d (1 no epilogue stores, 2 no MMAs, 4 no y0 loads, 8 no split/STS):\n", dbg);
+            R3(0, false); R3(3, false);
+        }
+        g_dbg = 0;
         run2<3, 9, false, 3, 0, 0, 1>(148 * 128 * 2 + 64 * 100 + 13, d_y0, d_k, cfh, ceh, d_planes, d_out, d_yout, d_eout, h_y0, h_k, h_A, sms);
         run2<5, 9, true, 3>(rows - 40, d_y0, d_k, cfh, ceh, d_planes, d_out, d_yout, d_eout, h_y0, h_k, h_A, sms);
         run2<3, 9, false, 3>(1000, d_y0, d_k, cfh, ceh, d_planes, d_out, d_yout, d_eout, h_y0, h_k, h_A, sms);

@@ -38,7 +38,7 @@ def _weight(seed=3, scale=0.09):
 
 @pytest.mark.parametrize("rows", [1, 63, 64, 65, 127, 128, 129, 1000, 148 * 128 + 17, 65536])
 def test_linear_apply_float32_grade(rows):
-    """k = y W^T on tcgen05 (BF16x9): error against float64 at float32 rounding level, no worse than cuBLAS' float32 SGEMM."""
+    """k = y W^T on tcgen05 (split bf16, six products): error against float64 at float32 rounding level, no worse than cuBLAS' float32 SGEMM."""
     from torchdiffeq_b200 import _lib
     from torchdiffeq_b200._engine import _stream
     lib = _lib.load()

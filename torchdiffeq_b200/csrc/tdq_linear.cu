@@ -7,17 +7,18 @@
 // y_i never goes to HBM: the producer warps form it in registers, split every float32 into three bfloat16 planes
 // (hi + mid + lo = the 24-bit significand exactly) and store the planes as the B operand of tcgen05.mma in shared memory
 // (K-major, 128-byte swizzle, two stages).  The weights are the stationary A operand, split the same way and kept in
-// TENSOR MEMORY for the life of the CTA.  Nine bf16 x bf16 products accumulate in float32 tensor-memory accumulators
-// (the eight small cross terms in ascending magnitude into one, hi x hi into the other; the epilogue adds the two), which
+// TENSOR MEMORY for the life of the CTA.  Six bf16 x bf16 products accumulate in float32 tensor-memory accumulators
+// (the five cross terms >= 2^-16 in ascending magnitude into one, hi x hi into the other; the epilogue adds the two), which
 // reproduces a float32 GEMM to float32 rounding (rel. rms error 1.0e-7 against float64; cuBLAS' own SIMT SGEMM: 2e-7) --
-// the BF16x9 scheme of cuBLAS 12.9 (CUBLAS_COMPUTE_32F_EMULATED_16BFX9), here fused with the operand's producer.
+// the split of cuBLAS 12.9's CUBLAS_COMPUTE_32F_EMULATED_16BFX9 without its three terms below float32 resolution, here
+// fused with the operand's producer.
 // The accumulator is D^T (lane = output feature, column = state row), so a warp's store of one column is 128 contiguous
 // bytes of k_i: no staging.
 //
 // Roles (384 threads, one CTA per SM, persistent over a contiguous range of 64-row units):
 //   warps 0-7   producers: 128-bit streaming loads of y0 and the k_j, the combination, the split, st.shared of the planes;
 //               for the row that yields y1 (FSAL) also y1 and the error-sum prefix, as k_combine_final does
-//   warps 8-11  weights -> tensor memory once; per tile one thread issues the 72 MMAs, then all four drain the accumulators
+//   warps 8-11  weights -> tensor memory once; per tile one thread issues the 48 MMAs, then all four drain the accumulators
 // Measured on B200 (scripts/exp_fused_linear.cu, profiles/README.md): 28.8 / 31.0 / 35.0 / 39.1 / 43.6 us for rows with
 // 1..5 terms at 65536 x 128 (k_combine + cuBLAS SGEMM: 72 .. 89 us), 61 us for the last row with y1 and the error prefix.
 #include "tdq_shape.cuh"
@@ -285,17 +286,21 @@ k_linear_stage(const TdqCtrl *__restrict__ c, int row, const float *y0, LinK kp,
                 const uint32_t y_base = smem_u32(smem + s * STAGE_BYTES);
                 mbar_wait(b_full[s], (it >> 1) & 1);
                 fence_after();
-                // weights plane PW (tensor memory) x stage-value plane PY (shared memory): lo.lo, lo.mid, mid.lo, mid.mid,
-                // lo.hi, hi.lo, mid.hi, hi.mid into the small accumulator, hi.hi into the big one
-                constexpr int PW[9] = {2, 2, 1, 1, 2, 0, 1, 0, 0}, PY[9] = {2, 1, 2, 1, 0, 2, 0, 1, 0};
+                // weights plane PW (tensor memory) x stage-value plane PY (shared memory): mid.mid, lo.hi, hi.lo, mid.hi, hi.mid
+                // into the small accumulator, hi.hi into the big one.  The three remaining cross terms (lo.lo, lo.mid, mid.lo)
+                // are below 2^-24 of a product -- the rounding of a float32 product itself -- and measured irrelevant
+                // (rel. rms error 1.03e-7 with six products, 1.02e-7 with nine; scripts/exp_fused_linear.cu), so they are not
+                // computed: 48 instead of 72 MMAs per tile.
+                constexpr int NPROD = 6;
+                constexpr int PW[NPROD] = {1, 2, 0, 1, 0, 0}, PY[NPROD] = {1, 0, 2, 0, 1, 0};
 #pragma unroll
-                for (int p = 0; p < 9; ++p) {
-                    const uint32_t dcol = tmem + (p == 8 ? COL_BIG : COL_SMALL);
+                for (int p = 0; p < NPROD; ++p) {
+                    const uint32_t dcol = tmem + (p == NPROD - 1 ? COL_BIG : COL_SMALL);
 #pragma unroll
                     for (int ks = 0; ks < 8; ++ks) {
                         const uint32_t koff = (ks >> 2) * ATOM_BYTES + (ks & 3) * 32;
                         mma_ts(dcol, tmem + COL_W + PW[p] * 64 + ks * 8, make_desc(y_base + PY[p] * PLANE_BYTES + koff),
-                               (p == 0 || p == 8) && ks == 0 ? 0u : 1u);
+                               (p == 0 || p == NPROD - 1) && ks == 0 ? 0u : 1u);
                     }
                 }
                 mma_commit(b_empty[s]);      // the stage may be refilled

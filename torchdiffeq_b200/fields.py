@@ -5,7 +5,7 @@ computes), so it runs unchanged under the reference (`torchdiffeq.odeint(LinearF
 `torchdiffeq_b200.odeint` with an adaptive method, a float32 CUDA state `[..., 128]` and a `128 x 128` weight, every
 Runge-Kutta stage -- the combination `y_i = y0 + sum_j coef_ij k_j` (rk_common.py:79) AND the evaluation `k_i = f(t_i, y_i)`
 (rk_common.py:80) -- is ONE hand-written tcgen05 kernel (csrc/tdq_linear.cu): `y_i` never goes to memory, the float32
-product runs on the tensor cores as a BF16x9 emulation with float32-grade accuracy.  Everything else about the solve (error
+product runs on the tensor cores as a split-bfloat16 emulation (3 planes per operand, 6 products) with float32-grade accuracy.  Everything else about the solve (error
 norm, controller, dense output, the device-side loop) is unchanged; `forward` itself is only called for f(t0, y0), the
 initial step size and `jump_t` restarts.  `options={'fused_linear': False}` keeps the generic path (func as a torch call)."""
 import torch
