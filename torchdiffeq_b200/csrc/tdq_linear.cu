@@ -19,8 +19,8 @@
 //   warps 0-7   producers: 128-bit streaming loads of y0 and the k_j, the combination, the split, st.shared of the planes;
 //               for the row that yields y1 (FSAL) also y1 and the error-sum prefix, as k_combine_final does
 //   warps 8-11  weights -> tensor memory once; per tile one thread issues the 48 MMAs, then all four drain the accumulators
-// Measured on B200 (scripts/exp_fused_linear.cu, profiles/README.md): 28.8 / 31.0 / 35.0 / 39.1 / 43.6 us for rows with
-// 1..5 terms at 65536 x 128 (k_combine + cuBLAS SGEMM: 72 .. 89 us), 61 us for the last row with y1 and the error prefix.
+// Measured on B200 (scripts/exp_fused_linear.cu, profiles/README.md), cold: 30 / 33 / 37 / 41 / 46 us for rows with 1..5
+// terms at 65536 x 128 (k_combine + cuBLAS SGEMM: 65 .. 89 us), 60 us for the last row with y1 and the error prefix.
 #include "tdq_shape.cuh"
 
 #include <cstdint>
