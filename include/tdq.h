@@ -326,6 +326,24 @@ int tdq_linear_stage(void *ctrl_dev, const tdq_tableau *tab, int32_t dtype, int3
                      void *err_out, const void *y0, const void *const *k, const void *planes, int32_t width, size_t n,
                      void *stream);
 
+/* ---- A WHOLE attempt of a linear vector field in one launch (tdq_attempt.cu) ---------------------------------------------
+ * For f(t, y) = y W^T an attempt is row-local, so one kernel takes every tile of 16 state rows through all S stages on chip:
+ * rk_common.py:43-90 (_runge_kutta_step: every y_i, every k_i, y1, the error estimate), the squared error ratio of
+ * misc.py:80-82 and the candidate commit of rk_common.py:341/:352 -- what S x tdq_linear_stage + tdq_error_norm_commit do
+ * in S + 1 launches.  HBM traffic: 2 reads + 2 writes per element.  Same arithmetic, operation for operation: k_i, y1 and the
+ * error prefix are bitwise what tdq_linear_stage writes.
+ * tdq_linear_attempt_supported: 1 for float32, width 128 and the FSAL tableaus dopri5 / bosh3.
+ * tdq_linear_attempt: y0 / k0 NULL: the control block's pointer table.  k_out[i] (i = 1..S), y1_out, err_out receive k_i, y1
+ * and the error-sum prefix ONLY for attempts that can contain an output time (t_out[cursor] <= the attempt's end), when the
+ * control block keeps every step (always_fit) or when store_always != 0 -- the lazy interpolant fit is their only reader.
+ * partials / norm_out (both or neither): norm_out[0] = sum over the state of ((err_pre + k_S e_S) / (atol + rtol max(|y0|,|y1|)))^2,
+ * norm_out[1] = number of non-finite y1 elements (what tdq_error_norm_commit writes for one segment), and y1 -> ybuf[par^1],
+ * k_S -> kbuf[par^1]; partials needs tdq_norm_partials_len doubles, zeroed once.  Scalar tolerances only.  No-op after halt. */
+int tdq_linear_attempt_supported(const tdq_tableau *tab, int32_t dtype, int32_t width);
+int tdq_linear_attempt(void *ctrl_dev, const tdq_tableau *tab, int32_t dtype, void *const *k_out, void *y1_out, void *err_out,
+                       const void *y0, const void *k0, const void *planes, int32_t width, size_t n, double *partials,
+                       double *norm_out, int32_t store_always, void *stream);
+
 /* interp='cubic' (solvers.py:120-125, :166-173): for records r in [rec_lo, rec_hi) of one step
  * solution[out_idx[r]] = h00*y0 + (h10*dt)*f0 + h01*y1 + (h11*dt)*f1 with the four weights of record r at
  * coef_dev[4*r .. 4*r+4) (state dtype; the caller evaluates them in t's dtype like the reference and folds the

@@ -271,3 +271,168 @@ def test_fused_reverse_time_tuple_and_grad_paths():
     out[-1].pow(2).sum().backward()
     assert torch.allclose(g1, y0g.grad, rtol=1e-4, atol=1e-5)
     assert torch.allclose(gw1, fp.weight.grad, rtol=1e-3, atol=1e-3 * float(fp.weight.grad.abs().max()))
+
+
+# ---- the whole attempt in one launch (csrc/tdq_attempt.cu) -------------------------------------------------------------------
+
+def _attempt_reference(eng, _lib, _stream, planes, y0, k0, n, S):
+    """S x tdq_linear_stage + tdq_error_norm_commit: (k_1..k_S, y1, err prefix, norm_out, candidate y, candidate k)."""
+    lib = eng.lib
+    ctrl, tabp, dc = eng.ctrl.data_ptr(), C.byref(eng.tab), eng.dt_code
+    ks = [k0] + [torch.full((n,), float("nan"), device=DEV) for _ in range(S)]
+    y1 = torch.full((n,), float("nan"), device=DEV)
+    er = torch.full((n,), float("nan"), device=DEV)
+    for row in range(S):
+        last = row == S - 1
+        kp = _lib.ptr_array([k.data_ptr() for k in ks])
+        _lib.check(lib.tdq_linear_stage(ctrl, tabp, dc, row, ks[row + 1].data_ptr(), y1.data_ptr() if last else None,
+                                        er.data_ptr() if last else None, y0.data_ptr(), kp, planes.data_ptr(), 128, n, _stream()))
+    for b in eng.ybuf + eng.kbuf:
+        b.fill_(float("nan"))
+    _lib.check(lib.tdq_error_norm_commit(ctrl, dc, er.data_ptr(), ks[S].data_ptr(), y0.data_ptr(), y1.data_ptr(), None, None, None,
+                                         0, 0, 1, n, eng.partials.data_ptr(), eng.norm_out.data_ptr(), None, _stream()))
+    torch.cuda.synchronize()
+    return ks, y1, er, eng.norm_out.clone(), eng.ybuf[1].clone(), eng.kbuf[1].clone()
+
+
+@pytest.mark.parametrize("method", ["dopri5", "bosh3"])
+@pytest.mark.parametrize("rows,t_sign", [(16, 1.0), (1000, 1.0), (4133, -1.0), (48 * 148 + 5, 1.0), (65536, 1.0)])
+def test_linear_attempt_equals_stage_sequence(method, rows, t_sign):
+    """tdq_linear_attempt == S x tdq_linear_stage + tdq_error_norm_commit: every k_i, y1 and the error prefix BITWISE, the
+    committed candidates bitwise, the squared error norm to float64 summation order (1e-12), the non-finite count exactly."""
+    n = rows * 128
+    eng, _lib, _stream = _engine(method, torch.float32, n, 0.0371, 0.5, t_sign)
+    lib = eng.lib
+    S = O.tableau(method)["n_stages"]
+    assert lib.tdq_linear_attempt_supported(C.byref(eng.tab), 0, 128) == 1
+    planes = _planes(lib, _lib, _weight(seed=11), _stream)
+    y0 = _rand(n, torch.float32, 1).to(DEV)
+    k0 = _rand(n, torch.float32, 2).to(DEV)
+    ks, y1, er, norm, ycand, kcand = _attempt_reference(eng, _lib, _stream, planes, y0, k0, n, S)
+    for store_always, fold in ((1, False), (1, True), (0, True)):
+        outs = [None] + [torch.full((n,), float("nan"), device=DEV) for _ in range(S)]
+        y1a = torch.full((n,), float("nan"), device=DEV)
+        era = torch.full((n,), float("nan"), device=DEV)
+        for b in eng.ybuf + eng.kbuf:
+            b.fill_(float("nan"))
+        eng.norm_out.fill_(-1.0)
+        kp = _lib.ptr_array([None] + [o.data_ptr() for o in outs[1:]])
+        _lib.check(lib.tdq_linear_attempt(eng.ctrl.data_ptr(), C.byref(eng.tab), 0, kp, y1a.data_ptr(), era.data_ptr(),
+                                          y0.data_ptr(), k0.data_ptr(), planes.data_ptr(), 128, n,
+                                          eng.partials.data_ptr() if fold else None, eng.norm_out.data_ptr() if fold else None,
+                                          store_always, _stream()))
+        torch.cuda.synchronize()
+        if store_always:
+            for i in range(1, S + 1):
+                assert torch.equal(outs[i], ks[i]), (method, "k", i, float((outs[i] - ks[i]).abs().max()))
+            assert torch.equal(y1a, y1) and torch.equal(era, er)
+        else:
+            # t_out[1] = 100 is far beyond this attempt: nothing but the candidates is written
+            assert torch.isnan(y1a).all() and torch.isnan(outs[S]).all() and torch.isnan(outs[1]).all()
+        if fold:
+            assert torch.equal(eng.ybuf[1], ycand) and torch.equal(eng.kbuf[1], kcand)
+            assert torch.isnan(eng.ybuf[0]).all()
+            got = eng.norm_out.clone()
+            assert abs(float(got[0]) - float(norm[0])) <= 1e-12 * abs(float(norm[0])), (float(got[0]), float(norm[0]))
+            assert float(got[1]) == float(norm[1]) == 0.0
+        else:
+            assert torch.isnan(eng.ybuf[1]).all() and float(eng.norm_out[0]) == -1.0
+    # deterministic
+    a = eng.norm_out.clone()
+    _lib.check(lib.tdq_linear_attempt(eng.ctrl.data_ptr(), C.byref(eng.tab), 0, kp, y1a.data_ptr(), era.data_ptr(),
+                                      y0.data_ptr(), k0.data_ptr(), planes.data_ptr(), 128, n, eng.partials.data_ptr(),
+                                      eng.norm_out.data_ptr(), 0, _stream()))
+    torch.cuda.synchronize()
+    assert torch.equal(a, eng.norm_out)
+
+
+def test_linear_attempt_nonfinite_and_output_window():
+    """Non-finite y1 elements are counted (rk_common.py:287 through the controller); an attempt whose end reaches the next
+    output time stores its stages without being asked to."""
+    rows = 333
+    n = rows * 128
+    # t0 = 0.5, dt = 0.0371, next output time 0.52 <= t0 + dt: the stages are needed by the interpolant fit
+    eng, _lib, _stream = _engine("dopri5", torch.float32, n, 0.0371, 0.5, 1.0, t_end=0.52)
+    lib = eng.lib
+    planes = _planes(lib, _lib, _weight(seed=11), _stream)
+    y0 = _rand(n, torch.float32, 1).to(DEV)
+    k0 = _rand(n, torch.float32, 2).to(DEV)
+    y0[5 * 128 + 7] = float("inf")
+    y0[100 * 128 + 1] = float("nan")
+    ks, y1, er, norm, ycand, kcand = _attempt_reference(eng, _lib, _stream, planes, y0, k0, n, 6)
+    outs = [None] + [torch.full((n,), float("nan"), device=DEV) for _ in range(6)]
+    y1a = torch.full((n,), float("nan"), device=DEV)
+    era = torch.full((n,), float("nan"), device=DEV)
+    kp = _lib.ptr_array([None] + [o.data_ptr() for o in outs[1:]])
+    _lib.check(lib.tdq_linear_attempt(eng.ctrl.data_ptr(), C.byref(eng.tab), 0, kp, y1a.data_ptr(), era.data_ptr(), y0.data_ptr(),
+                                      k0.data_ptr(), planes.data_ptr(), 128, n, eng.partials.data_ptr(), eng.norm_out.data_ptr(),
+                                      0, _stream()))
+    torch.cuda.synchronize()
+    assert float(norm[1]) > 0 and float(eng.norm_out[1]) == float(norm[1])
+    same = lambda a, b: torch.equal(a.view(torch.int32), b.view(torch.int32))
+    for i in range(1, 7):
+        assert same(outs[i], ks[i]), i
+    assert same(y1a, y1) and same(era, er)
+
+
+def test_linear_attempt_argument_checks():
+    eng, _lib, _stream = _engine("dopri5", torch.float32, 1280, 0.01)
+    lib = eng.lib
+    planes = _planes(lib, _lib, _weight(), _stream)
+    bufs = [torch.zeros(1280, device=DEV) for _ in range(9)]
+    kp = _lib.ptr_array([None] + [b.data_ptr() for b in bufs[:6]])
+    ctrl, tabp = eng.ctrl.data_ptr(), C.byref(eng.tab)
+    y1, er = bufs[6].data_ptr(), bufs[7].data_ptr()
+    ok = lambda rc: rc == 0
+    assert ok(lib.tdq_linear_attempt(ctrl, tabp, 0, kp, y1, er, None, None, planes.data_ptr(), 128, 1280, None, None, 1, _stream()))
+    assert not ok(lib.tdq_linear_attempt(ctrl, tabp, 1, kp, y1, er, None, None, planes.data_ptr(), 128, 1280, None, None, 1, _stream()))
+    assert not ok(lib.tdq_linear_attempt(ctrl, tabp, 0, kp, y1, er, None, None, planes.data_ptr(), 128, 1281, None, None, 1, _stream()))
+    assert not ok(lib.tdq_linear_attempt(ctrl, tabp, 0, kp, y1, er, None, None, planes.data_ptr(), 128, 1280,
+                                         eng.partials.data_ptr(), None, 1, _stream()))
+    for m, want in (("dopri5", 1), ("bosh3", 1), ("tsit5", 0), ("dopri8", 0), ("fehlberg2", 0), ("adaptive_heun", 0)):
+        e2, _, _ = _engine(m, torch.float32, 1280, 0.01)
+        assert lib.tdq_linear_attempt_supported(C.byref(e2.tab), 0, 128) == want, m
+        assert lib.tdq_linear_attempt_supported(C.byref(e2.tab), 1, 128) == 0
+    e8, _, _ = _engine("dopri8", torch.float32, 1280, 0.01)
+    k8 = _lib.ptr_array([None] + [bufs[0].data_ptr()] * 13)
+    assert not ok(lib.tdq_linear_attempt(e8.ctrl.data_ptr(), C.byref(e8.tab), 0, k8, y1, er, None, None, planes.data_ptr(), 128, 1280,
+                                         None, None, 1, _stream()))
+    torch.cuda.synchronize()
+
+
+@pytest.mark.parametrize("method", ["dopri5", "bosh3"])
+@pytest.mark.parametrize("batch", [100, 2048])
+def test_whole_attempt_solve_matches_stage_path(method, batch):
+    """One launch per attempt against one launch per stage: the same arithmetic per element, so the same step sequence (the
+    float64 sum of the squared error ratios is ordered differently: a borderline decision may flip) and the same solution to
+    round-off; outputs inside steps (the lazy fit reads the stored stages) included."""
+    A = P.skew_matrix(128, torch.float32).to(DEV)
+    f = tdq().LinearField(A)
+    y0 = torch.randn(batch, 128, generator=torch.Generator().manual_seed(1)).to(DEV)
+    t = torch.linspace(0, 2.0, 9).to(DEV)
+    ya, sa = _solve(f, y0, t, method)
+    ys, ss = _solve(f, y0, t, method, fused_attempt=False)
+    assert sa["fused_attempt"] and not ss["fused_attempt"] and ss["fused_linear"]
+    assert abs(sa["n_accept"] - ss["n_accept"]) <= 1 and abs(sa["n_reject"] - ss["n_reject"]) <= 1
+    assert sa["nfe"] == 2 + eng_stages(method) * (sa["n_accept"] + sa["n_reject"])
+    if (sa["n_accept"], sa["n_reject"]) == (ss["n_accept"], ss["n_reject"]):
+        assert torch.equal(ya, ys)
+    assert torch.allclose(ya, ys, rtol=1e-4, atol=2e-5), float((ya - ys).abs().max())
+    # lock step, run-ahead, graph + device loop: the same bits
+    b, _ = _solve(f, y0, t, method, graph=False, run_ahead=0)
+    c, _ = _solve(f, y0, t, method, graph=True)
+    assert torch.equal(ya, b) and torch.equal(ya, c)
+
+
+def test_whole_attempt_dense_and_events():
+    """Callers that keep every step (odeint_dense, events) get the stages of every attempt."""
+    A = P.skew_matrix(128, torch.float32).to(DEV)
+    f = tdq().LinearField(A)
+    y0 = torch.randn(64, 128, generator=torch.Generator().manual_seed(3)).to(DEV)
+    with torch.no_grad():
+        t0, t1 = torch.tensor(0.0, device=DEV), torch.tensor(1.5, device=DEV)
+        da = tdq().odeint_dense(f, y0, t0, t1, rtol=1e-5, atol=1e-7)
+        ds = tdq().odeint_dense(f, y0, t0, t1, rtol=1e-5, atol=1e-7, options={"fused_attempt": False})
+        for tq in (0.1, 0.77, 1.5):
+            tt = torch.tensor(tq, device=DEV)
+            assert torch.allclose(da(tt), ds(tt), rtol=1e-5, atol=1e-6)

@@ -323,9 +323,11 @@ class AdaptiveEngine:
             self.post_fn(buf)
         return buf
 
-    def set_linear(self, weight):
+    def set_linear(self, weight, whole_attempt=True):
         """Fuse the stage combination with func = y @ weight^T (torchdiffeq_b200.LinearField): tdq_linear_stage replaces
         tdq_stage_combine + the torch call for every row (rk_common.py:79-81 in one launch; csrc/tdq_linear.cu).
+        For dopri5 / bosh3 the whole attempt -- every stage, the error norm, the candidate commit -- is ONE launch
+        (tdq_linear_attempt, csrc/tdq_attempt.cu) unless whole_attempt=False.
         Returns False (and changes nothing) if a row of the tableau has more terms than the fused kernel takes."""
         width, S = int(weight.shape[0]), self.S
         if self.pieces is not None or self.post_fn is not None or self.n % width:
@@ -338,7 +340,11 @@ class AdaptiveEngine:
             if not 1 <= len(used) <= 8:
                 return False
         planes = torch.empty(int(self.lib.tdq_linear_weights_bytes(width)), dtype=torch.uint8, device=self.device)
-        self.linear = dict(weight=weight, width=width, planes=planes,
+        # the whole attempt in ONE launch (csrc/tdq_attempt.cu: all stages, error norm, candidate commit; FSAL tableaus of
+        # at most 7 stages); the squared norm is folded in when it is the plain one (one segment, scalar tolerances)
+        whole = bool(whole_attempt) and bool(self.lib.tdq_linear_attempt_supported(C.byref(self.tab), self.dt_code, width))
+        fold = (whole and self.norm_table is None and self.n_seg == 1 and self.rtol_vec is None and self.norm_fn is None)
+        self.linear = dict(weight=weight, width=width, planes=planes, whole=whole, fold=fold,
                            k=[torch.zeros(self.n, dtype=self.dtype, device=self.device) for _ in range(S)])
         self._drop_graph()
         return True
@@ -415,7 +421,21 @@ class AdaptiveEngine:
         S = self.S
         k = [None] * (S + 1)             # k[0] = NULL: the kernels read k_0 (and y0) through the pointer table
         keep = []
-        if self.linear is not None:
+        folded = False
+        if self.linear is not None and self.linear["whole"]:
+            # the whole attempt in one tcgen05 launch (csrc/tdq_attempt.cu): the stages, y1 and the error prefix reach
+            # memory only when an output time can fall into the attempt (or every step is kept)
+            L = self.linear
+            for i in range(S):
+                k[i + 1] = L["k"][i].data_ptr()
+            folded = L["fold"]
+            self._launch(lib.tdq_linear_attempt(ctrl, tab, dc, _lib.ptr_array(k), self.y1.data_ptr(), self.errp.data_ptr(),
+                                                None, None, L["planes"].data_ptr(), L["width"], self.n,
+                                                self.partials.data_ptr() if folded else None,
+                                                self.norm_out.data_ptr() if folded else None,
+                                                0 if folded else 1, st))
+            self.nfe += S
+        elif self.linear is not None:
             # combination + evaluation of every row in one tcgen05 launch (csrc/tdq_linear.cu); the FSAL row also writes
             # y1 and the error-sum prefix exactly as tdq_stage_combine_final does
             L = self.linear
@@ -446,13 +466,14 @@ class AdaptiveEngine:
                                                      _lib.ptr_array(k), self.n, st))
         kp = _lib.ptr_array(k)
         # error ratio + candidate commit (y1 -> ybuf[par^1], k_S -> kbuf[par^1]) in one pass
-        self._launch(lib.tdq_error_norm_commit(
-            ctrl, dc, self.errp.data_ptr(), k[S], None, self.y1.data_ptr(),
-            self.rtol_vec.data_ptr() if self.rtol_vec is not None else None,
-            self.atol_vec.data_ptr() if self.atol_vec is not None else None,
-            self.norm_table.data_ptr() if self.norm_table is not None else None, self.n_chunks, self.table_aligned,
-            self.n_seg, self.n, self.partials.data_ptr(), self.norm_out.data_ptr(),
-            self.qbuf.data_ptr() if self.qbuf is not None else None, st))
+        if not folded:
+            self._launch(lib.tdq_error_norm_commit(
+                ctrl, dc, self.errp.data_ptr(), k[S], None, self.y1.data_ptr(),
+                self.rtol_vec.data_ptr() if self.rtol_vec is not None else None,
+                self.atol_vec.data_ptr() if self.atol_vec is not None else None,
+                self.norm_table.data_ptr() if self.norm_table is not None else None, self.n_chunks, self.table_aligned,
+                self.n_seg, self.n, self.partials.data_ptr(), self.norm_out.data_ptr(),
+                self.qbuf.data_ptr() if self.qbuf is not None else None, st))
         ratio_ptr = None
         if self.norm_fn is not None:
             r = self.norm_fn(self.q_view(self.qbuf))

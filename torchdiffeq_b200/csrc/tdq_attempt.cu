@@ -1,0 +1,475 @@
+// tdq_attempt.cu -- a WHOLE Runge-Kutta attempt of a LINEAR vector field f(t, y) = y W^T in one launch: every stage
+// combination, every evaluation of the field, the error estimate, its squared norm and the candidate commit.
+//
+// Why this is possible: for a linear field an attempt is ROW-LOCAL.  k_i = (y0 + sum_j coef_ij k_j) W^T needs nothing from
+// other state rows, so a tile of rows can be taken through all S stages without leaving the SM: y0 and the k_j stay in
+// registers, the stage value goes to shared memory as the B operand of tcgen05.mma (three bfloat16 planes, as in
+// tdq_linear.cu), the product comes back from tensor memory.  HBM sees 2 reads (y0, k_0) and 2 writes (the candidate pair
+// y1, k_S) per element and attempt instead of the 34 + 6 of six fused stage launches plus the norm launch (tdq_linear.cu,
+// tdq_norm.cu), and one launch instead of seven; the attempt becomes tensor bound (S x 6 bf16 products per element).
+// What rk_common.py:43-90 (_runge_kutta_step), misc.py:80-82 (_compute_error_ratio up to the mean) and the assignment
+// y_next = y1, f_next = f1 of rk_common.py:341/:352 do, for the FSAL tableaus dopri5 and bosh3.
+//
+// Arithmetic is the stage kernels' arithmetic, operation for operation: products and sums of the combination rounded
+// separately in ascending j (rk_common.py:79), the same float32 -> hi + mid + lo split, the same six bf16 products in the
+// same accumulation order -- k_i, y1 and the error-sum prefix are BITWISE what tdq_linear_stage writes, (err/tol)^2 per
+// element bitwise what k_norm computes; only the order of the float64 sum over elements differs (tests/test_gpu_linear.py).
+//
+// Layout: 384 threads = 3 independent tile pipelines ("groups") of 4 warps, one CTA per SM.  A tile is 16 state rows x 128
+// features.  The accumulator is D^T (lane = output feature, column = state row; M = 128, N = 16), so thread (warp e, lane l)
+// of a group owns feature f = 32 e + l of all 16 rows: k_0..k_{S-1}[16] are 96 registers (dopri5; y0 sits in shared memory), a warp's
+// access to one row is 128 contiguous bytes of global memory, and the bf16 planes are written with 2-byte stores (32 lanes
+// = 64 contiguous bytes of a 128-byte swizzle row: conflict free).  Per stage a group does: combine + split + st.shared,
+// fence.proxy.async, bar.sync (its 128 threads), one thread issues 48 MMAs (weights stationary in tensor memory, 192
+// columns, shared by the groups) and a commit, everybody waits on the group's mbarrier and drains 2 x 16 columns.  The
+// chain of a tile is serial by nature (stage i+1 needs k_i); the three groups interleave, one hiding the other's latency.
+//
+// Stage derivatives, y1 and the error prefix are written to HBM only for attempts that can contain an output time (the
+// lazy interpolant fit needs them, tdq_interp.cu) or when the caller keeps every step (dense output, events).
+#include "tdq_shape.cuh"
+#include "tdq_tc.cuh"
+
+#include <type_traits>
+
+namespace {
+
+using namespace tdq_tc;
+
+constexpr int LD = 128;                        // state width = output features = GEMM K and M
+constexpr int AT_ROWS = 16;                    // state rows per tile = MMA N
+constexpr int AT_GROUPS = 3;
+constexpr int AT_THREADS = AT_GROUPS * 128;
+constexpr int AT_ATOM = AT_ROWS * 128;         // one swizzle-atom column of a tile: 16 rows x 128 B (64 bf16 of K)
+constexpr int AT_PLANE = 2 * AT_ATOM;          // K = 128
+constexpr int AT_STAGE = 3 * AT_PLANE;         // hi, mid, lo
+constexpr int AT_AUX = 1024;                   // barriers, tensor-memory slot, coefficient tables, reduction scratch
+constexpr int AT_Y0 = AT_ROWS * LD * 4;         // a tile's y0 (float32) stays in shared memory: read once per stage
+constexpr int AT_SMEM = AT_GROUPS * (AT_STAGE + AT_Y0) + AT_AUX + 1024;
+constexpr int AT_TMEM_COLS = 512;
+constexpr int AT_COL_W = 256;                  // weights: 3 planes x 64 columns; accumulators of group g: [32 g, 32 g + 32)
+constexpr int AT_MAX_S = 7;
+constexpr uint32_t IDESC16 = tc_idesc(AT_ROWS);
+
+// explicit shared-space accesses with 32-bit addresses (a pointer derived from the aligned dynamic shared memory base is
+// generic to the compiler: 64-bit address registers and generic ST/LD otherwise)
+// the two bfloat16 of a packed pair to two addresses
+__device__ __forceinline__ void sts_bf16x2(uint32_t addr_lo, uint32_t addr_hi, uint32_t v) {
+    asm volatile("{\n\t.reg .b16 lo, hi;\n\tmov.b32 {lo, hi}, %2;\n\tst.shared.b16 [%0], lo;\n\tst.shared.b16 [%1], hi;\n\t}\n"
+                 :: "r"(addr_lo), "r"(addr_hi), "r"(v) : "memory");
+}
+// one lane of a converged warp (the compiler keeps the operands of what follows in uniform registers)
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred = 0;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\t@p mov.s32 %0, 1;\n\t}\n" : "+r"(pred));
+    return pred != 0;
+}
+__device__ __forceinline__ void sts_f32(uint32_t addr, float v) { asm volatile("st.shared.f32 [%0], %1;" :: "r"(addr), "f"(v) : "memory"); }
+__device__ __forceinline__ float lds_f32(uint32_t addr) {
+    float v;
+    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr) : "memory");
+    return v;
+}
+
+struct AttOut {
+    float *k[AT_MAX_S + 1];                    // k[i], i = 1..S: where k_i goes when the attempt's stages are kept
+    float *y1, *err;
+};
+
+__host__ __device__ constexpr int popc_below(unsigned mask, int j) {
+    int n = 0;
+    for (int b = 0; b < j; ++b) n += (mask >> b) & 1u;
+    return n;
+}
+
+// S: stages of an FSAL tableau (rows 0..S-1, the last one is c_sol and yields y1).  RM: 8 bits per row, bit j set <=> slot j has
+// a non-zero coefficient in that row.  EM: the same for the error weights of slots 0..S-1 (k_S always carries the last one).
+template <int S, unsigned long long RM, unsigned EM>
+__global__ void __launch_bounds__(AT_THREADS, 1)
+k_linear_attempt(const TdqCtrl *__restrict__ c, const float *y0, const float *k0, AttOut out, const uint32_t *__restrict__ wt,
+                 double *partials, double *norm_out, int store_always, size_t n_rows_sz) {
+    if (c->halt) return;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint8_t *aux = smem + AT_GROUPS * (AT_STAGE + AT_Y0);
+    uint64_t *bars = reinterpret_cast<uint64_t *>(aux);                    // one "accumulators complete" barrier per group
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(aux + 32);
+    int *s_flag = reinterpret_cast<int *>(aux + 40);
+    float *s_cr = reinterpret_cast<float *>(aux + 64);                    // [S][8]: coef[i][m] as float32
+    float *s_ce = s_cr + AT_MAX_S * 8;                                    // [8]:    ecoef[m]
+    double *s_red = reinterpret_cast<double *>(aux + 512);                // [2][12]
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);                  // warp-uniform for the compiler as well
+    const int n_rows = (int)n_rows_sz;
+    const uint32_t bar0 = smem_u32(bars);
+
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(smem_u32(tmem_slot)), "n"(AT_TMEM_COLS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    if (tid == 32) {
+#pragma unroll
+        for (int g = 0; g < AT_GROUPS; ++g) mbar_init(bar0 + 8 * g, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (tid >= 64 && tid < 64 + AT_MAX_S * 8) {                           // this attempt's coefficients (prepare_tables)
+        const int i = (tid - 64) >> 3, m = (tid - 64) & 7;
+        s_cr[i * 8 + m] = (i < S) ? (float)c->coef[i][m] : 0.f;
+        if (i == 0) s_ce[m] = (float)c->ecoef[m];
+    }
+    fence_before();
+    __syncthreads();
+    fence_after();
+    const uint32_t tmem = __shfl_sync(0xffffffffu, *tmem_slot, 0);
+
+    const int g = warp >> 2, e = warp & 3, f = e * 32 + lane;             // this thread's tensor-memory lane = feature
+    const uint32_t lane_base = tmem + ((uint32_t)(e * 32) << 16);
+    {   // weights -> tensor memory, once: group g stores plane g (hi, mid, lo)
+#pragma unroll 1
+        for (int c0 = 0; c0 < 64; c0 += 32) {
+            uint32_t r[32];
+            const uint4 *src = reinterpret_cast<const uint4 *>(wt + ((size_t)g * LD + f) * 64 + c0);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const uint4 v = src[j];
+                r[4 * j] = v.x; r[4 * j + 1] = v.y; r[4 * j + 2] = v.z; r[4 * j + 3] = v.w;
+            }
+            tmem_st32(lane_base + AT_COL_W + g * 64 + c0, r);
+        }
+        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+    }
+    fence_before();
+    __syncthreads();
+    fence_after();
+
+    // ---- per-attempt scalars ---------------------------------------------------------------------------------
+    if (y0 == nullptr) y0 = reinterpret_cast<const float *>(c->y0_cur);
+    if (k0 == nullptr) k0 = reinterpret_cast<const float *>(c->k0_cur);
+    y0 = tdq_detach(y0, n_rows_sz);
+    k0 = tdq_detach(k0, n_rows_sz);
+    const bool fold = partials != nullptr;                                // squared error norm + candidate commit in here
+    float *ycand = nullptr, *kcand = nullptr;
+    if (fold && c->ybuf[0] != nullptr) {
+        ycand = tdq_detach(reinterpret_cast<float *>(c->ybuf[c->par ^ 1]), n_rows_sz);
+        kcand = tdq_detach(reinterpret_cast<float *>(c->kbuf[c->par ^ 1]), n_rows_sz);
+    }
+    // the stages of this attempt are needed afterwards only if an output time can fall into it (the controller's
+    // test `!(t_out[cursor] > t1)` for t1 = att_t1, rk_common.py:246) or the caller keeps every step
+    bool store = store_always != 0 || c->always_fit != 0;
+    if (!store) {
+        const int cur = c->out_cursor;
+        store = cur < c->n_out && !(c->t_out[cur] > c->att_t1);
+    }
+    const float rtolT = (float)c->rtol, atolT = (float)c->atol;
+    constexpr int EK = popc_below(EM, S);                                 // index of k_S's error weight in ecoef
+    const float ecS = s_ce[EK];
+
+    uint8_t *stage = smem + g * AT_STAGE;
+    const uint32_t sy0 = smem_u32(smem + AT_GROUPS * AT_STAGE + g * AT_Y0) + (uint32_t)f * 4;   // [row][feature], this thread's column
+    const uint32_t stage_u32 = smem_u32(stage);
+    const uint32_t bar = bar0 + 8 * g;
+    const uint32_t acc_big = tmem + g * 32, acc_small = tmem + g * 32 + 16;
+    uint32_t phase = 0;
+    // byte offset of (row r, feature f) in a plane: K-major, 128-byte swizzle -- (f >> 6) atoms, row r at r * 128, 16-byte
+    // chunk ((f & 63) >> 3) ^ (r & 7), element (f & 7)
+    const uint32_t f_off = (uint32_t)(f >> 6) * AT_ATOM + (uint32_t)(f & 7) * 2;
+    const uint32_t f_chunk = (uint32_t)(f & 63) >> 3;
+
+    const int tiles = (n_rows + AT_ROWS - 1) / AT_ROWS;
+    const int workers = (int)gridDim.x * AT_GROUPS;
+    double acc = 0.0;
+    int nbad = 0;
+
+    // One tile through all S stages.  FULL: all 16 rows exist (no per-row predicates); the one partial tile of a launch
+    // takes the predicated copy of the same code.
+    auto do_tile = [&](auto full_tag, const int t) {
+        constexpr bool FULL = decltype(full_tag)::value;
+        const int row0 = t * AT_ROWS;
+        const int rows_here = FULL ? AT_ROWS : n_rows - row0;
+        const size_t base = (size_t)row0 * LD + f;
+        float K[S][AT_ROWS];
+        {
+            float Y0[AT_ROWS];
+#pragma unroll
+            for (int r = 0; r < AT_ROWS; ++r) {
+                Y0[r] = 0.f;
+                K[0][r] = 0.f;
+                if (FULL || r < rows_here) {
+                    Y0[r] = __ldcs(y0 + base + (size_t)r * LD);
+                    K[0][r] = __ldcs(k0 + base + (size_t)r * LD);
+                }
+            }
+#pragma unroll
+            for (int r = 0; r < AT_ROWS; ++r) sts_f32(sy0 + r * LD * 4, Y0[r]);   // only this thread reads it back: no barrier
+        }
+        float EP[AT_ROWS], TOL[AT_ROWS];                                   // error-sum prefix, tolerance (last row)
+#pragma unroll
+        for (int i = 0; i < S; ++i) {
+            const unsigned mask = (unsigned)((RM >> (8 * i)) & 0xffull);
+            const bool last = i == S - 1;
+            float cr[S], ce[S];
+#pragma unroll
+            for (int j = 0; j < S; ++j) {
+                cr[j] = ((mask >> j) & 1u) ? s_cr[i * 8 + popc_below(mask, j)] : 0.f;
+                ce[j] = (last && ((EM >> j) & 1u)) ? s_ce[popc_below(EM, j)] : 0.f;
+            }
+            // ---- y_i = y0 + sum_j k_j coef_ij (ascending j over the non-zero terms, rounded separately), split, planes ----
+#pragma unroll
+            for (int r = 0; r < AT_ROWS; r += 2) {
+                float yv[2];
+#pragma unroll
+                for (int q = 0; q < 2; ++q) {
+                    float ar = 0.f, ae = 0.f;
+                    bool fr = true, fe = true;
+#pragma unroll
+                    for (int j = 0; j <= i; ++j) {
+                        if ((mask >> j) & 1u) {
+                            const float p = K[j][r + q] * cr[j];
+                            ar = fr ? p : ar + p;
+                            fr = false;
+                        }
+                        if (last && ((EM >> j) & 1u)) {
+                            const float p = K[j][r + q] * ce[j];
+                            ae = fe ? p : ae + p;
+                            fe = false;
+                        }
+                    }
+                    const float y0v = lds_f32(sy0 + (r + q) * LD * 4);
+                    yv[q] = y0v + ar;
+                    if (last) {
+                        EP[r + q] = ae;
+                        // tol = atol + rtol * max(|y0|, |y1|) (misc.py:81), as k_norm forms it
+                        TOL[r + q] = Ar<float>::add(atolT, Ar<float>::mul(rtolT, Ar<float>::max_nan(fabsf(y0v), fabsf(yv[q]))));
+                        if (FULL || r + q < rows_here) {
+                            if (!isfinite(yv[q])) nbad += 1;
+                            const size_t o = base + (size_t)(r + q) * LD;
+                            if (ycand) ycand[o] = yv[q];
+                            if (store) {
+                                out.y1[o] = yv[q];
+                                out.err[o] = ae;
+                            }
+                        }
+                    }
+                }
+                uint32_t h, m, l;
+                split2(yv[0], yv[1], h, m, l);
+                const uint32_t o0 = f_off + (uint32_t)r * 128 + ((f_chunk ^ (uint32_t)(r & 7)) << 4);
+                const uint32_t o1 = f_off + (uint32_t)(r + 1) * 128 + ((f_chunk ^ (uint32_t)((r + 1) & 7)) << 4);
+                sts_bf16x2(stage_u32 + o0, stage_u32 + o1, h);
+                sts_bf16x2(stage_u32 + AT_PLANE + o0, stage_u32 + AT_PLANE + o1, m);
+                sts_bf16x2(stage_u32 + 2 * AT_PLANE + o0, stage_u32 + 2 * AT_PLANE + o1, l);
+            }
+            // ---- k_{i+1} = y_i W^T ----
+            fence_async_smem();
+            fence_before();
+            asm volatile("bar.sync %0, 128;" :: "r"(g + 1) : "memory");
+            if (e == g && elect_one()) {                              // group g issues from sub-partition g
+                fence_after();
+                // weights plane PW (tensor memory) x stage plane PY (shared memory): the five cross terms >= 2^-16 in
+                // ascending magnitude into the small accumulator, hi.hi into the big one (tdq_linear.cu)
+                constexpr int NPROD = 6;
+                constexpr int PW[NPROD] = {1, 2, 0, 1, 0, 0}, PY[NPROD] = {1, 0, 2, 0, 1, 0};
+#pragma unroll
+                for (int p = 0; p < NPROD; ++p) {
+                    const uint32_t dcol = p == NPROD - 1 ? acc_big : acc_small;
+#pragma unroll
+                    for (int ks = 0; ks < 8; ++ks) {
+                        const uint32_t koff = (ks >> 2) * AT_ATOM + (ks & 3) * 32;
+                        mma_ts(dcol, tmem + AT_COL_W + PW[p] * 64 + ks * 8, make_desc(stage_u32 + PY[p] * AT_PLANE + koff), IDESC16,
+                               (p == 0 || p == NPROD - 1) && ks == 0 ? 0u : 1u);
+                    }
+                }
+                mma_commit(bar);
+            }
+            __syncwarp();
+            mbar_wait(bar, phase);
+            phase ^= 1u;
+            fence_after();
+            // drain: the small accumulator first, then the big one on top of it (16 registers of staging, not 32)
+            uint32_t tq[16];
+            float KN[AT_ROWS];
+            tmem_ld16(lane_base + (uint32_t)(g * 32 + 16), tq);
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+            for (int r = 0; r < AT_ROWS; ++r) KN[r] = __uint_as_float(tq[r]);
+            tmem_ld16(lane_base + (uint32_t)(g * 32), tq);
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+            for (int r = 0; r < AT_ROWS; ++r) KN[r] = KN[r] + __uint_as_float(tq[r]);
+            if (!last) {
+#pragma unroll
+                for (int r = 0; r < AT_ROWS; ++r) K[(i + 1) < S ? (i + 1) : 0][r] = KN[r];
+                if (store) {
+#pragma unroll
+                    for (int r = 0; r < AT_ROWS; ++r)
+                        if (FULL || r < rows_here) out.k[i + 1][base + (size_t)r * LD] = KN[r];
+                }
+            } else {
+                // ---- k_S: candidate commit, error ratio (misc.py:80-82 up to the mean) ----
+#pragma unroll
+                for (int r = 0; r < AT_ROWS; ++r) {
+                    if (FULL || r < rows_here) {
+                        const size_t o = base + (size_t)r * LD;
+                        if (kcand) kcand[o] = KN[r];
+                        if (store) out.k[S][o] = KN[r];
+                        if (fold) {
+                            const float num = Ar<float>::add(EP[r], Ar<float>::mul(KN[r], ecS));
+                            const float q = Ar<float>::div(num, TOL[r]);
+                            acc += (double)Ar<float>::mul(q, q);
+                        }
+                    }
+                }
+            }
+        }
+    };
+#pragma unroll 1
+    for (int t = g * (int)gridDim.x + (int)blockIdx.x; t < tiles; t += workers) {
+        if (n_rows - t * AT_ROWS >= AT_ROWS) do_tile(std::true_type{}, t);
+        else do_tile(std::false_type{}, t);
+    }
+    const double bad = (double)nbad;
+
+    // ---- per-CTA partial of the squared norm and of the non-finite count; the last CTA adds them in index order ----
+    if (fold) {
+        const double wa = warp_sum(acc), wb = warp_sum(bad);
+        if (lane == 0) {
+            s_red[warp] = wa;
+            s_red[12 + warp] = wb;
+        }
+    }
+    fence_before();
+    __syncthreads();
+    if (warp == 0) {
+        fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem), "n"(AT_TMEM_COLS) : "memory");
+    }
+    if (!fold) return;
+    const int P = (int)gridDim.x;
+    double *p_sum = partials + 2, *p_bad = p_sum + P;
+    unsigned int *ticket = reinterpret_cast<unsigned int *>(partials);
+    if (tid == 0) {
+        double a = 0.0, b = 0.0;
+        for (int w = 0; w < AT_THREADS / 32; ++w) {
+            a += s_red[w];
+            b += s_red[12 + w];
+        }
+        p_sum[blockIdx.x] = a;
+        p_bad[blockIdx.x] = b;
+        __threadfence();
+        const unsigned int tk = atomicAdd(ticket, 1u);
+        *s_flag = (tk == gridDim.x - 1) ? 1 : 0;
+    }
+    __syncthreads();
+    if (!*s_flag) return;
+    __threadfence();
+    if (warp == 0) {
+        double a = 0.0, b = 0.0;
+        for (int i = lane; i < P; i += 32) {
+            a += __ldcg(&p_sum[i]);
+            b += __ldcg(&p_bad[i]);
+        }
+        a = warp_sum(a);
+        b = warp_sum(b);
+        if (lane == 0) {
+            norm_out[0] = a;
+            norm_out[1] = b;
+            *ticket = 0;                                                  // self-reset for the next launch
+        }
+    }
+}
+
+// the sparsity of the supported FSAL tableaus (row masks 8 bits per row, error-prefix mask); tsit5 as the reference
+// tabulates it is not FSAL (its c_sol has a weight on k_S), fehlberg2 / adaptive_heun neither, dopri8 has 13 stages
+constexpr unsigned long long RM_DOPRI5 = 0x01ull | (0x03ull << 8) | (0x07ull << 16) | (0x0full << 24) | (0x1full << 32) | (0x3dull << 40);
+constexpr unsigned long long RM_BOSH3 = 0x01ull | (0x02ull << 8) | (0x07ull << 16);
+
+template <int S, unsigned long long RM, unsigned EM>
+int launch_attempt(const TdqCtrl *c, const float *y0, const float *k0, const AttOut &out, const uint32_t *wt, double *partials,
+                   double *norm_out, int store_always, size_t n_rows, cudaStream_t st) {
+    auto kern = k_linear_attempt<S, RM, EM>;
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM) != cudaSuccess) return -2;
+    const size_t tiles = (n_rows + AT_ROWS - 1) / AT_ROWS;
+    size_t grid = (tiles + AT_GROUPS - 1) / AT_GROUPS;
+    const size_t cap = (size_t)tdq_sm_count();
+    if (grid > cap) grid = cap;
+    if (grid == 0) grid = 1;
+    kern<<<(unsigned)grid, AT_THREADS, AT_SMEM, st>>>(c, y0, k0, out, wt, partials, norm_out, store_always, n_rows);
+    return 0;
+}
+
+// row / error masks of a tableau, or false if it is not FSAL with 2..AT_MAX_S stages and an error weight on k_S
+bool attempt_masks(const TdqHostShape &hs, unsigned long long *rm, unsigned *em) {
+    const int S = hs.n_stages;
+    if (!hs.fsal || S < 2 || S > AT_MAX_S) return false;
+    *rm = 0;
+    *em = 0;
+    for (int i = 0; i < S; ++i) {
+        unsigned m = 0;
+        for (int q = 0; q < hs.row_nnz[i]; ++q) {
+            if (hs.row_idx[i][q] > i) return false;
+            m |= 1u << hs.row_idx[i][q];
+        }
+        if (m == 0) return false;
+        *rm |= (unsigned long long)m << (8 * i);
+    }
+    bool has_S = false;
+    for (int q = 0; q < hs.err_nnz; ++q) {
+        if (hs.err_idx[q] == S) has_S = true;
+        else *em |= 1u << hs.err_idx[q];
+    }
+    return has_S && hs.err_idx[hs.err_nnz - 1] == S;
+}
+
+}  // namespace
+
+extern "C" {
+
+int tdq_linear_attempt_supported(const tdq_tableau *tab, int32_t dtype, int32_t width) {
+    if (!tab || dtype != TDQ_F32 || width != LD) return 0;
+    TdqHostShape hs;
+    tdq_shape_from_tableau(tab, &hs);
+    unsigned long long rm;
+    unsigned em;
+    if (!attempt_masks(hs, &rm, &em)) return 0;
+    const int S = hs.n_stages;
+    return ((S == 6 && rm == RM_DOPRI5 && em == 0x3du) || (S == 3 && rm == RM_BOSH3 && em == 0x07u)) ? 1 : 0;
+}
+
+int tdq_linear_attempt(void *ctrl_dev, const tdq_tableau *tab, int32_t dtype, void *const *k_out, void *y1_out, void *err_out,
+                       const void *y0, const void *k0, const void *planes, int32_t width, size_t n, double *partials,
+                       double *norm_out, int32_t store_always, void *stream) {
+    TDQ_REQUIRE(ctrl_dev && tab && k_out && y1_out && err_out && planes, "null argument");
+    TDQ_REQUIRE(dtype == TDQ_F32 && width == LD, "the fused linear field is float32, width 128");
+    TDQ_REQUIRE(n % (size_t)width == 0, "state size is not a multiple of the field width");
+    TDQ_REQUIRE((partials == nullptr) == (norm_out == nullptr), "partials and norm_out go together");
+    const size_t n_rows = n / (size_t)width;
+    TDQ_REQUIRE(n_rows < ((size_t)1 << 31) - 64, "too many rows");
+    TdqHostShape hs;
+    tdq_shape_from_tableau(tab, &hs);
+    unsigned long long rm = 0;
+    unsigned em = 0;
+    TDQ_REQUIRE(attempt_masks(hs, &rm, &em), "the whole-attempt kernel takes FSAL tableaus of at most 7 stages");
+    const int S = hs.n_stages;
+    AttOut out;
+    memset(&out, 0, sizeof(out));
+    for (int i = 1; i <= S; ++i) {
+        TDQ_REQUIRE(k_out[i] != nullptr, "missing stage slot");
+        out.k[i] = (float *)k_out[i];
+    }
+    out.y1 = (float *)y1_out;
+    out.err = (float *)err_out;
+    if (n_rows == 0) return TDQ_OK;
+    const TdqCtrl *c = (const TdqCtrl *)ctrl_dev;
+    const uint32_t *wt = (const uint32_t *)planes;
+    cudaStream_t st = (cudaStream_t)stream;
+    int rc = -1;
+    if (S == 6 && rm == RM_DOPRI5 && em == 0x3du)
+        rc = launch_attempt<6, RM_DOPRI5, 0x3du>(c, (const float *)y0, (const float *)k0, out, wt, partials, norm_out, store_always, n_rows, st);
+    else if (S == 3 && rm == RM_BOSH3 && em == 0x07u)
+        rc = launch_attempt<3, RM_BOSH3, 0x07u>(c, (const float *)y0, (const float *)k0, out, wt, partials, norm_out, store_always, n_rows, st);
+    TDQ_REQUIRE(rc != -1, "no whole-attempt kernel for this tableau (tdq_linear_attempt_supported)");
+    TDQ_REQUIRE(rc == 0, "launch configuration failed");
+    TDQ_CHECK_CUDA(cudaGetLastError());
+    return TDQ_OK;
+}
+
+}  // extern "C"

@@ -22,6 +22,7 @@
 // Measured on B200 (scripts/exp_fused_linear.cu, profiles/README.md), cold: 30 / 33 / 37 / 41 / 46 us for rows with 1..5
 // terms at 65536 x 128 (k_combine + cuBLAS SGEMM: 65 .. 89 us), 60 us for the last row with y1 and the error prefix.
 #include "tdq_shape.cuh"
+#include "tdq_tc.cuh"
 
 #include <cstdint>
 
@@ -44,16 +45,9 @@ struct LinK {
     const float *p[MAX_TERMS];
 };
 
-__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+using namespace tdq_tc;
 
-// two float32 -> packed bf16 pairs of the three planes (element 0 in the low half); the remainders are exact
-__device__ __forceinline__ void split2(float a, float b, uint32_t &h, uint32_t &m, uint32_t &l) {
-    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(h) : "f"(b), "f"(a));
-    const float ra = a - __uint_as_float(h << 16), rb = b - __uint_as_float(h & 0xffff0000u);
-    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(m) : "f"(rb), "f"(ra));
-    const float sa = ra - __uint_as_float(m << 16), sb = rb - __uint_as_float(m & 0xffff0000u);
-    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(l) : "f"(sb), "f"(sa));
-}
+constexpr uint32_t IDESC = tc_idesc(128);
 
 // elements [4q, 4q+4) of row r inside one plane: K-major, 128-byte swizzle (atoms of 8 rows x 128 B, 16-byte chunk
 // index XOR row mod 8), rows 128 B apart, the second 64 elements of K one ATOM further
@@ -75,52 +69,6 @@ __global__ void k_split_weights(const float *__restrict__ W, uint32_t *__restric
     wt[(0 * LD + n) * 64 + c] = h;
     wt[(1 * LD + n) * 64 + c] = m;
     wt[(2 * LD + n) * 64 + c] = l;
-}
-
-// UMMA shared-memory descriptor: start >> 4 in [0,14), leading byte offset (unused, 1) in [16,30), stride byte offset
-// 1024 >> 4 in [32,46), version 1 in [46,48), SWIZZLE_128B = 2 in [61,64)
-__device__ __forceinline__ uint64_t make_desc(uint32_t saddr) {
-    return (uint64_t)((saddr & 0x3FFFFu) >> 4) | (1ull << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
-}
-// instruction descriptor: D = f32, A = B = bf16, both K-major, N = 128 (>> 3 at [17,23)), M = 128 (>> 4 at [24,29))
-constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(128 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
-
-__device__ __forceinline__ void mma_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t db, uint32_t accumulate) {
-    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-                 "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}\n"
-                 :: "r"(tmem_d), "r"(tmem_a), "l"(db), "r"(IDESC), "r"(accumulate) : "memory");
-}
-__device__ __forceinline__ void mma_commit(uint32_t bar) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" :: "r"(bar) : "memory");
-}
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(bar), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
-    asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.shared::cta.b64 st, [%0];\n\t}\n" :: "r"(bar) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-    asm volatile("{\n\t.reg .pred p;\n\tWAIT_%=:\n\t"
-                 "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
-                 "@p bra DONE_%=;\n\tbra WAIT_%=;\n\tDONE_%=:\n\t}\n" :: "r"(bar), "r"(parity) : "memory");
-}
-__device__ __forceinline__ void fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-
-__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
-    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
-                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
-                   "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-                 : "r"(taddr) : "memory");
-}
-__device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&r)[32]) {
-    asm volatile("tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
-                 "{%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31,%32};"
-                 :: "r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]),
-                    "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]),
-                    "r"(r[16]), "r"(r[17]), "r"(r[18]), "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]),
-                    "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31]) : "memory");
 }
 
 // NU: stage terms read.  MODE 0: no control block, NU = 0 (k = y W^T).  MODE 1: a middle row (coef[row][m], m < NU).
@@ -299,7 +247,7 @@ k_linear_stage(const TdqCtrl *__restrict__ c, int row, const float *y0, LinK kp,
 #pragma unroll
                     for (int ks = 0; ks < 8; ++ks) {
                         const uint32_t koff = (ks >> 2) * ATOM_BYTES + (ks & 3) * 32;
-                        mma_ts(dcol, tmem + COL_W + PW[p] * 64 + ks * 8, make_desc(y_base + PY[p] * PLANE_BYTES + koff),
+                        mma_ts(dcol, tmem + COL_W + PW[p] * 64 + ks * 8, make_desc(y_base + PY[p] * PLANE_BYTES + koff), IDESC,
                                (p == 0 || p == NPROD - 1) && ks == 0 ? 0u : 1u);
                     }
                 }

@@ -32,7 +32,7 @@ _ADAPTIVE_OPTIONS = {"min_step", "max_step", "first_step", "step_t", "jump_t", "
                      "max_num_steps", "dtype", "norm"}
 _FIXED_OPTIONS = {"step_size", "grid_constructor", "interp", "perturb", "norm"}
 _ADAMS_OPTIONS = _FIXED_OPTIONS | {"max_iters", "max_order"}
-_OUR_OPTIONS = {"graph", "run_ahead", "process_group", "cache", "exchange", "device_loop", "fused_linear"}
+_OUR_OPTIONS = {"graph", "run_ahead", "process_group", "cache", "exchange", "device_loop", "fused_linear", "fused_attempt"}
 
 
 def _rms_norm(tensor):
@@ -298,7 +298,7 @@ def _make_adaptive_engine(p, method, rtol, atol, rtol_vec, atol_vec, options, fn
         from .fields import fusable
         w = fusable(getattr(p, "original_func", None), tuple(p.shape), p.dtype, p.device, eng.lib)
         if w is not None:
-            eng.set_linear(w)
+            eng.set_linear(w, whole_attempt=o.get("fused_attempt", True))
     return eng
 
 
@@ -694,7 +694,8 @@ def _odeint_backprop(p, func, y0, t, params, _stats):
         _LAST_STATS.clear()
         _LAST_STATS.update(nfe=eng.nfe, launches=getattr(eng, "launches", 0), attempts=getattr(eng, "n_attempts", None),
                            n_accept=getattr(eng, "n_accept", None), n_reject=getattr(eng, "n_reject", None),
-                       fused_linear=getattr(eng, "linear", None) is not None)
+                       fused_linear=getattr(eng, "linear", None) is not None,
+                       fused_attempt=bool((getattr(eng, "linear", None) or {}).get("whole")))
         if _stats is not None:
             _stats.update(_LAST_STATS)
     return _unflatten(p, sol)
@@ -737,7 +738,8 @@ def odeint(func, y0, t, *, rtol=1e-7, atol=1e-9, method=None, options=None, even
     _LAST_STATS.clear()
     _LAST_STATS.update(nfe=eng.nfe, launches=getattr(eng, "launches", 0), attempts=getattr(eng, "n_attempts", None),
                        n_accept=getattr(eng, "n_accept", None), n_reject=getattr(eng, "n_reject", None),
-                       fused_linear=getattr(eng, "linear", None) is not None)
+                       fused_linear=getattr(eng, "linear", None) is not None,
+                       fused_attempt=bool((getattr(eng, "linear", None) or {}).get("whole")))
     if _stats is not None:               # private: solver counters for bench.py and the tests
         _stats["nfe"] = eng.nfe
         _stats["launches"] = _stats.get("launches", 0) + getattr(eng, "launches", 0)
