@@ -66,6 +66,17 @@ def measured_peaks():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def measured_tensor_peak():
+    """Dense bf16 TFLOP/s: the burst figure (the probe times the kernel alone, a few milliseconds)."""
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            v = json.load(f).get("bf16_tflops")
+        if v:
+            return float(v), "measured (MEASURED_PEAKS.json bf16_tflops, burst)"
+    return 1700.0, "fallback (B200_PROFILING.md)"
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons sampled during the timed region."""
     Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
@@ -113,6 +124,8 @@ TRAFFIC_STATIC = {"bytes": 928.4e6, "source": "static: dram__bytes_read+write of
 TRAFFIC_FUSED = {"bytes": 946.1e6, "source": "static: dram__bytes_read+write of the six k_linear_stage launches of one attempt, ncu --set full "
                                                "(profiles/r2_ncu_full_fused_rows_summary.csv: reads 873 MB = the algorithmic reads, writes 73 MB -- most "
                                                "of the 268 MB written is still in L2 when a kernel ends); not measured by this run"}
+# the whole-attempt launch (k_linear_attempt): from the ncu --set full capture under profiles/
+TRAFFIC_ATTEMPT = {"bytes": None, "source": "see profiles/README.md (ncu --set full of k_linear_attempt)"}
 FULL_ATTEMPTS = 74         # step attempts of the full workload (reference, oracle and CUDA path agree)
 CPU_SAMPLE_T_END = 1.0     # the CPU sample integrates the FULL batch over t in [0, 1] (9 of the 74 attempts, + the start-up work)
 REF_DIR = os.path.join(ROOT, "baseline", "_ref")      # the unmodified reference, `pip install --target`
@@ -288,6 +301,18 @@ def roofline_probe(dev, n_elems, reps=20):
         frows = [lambda r=r: fused_row(r) for r in range(6)]
         res["fused_ms"] = timed(frows, reps)
         res["fused_group_ms"] = timed(frows + [norm], reps)
+        if lib.tdq_linear_attempt_supported(tab, dc, DIM):
+            # the WHOLE attempt in one launch (csrc/tdq_attempt.cu), as the engine issues it: the squared error norm and the
+            # candidate commit folded in, stages not stored.  Three rotating (y0, k_0) input pairs (201 MB) + the 67 MB of
+            # candidates it writes: nothing a launch reads is left in L2 by the previous one
+            pairs = [(y0, ks[0]), (ks[1], ks[2]), (ks[3], ks[4])]
+            kout = _lib.ptr_array([None] + [ks[6].data_ptr()] * 6)
+
+            def attempt(pair):
+                _lib.check(lib.tdq_linear_attempt(ctrl, tab, dc, kout, outs[1].data_ptr(), errp.data_ptr(), pair[0].data_ptr(),
+                                                  pair[1].data_ptr(), planes.data_ptr(), DIM, n_elems, eng.partials.data_ptr(),
+                                                  eng.norm_out.data_ptr(), None, 0, _stream()))
+            res["attempt_ms"] = timed([lambda p=p: attempt(p) for p in pairs], reps) / len(pairs)
     return res
 
 
@@ -426,8 +451,9 @@ def run_ours(args):
                        "batch_per_gpu": rows, "dim": DIM,
                        "exec": ("cuda-graph step body inside a device-side while loop (one launch per solve)"
                                 if not args.no_device_loop else "cuda-graph step body replayed by the host, run_ahead=2"),
-                       "func": ("torchdiffeq_b200.LinearField(A): forward(t, y) = y @ A^T; each stage (combination + field) is one "
-                                "tcgen05 kernel, split-bf16 float32-grade product (tdq_linear.cu)" if fused else
+                       "func": ("torchdiffeq_b200.LinearField(A): forward(t, y) = y @ A^T; a whole attempt (6 stage combinations, 6 field "
+                                "evaluations, error norm, candidate commit) is ONE tcgen05 kernel, split-bf16 float32-grade products "
+                                "(tdq_attempt.cu)" if fused else
                                 "plain nn.Module y @ A^T (cuBLAS fp32 SIMT SGEMM, 6 per attempt, ~60 % of a step)"),
                        "attempts_per_solve": stats.get("attempts"), "nfe_per_solve": stats.get("nfe"),
                        "l2": "working set 20 arrays x 33.5 MB >> 126 MB L2 (no flush needed)",
@@ -456,7 +482,7 @@ def run_ours(args):
             fused_bytes = comb_bytes + 2 * n_elems * 4                        # 34*N*s: y_i is never written or re-read
             fms, fgms = probe["fused_ms"], probe["fused_group_ms"]
             flops = 6 * 6 * 2.0 * B_PER_GPU * DIM * DIM                       # six bf16 products per float32 product
-            line["roofline"] = {
+            stage_roof = {
                 "bound": "hbm", "kernel": "k_linear_stage (6 launches per attempt: stage combination + linear field, tcgen05)",
                 "achieved": fused_bytes / (fms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
                 "frac": fused_bytes / (fms * 1e-3) / 1e9 / peak, "peak_source": peak_src,
@@ -466,8 +492,34 @@ def run_ours(args):
                            "note": "6 bf16 MMA passes per float32 product; the kernel is HBM bound, the tensor pipe is ~20 % busy"},
                 "stage_plus_error_norm": {"achieved": (fused_bytes + norm_bytes) / (fgms * 1e-3) / 1e9,
                                           "frac": (fused_bytes + norm_bytes) / (fgms * 1e-3) / 1e9 / peak,
-                                          "bytes": fused_bytes + norm_bytes, "ms": fgms},
-                "generic_path_kernel": k_combine_roof}
+                                          "bytes": fused_bytes + norm_bytes, "ms": fgms}}
+            if "attempt_ms" in probe and stats.get("fused_attempt"):
+                # ONE launch per attempt: y0, k_0 in, the candidate pair out (4*N*s), everything else on chip -- the kernel
+                # is bound by the tensor pipe (6 bf16 products per float32 product, S stages) and the CUDA cores that
+                # form, split and store the stage values, not by HBM
+                ams = probe["attempt_ms"]
+                tpeak, tsrc = measured_tensor_peak()
+                att_bytes = 4 * n_elems * 4
+                line["roofline"] = {
+                    "bound": "tensor",
+                    "kernel": "k_linear_attempt (1 launch per attempt: 6 stage combinations + 6 field evaluations + error norm + "
+                              "candidate commit, tcgen05 with the stage values resident on chip; csrc/tdq_attempt.cu)",
+                    "achieved": flops / (ams * 1e-3) / 1e12, "peak": tpeak, "unit": "TFLOP/s",
+                    "frac": flops / (ams * 1e-3) / 1e12 / tpeak, "peak_source": tsrc,
+                    "flop_per_launch": flops,
+                    "flop_counted": "bf16 tensor flops issued: 2 x 65536 x 128 x 128 per product, six bf16 products per float32 "
+                                    "product (hi/mid/lo split, float32-grade result), six stages",
+                    "float32_equivalent_tflops": flops / 6 / (ams * 1e-3) / 1e12,
+                    "traffic": TRAFFIC_ATTEMPT["bytes"], "traffic_source": TRAFFIC_ATTEMPT["source"],
+                    "ms_per_attempt": ams, "launches_per_attempt": 1,
+                    "hbm": {"algorithmic_bytes_per_attempt": att_bytes, "achieved_gbs": att_bytes / (ams * 1e-3) / 1e9,
+                            "frac_of_hbm_peak": att_bytes / (ams * 1e-3) / 1e9 / peak,
+                            "note": "2 reads + 2 writes per element: the six launches it replaces moved 34 + 6 per element"},
+                    "replaces": {"launches": 7, "ms": fgms, "speedup": fgms / ams},
+                    "stage_kernels": stage_roof, "generic_path_kernel": k_combine_roof}
+            else:
+                stage_roof["generic_path_kernel"] = k_combine_roof
+                line["roofline"] = stage_roof
         else:
             k_combine_roof.update({"bound": "hbm", "peak_source": peak_src})
             line["roofline"] = k_combine_roof

@@ -338,11 +338,14 @@ int tdq_linear_stage(void *ctrl_dev, const tdq_tableau *tab, int32_t dtype, int3
  * control block keeps every step (always_fit) or when store_always != 0 -- the lazy interpolant fit is their only reader.
  * partials / norm_out (both or neither): norm_out[0] = sum over the state of ((err_pre + k_S e_S) / (atol + rtol max(|y0|,|y1|)))^2,
  * norm_out[1] = number of non-finite y1 elements (what tdq_error_norm_commit writes for one segment), and y1 -> ybuf[par^1],
- * k_S -> kbuf[par^1]; partials needs tdq_norm_partials_len doubles, zeroed once.  Scalar tolerances only.  No-op after halt. */
+ * k_S -> kbuf[par^1]; partials needs tdq_norm_partials_len doubles, zeroed once.  Scalar tolerances only.  No-op after halt.
+ * seg_counts_dev != NULL (needs partials / norm_out): the last block to finish also performs the controller step, exactly
+ * what tdq_controller(ctrl, dtype, norm_out, seg_counts_dev, 1, NULL) would do next (rk_common.py:323-361, misc.py:85-95,
+ * the peer exchange of a sharded solve included) -- the caller then skips that launch. */
 int tdq_linear_attempt_supported(const tdq_tableau *tab, int32_t dtype, int32_t width);
 int tdq_linear_attempt(void *ctrl_dev, const tdq_tableau *tab, int32_t dtype, void *const *k_out, void *y1_out, void *err_out,
                        const void *y0, const void *k0, const void *planes, int32_t width, size_t n, double *partials,
-                       double *norm_out, int32_t store_always, void *stream);
+                       double *norm_out, const int64_t *seg_counts_dev, int32_t store_always, void *stream);
 
 /* interp='cubic' (solvers.py:120-125, :166-173): for records r in [rec_lo, rec_hi) of one step
  * solution[out_idx[r]] = h00*y0 + (h10*dt)*f0 + h01*y1 + (h11*dt)*f1 with the four weights of record r at

@@ -25,7 +25,7 @@ def attempt_whole(s, store=0, fold=True):
     st = sets[s % NS]
     _lib.check(lib.tdq_linear_attempt(ctrl, tabp, dc, kp_out, y1.data_ptr(), er.data_ptr(), st[0].data_ptr(), st[1].data_ptr(),
                                       planes.data_ptr(), 128, n, eng.partials.data_ptr() if fold else None,
-                                      eng.norm_out.data_ptr() if fold else None, store, _stream()))
+                                      eng.norm_out.data_ptr() if fold else None, None, store, _stream()))
 
 def attempt_stages(s):
     st = sets[s % NS]
@@ -52,6 +52,21 @@ def timeit(name, fn, reps=15):
     print("%-58s %9.1f us" % (name, us), flush=True)
     return us
 
+# reference for a bitwise check of every variant
+attempt_stages(0)
+torch.cuda.synchronize()
+ref = [k.clone() for k in ks] + [y1.clone(), er.clone(), eng.norm_out.clone()]
+for grp in ("3", "4", "5"):
+    os.environ["TDQ_ATTEMPT_GROUPS"] = grp
+    for k in ks:
+        k.zero_()
+    attempt_whole(0, 1, True)
+    torch.cuda.synchronize()
+    got = [k.clone() for k in ks] + [y1.clone(), er.clone(), eng.norm_out.clone()]
+    ok = all(torch.equal(a_, b_) for a_, b_ in zip(got[:-1], ref[:-1]))
+    print("groups", grp, "bitwise", ok, "norm rel diff", float((got[-1][0] - ref[-1][0]).abs() / ref[-1][0]))
+    timeit("%s whole attempt [%s groups], norm folded, stages not stored" % (method, grp), lambda i: attempt_whole(i, 0, True))
+os.environ["TDQ_ATTEMPT_GROUPS"] = os.environ.get("MB_GROUPS", "4")
 a = timeit("%s whole attempt, norm folded, stages not stored" % method, lambda i: attempt_whole(i, 0, True))
 b = timeit("%s whole attempt, norm folded, stages stored" % method, lambda i: attempt_whole(i, 1, True))
 c = timeit("%s whole attempt, no norm, stages stored" % method, lambda i: attempt_whole(i, 1, False))

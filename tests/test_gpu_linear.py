@@ -320,7 +320,7 @@ def test_linear_attempt_equals_stage_sequence(method, rows, t_sign):
         _lib.check(lib.tdq_linear_attempt(eng.ctrl.data_ptr(), C.byref(eng.tab), 0, kp, y1a.data_ptr(), era.data_ptr(),
                                           y0.data_ptr(), k0.data_ptr(), planes.data_ptr(), 128, n,
                                           eng.partials.data_ptr() if fold else None, eng.norm_out.data_ptr() if fold else None,
-                                          store_always, _stream()))
+                                          None, store_always, _stream()))
         torch.cuda.synchronize()
         if store_always:
             for i in range(1, S + 1):
@@ -341,7 +341,7 @@ def test_linear_attempt_equals_stage_sequence(method, rows, t_sign):
     a = eng.norm_out.clone()
     _lib.check(lib.tdq_linear_attempt(eng.ctrl.data_ptr(), C.byref(eng.tab), 0, kp, y1a.data_ptr(), era.data_ptr(),
                                       y0.data_ptr(), k0.data_ptr(), planes.data_ptr(), 128, n, eng.partials.data_ptr(),
-                                      eng.norm_out.data_ptr(), 0, _stream()))
+                                      eng.norm_out.data_ptr(), None, 0, _stream()))
     torch.cuda.synchronize()
     assert torch.equal(a, eng.norm_out)
 
@@ -366,7 +366,7 @@ def test_linear_attempt_nonfinite_and_output_window():
     kp = _lib.ptr_array([None] + [o.data_ptr() for o in outs[1:]])
     _lib.check(lib.tdq_linear_attempt(eng.ctrl.data_ptr(), C.byref(eng.tab), 0, kp, y1a.data_ptr(), era.data_ptr(), y0.data_ptr(),
                                       k0.data_ptr(), planes.data_ptr(), 128, n, eng.partials.data_ptr(), eng.norm_out.data_ptr(),
-                                      0, _stream()))
+                                      None, 0, _stream()))
     torch.cuda.synchronize()
     assert float(norm[1]) > 0 and float(eng.norm_out[1]) == float(norm[1])
     same = lambda a, b: torch.equal(a.view(torch.int32), b.view(torch.int32))
@@ -384,11 +384,14 @@ def test_linear_attempt_argument_checks():
     ctrl, tabp = eng.ctrl.data_ptr(), C.byref(eng.tab)
     y1, er = bufs[6].data_ptr(), bufs[7].data_ptr()
     ok = lambda rc: rc == 0
-    assert ok(lib.tdq_linear_attempt(ctrl, tabp, 0, kp, y1, er, None, None, planes.data_ptr(), 128, 1280, None, None, 1, _stream()))
-    assert not ok(lib.tdq_linear_attempt(ctrl, tabp, 1, kp, y1, er, None, None, planes.data_ptr(), 128, 1280, None, None, 1, _stream()))
-    assert not ok(lib.tdq_linear_attempt(ctrl, tabp, 0, kp, y1, er, None, None, planes.data_ptr(), 128, 1281, None, None, 1, _stream()))
+    assert ok(lib.tdq_linear_attempt(ctrl, tabp, 0, kp, y1, er, None, None, planes.data_ptr(), 128, 1280, None, None, None, 1, _stream()))
+    assert not ok(lib.tdq_linear_attempt(ctrl, tabp, 1, kp, y1, er, None, None, planes.data_ptr(), 128, 1280, None, None, None, 1, _stream()))
+    assert not ok(lib.tdq_linear_attempt(ctrl, tabp, 0, kp, y1, er, None, None, planes.data_ptr(), 128, 1281, None, None, None, 1, _stream()))
     assert not ok(lib.tdq_linear_attempt(ctrl, tabp, 0, kp, y1, er, None, None, planes.data_ptr(), 128, 1280,
-                                         eng.partials.data_ptr(), None, 1, _stream()))
+                                         eng.partials.data_ptr(), None, None, 1, _stream()))
+    # the controller step needs the folded norm
+    assert not ok(lib.tdq_linear_attempt(ctrl, tabp, 0, kp, y1, er, None, None, planes.data_ptr(), 128, 1280,
+                                         None, None, eng.seg_counts.data_ptr(), 1, _stream()))
     for m, want in (("dopri5", 1), ("bosh3", 1), ("tsit5", 0), ("dopri8", 0), ("fehlberg2", 0), ("adaptive_heun", 0)):
         e2, _, _ = _engine(m, torch.float32, 1280, 0.01)
         assert lib.tdq_linear_attempt_supported(C.byref(e2.tab), 0, 128) == want, m
@@ -396,7 +399,7 @@ def test_linear_attempt_argument_checks():
     e8, _, _ = _engine("dopri8", torch.float32, 1280, 0.01)
     k8 = _lib.ptr_array([None] + [bufs[0].data_ptr()] * 13)
     assert not ok(lib.tdq_linear_attempt(e8.ctrl.data_ptr(), C.byref(e8.tab), 0, k8, y1, er, None, None, planes.data_ptr(), 128, 1280,
-                                         None, None, 1, _stream()))
+                                         None, None, None, 1, _stream()))
     torch.cuda.synchronize()
 
 
@@ -418,10 +421,12 @@ def test_whole_attempt_solve_matches_stage_path(method, batch):
     if (sa["n_accept"], sa["n_reject"]) == (ss["n_accept"], ss["n_reject"]):
         assert torch.equal(ya, ys)
     assert torch.allclose(ya, ys, rtol=1e-4, atol=2e-5), float((ya - ys).abs().max())
-    # lock step, run-ahead, graph + device loop: the same bits
+    # lock step, run-ahead, graph + device loop: the same bits; the controller step as its own launch too
     b, _ = _solve(f, y0, t, method, graph=False, run_ahead=0)
     c, _ = _solve(f, y0, t, method, graph=True)
-    assert torch.equal(ya, b) and torch.equal(ya, c)
+    d, sd = _solve(f, y0, t, method, fused_controller=False)
+    assert torch.equal(ya, b) and torch.equal(ya, c) and torch.equal(ya, d)
+    assert (sd["n_accept"], sd["n_reject"]) == (sa["n_accept"], sa["n_reject"])
 
 
 def test_whole_attempt_dense_and_events():
@@ -436,3 +441,38 @@ def test_whole_attempt_dense_and_events():
         for tq in (0.1, 0.77, 1.5):
             tt = torch.tensor(tq, device=DEV)
             assert torch.allclose(da(tt), ds(tt), rtol=1e-5, atol=1e-6)
+
+
+@pytest.mark.parametrize("method,dt,accepted", [("dopri5", 1e-7, 1), ("dopri5", 0.0371, 0), ("bosh3", 1e-7, 1)])
+def test_linear_attempt_with_controller_step(method, dt, accepted):
+    """seg_counts given: the last block of tdq_linear_attempt runs the controller step.  The control block afterwards is
+    bit for bit what tdq_linear_attempt + tdq_controller leave behind (accepted and rejected attempts)."""
+    rows = 777
+    n = rows * 128
+    eng, _lib, _stream = _engine(method, torch.float32, n, dt, 0.5, 1.0)
+    lib = eng.lib
+    S = O.tableau(method)["n_stages"]
+    planes = _planes(lib, _lib, _weight(seed=11), _stream)
+    y0 = _rand(n, torch.float32, 1).to(DEV)
+    k0 = _rand(n, torch.float32, 2).to(DEV)
+    outs = [None] + [torch.zeros(n, device=DEV) for _ in range(S)]
+    y1a, era = torch.zeros(n, device=DEV), torch.zeros(n, device=DEV)
+    kp = _lib.ptr_array([None] + [o.data_ptr() for o in outs[1:]])
+    ctrl0 = eng.ctrl.clone()
+
+    def run(with_ctrl):
+        eng.ctrl.copy_(ctrl0)
+        eng.norm_out.zero_()
+        _lib.check(lib.tdq_linear_attempt(eng.ctrl.data_ptr(), C.byref(eng.tab), 0, kp, y1a.data_ptr(), era.data_ptr(), y0.data_ptr(),
+                                          k0.data_ptr(), planes.data_ptr(), 128, n, eng.partials.data_ptr(), eng.norm_out.data_ptr(),
+                                          eng.seg_counts.data_ptr() if with_ctrl else None, 0, _stream()))
+        if not with_ctrl:
+            _lib.check(lib.tdq_controller(eng.ctrl.data_ptr(), 0, eng.norm_out.data_ptr(), eng.seg_counts.data_ptr(), 1, None, _stream()))
+        torch.cuda.synchronize()
+        return eng.ctrl.clone(), eng.mbox_host.contents.accept, eng.mbox_host.contents.seq
+
+    a, acc_a, _ = run(False)
+    b, acc_b, _ = run(True)
+    assert torch.equal(a, b)
+    assert acc_a == acc_b == accepted          # random slopes: only a tiny step passes the error test
+    assert not torch.equal(a, ctrl0)

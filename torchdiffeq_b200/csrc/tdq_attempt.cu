@@ -28,7 +28,9 @@
 // lazy interpolant fit needs them, tdq_interp.cu) or when the caller keeps every step (dense output, events).
 #include "tdq_shape.cuh"
 #include "tdq_tc.cuh"
+#include "tdq_ctrl_dev.cuh"
 
+#include <cstdlib>
 #include <type_traits>
 
 namespace {
@@ -37,25 +39,41 @@ using namespace tdq_tc;
 
 constexpr int LD = 128;                        // state width = output features = GEMM K and M
 constexpr int AT_ROWS = 16;                    // state rows per tile = MMA N
-constexpr int AT_GROUPS = 3;
-constexpr int AT_THREADS = AT_GROUPS * 128;
-constexpr int AT_ATOM = AT_ROWS * 128;         // one swizzle-atom column of a tile: 16 rows x 128 B (64 bf16 of K)
-constexpr int AT_PLANE = 2 * AT_ATOM;          // K = 128
+constexpr int AT_PLANE = AT_ROWS * LD * 2;      // one bfloat16 plane of a tile: 16 rows x 128 features
 constexpr int AT_STAGE = 3 * AT_PLANE;         // hi, mid, lo
 constexpr int AT_AUX = 1024;                   // barriers, tensor-memory slot, coefficient tables, reduction scratch
 constexpr int AT_Y0 = AT_ROWS * LD * 4;         // a tile's y0 (float32) stays in shared memory: read once per stage
-constexpr int AT_SMEM = AT_GROUPS * (AT_STAGE + AT_Y0) + AT_AUX + 1024;
+// G: tile pipelines (groups of 4 warps) per CTA
+constexpr int at_smem(int G) { return G * (AT_STAGE + AT_Y0) + AT_AUX + 1024; }
 constexpr int AT_TMEM_COLS = 512;
 constexpr int AT_COL_W = 256;                  // weights: 3 planes x 64 columns; accumulators of group g: [32 g, 32 g + 32)
 constexpr int AT_MAX_S = 7;
-constexpr uint32_t IDESC16 = tc_idesc(AT_ROWS);
+constexpr uint32_t IDESC16 = tc_idesc(AT_ROWS) | (1u << 16);   // B (the stage planes) is MN-major: bit 16
+
+// Stage planes: MN-major, no swizzle.  Core matrix = 8 rows (MN, contiguous: 16 bytes) x 8 features (K, 16 bytes apart) =
+// 128 contiguous bytes; core matrices 128 B apart along K (leading byte offset), 2048 B apart along the rows (stride byte
+// offset).  Element (row n, feature k) of a plane sits at (n >> 3) * 2048 + (k >> 3) * 128 + (k & 7) * 16 + (n & 7) * 2, so the
+// thread that owns feature k stores rows 0-7 and rows 8-15 as two 16-byte vectors, and a warp's store is 512 contiguous bytes.
+constexpr uint32_t AT_LBO = 128, AT_SBO = 2048;
+// descriptor: start >> 4 in [0,14), leading byte offset >> 4 in [16,30), stride byte offset >> 4 in [32,46), version 1 in
+// [46,48), layout type 0 (no swizzle) in [61,64)  (verified on a B200: LBO is the K direction, SBO the MN direction)
+__device__ __forceinline__ uint64_t make_desc_mn(uint32_t saddr) {
+    return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)(AT_LBO >> 4) << 16) | ((uint64_t)(AT_SBO >> 4) << 32) | (1ull << 46);
+}
+__device__ __forceinline__ void sts_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" :: "r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
 
 // explicit shared-space accesses with 32-bit addresses (a pointer derived from the aligned dynamic shared memory base is
 // generic to the compiler: 64-bit address registers and generic ST/LD otherwise)
-// the two bfloat16 of a packed pair to two addresses
-__device__ __forceinline__ void sts_bf16x2(uint32_t addr_lo, uint32_t addr_hi, uint32_t v) {
-    asm volatile("{\n\t.reg .b16 lo, hi;\n\tmov.b32 {lo, hi}, %2;\n\tst.shared.b16 [%0], lo;\n\tst.shared.b16 [%1], hi;\n\t}\n"
-                 :: "r"(addr_lo), "r"(addr_hi), "r"(v) : "memory");
+// A value that is zero at run time but depends on every element of `a`: added to the address of the mbarrier the group is
+// about to wait on, it forces the arithmetic of the MMA window to be issued BEFORE the wait (ptxas otherwise sinks part of it
+// below the wait, onto the critical path).  `zero` is a run-time zero the compiler cannot fold.  8 LOP3 per array.
+__device__ __forceinline__ uint32_t dep16(const float (&a)[16], uint32_t zero) {
+    uint32_t x = 0;
+#pragma unroll
+    for (int r = 0; r < 16; ++r) x ^= __float_as_uint(a[r]);
+    return x & zero;
 }
 // one lane of a converged warp (the compiler keeps the operands of what follows in uniform registers)
 __device__ __forceinline__ bool elect_one() {
@@ -83,20 +101,24 @@ __host__ __device__ constexpr int popc_below(unsigned mask, int j) {
 
 // S: stages of an FSAL tableau (rows 0..S-1, the last one is c_sol and yields y1).  RM: 8 bits per row, bit j set <=> slot j has
 // a non-zero coefficient in that row.  EM: the same for the error weights of slots 0..S-1 (k_S always carries the last one).
-template <int S, unsigned long long RM, unsigned EM>
-__global__ void __launch_bounds__(AT_THREADS, 1)
-k_linear_attempt(const TdqCtrl *__restrict__ c, const float *y0, const float *k0, AttOut out, const uint32_t *__restrict__ wt,
-                 double *partials, double *norm_out, int store_always, size_t n_rows_sz) {
+// CTRL: the last block to finish also runs the controller step (tdq_ctrl_dev.cuh: accept / reject, next step size, the next
+// attempt's tables, the device-side loop's condition) -- one launch per attempt instead of two.  That instantiation carries a
+// device-runtime call (cudaGraphSetConditional), which kernel-level profilers refuse; the CTRL = false one is what ncu sees.
+template <int S, unsigned long long RM, unsigned EM, int G, bool CTRL>
+__global__ void __launch_bounds__(G * 128, 1)
+k_linear_attempt(TdqCtrl *c, const float *y0, const float *k0, AttOut out, const uint32_t *__restrict__ wt,
+                 double *partials, double *norm_out, const int64_t *seg_counts, int store_always, size_t n_rows_sz) {
     if (c->halt) return;
     extern __shared__ uint8_t smem_raw[];
     uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-    uint8_t *aux = smem + AT_GROUPS * (AT_STAGE + AT_Y0);
+    constexpr int AT_GROUPS = G, AT_THREADS = G * 128;
+    uint8_t *aux = smem + G * (AT_STAGE + AT_Y0);
     uint64_t *bars = reinterpret_cast<uint64_t *>(aux);                    // one "accumulators complete" barrier per group
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(aux + 32);
     int *s_flag = reinterpret_cast<int *>(aux + 40);
     float *s_cr = reinterpret_cast<float *>(aux + 64);                    // [S][8]: coef[i][m] as float32
     float *s_ce = s_cr + AT_MAX_S * 8;                                    // [8]:    ecoef[m]
-    double *s_red = reinterpret_cast<double *>(aux + 512);                // [2][12]
+    double *s_red = reinterpret_cast<double *>(aux + 512);                // [2][20]
     const int tid = threadIdx.x, lane = tid & 31;
     const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);                  // warp-uniform for the compiler as well
     const int n_rows = (int)n_rows_sz;
@@ -123,7 +145,7 @@ k_linear_attempt(const TdqCtrl *__restrict__ c, const float *y0, const float *k0
 
     const int g = warp >> 2, e = warp & 3, f = e * 32 + lane;             // this thread's tensor-memory lane = feature
     const uint32_t lane_base = tmem + ((uint32_t)(e * 32) << 16);
-    {   // weights -> tensor memory, once: group g stores plane g (hi, mid, lo)
+    if (g < 3) {   // weights -> tensor memory, once: group g stores plane g (hi, mid, lo)
 #pragma unroll 1
         for (int c0 = 0; c0 < 64; c0 += 32) {
             uint32_t r[32];
@@ -169,100 +191,88 @@ k_linear_attempt(const TdqCtrl *__restrict__ c, const float *y0, const float *k0
     const uint32_t bar = bar0 + 8 * g;
     const uint32_t acc_big = tmem + g * 32, acc_small = tmem + g * 32 + 16;
     uint32_t phase = 0;
-    // byte offset of (row r, feature f) in a plane: K-major, 128-byte swizzle -- (f >> 6) atoms, row r at r * 128, 16-byte
-    // chunk ((f & 63) >> 3) ^ (r & 7), element (f & 7)
-    const uint32_t f_off = (uint32_t)(f >> 6) * AT_ATOM + (uint32_t)(f & 7) * 2;
-    const uint32_t f_chunk = (uint32_t)(f & 63) >> 3;
+    const uint32_t st_f = stage_u32 + (uint32_t)f * 16;                    // this thread's 16-byte slot of a core-matrix row
 
     const int tiles = (n_rows + AT_ROWS - 1) / AT_ROWS;
     const int workers = (int)gridDim.x * AT_GROUPS;
     double acc = 0.0;
     int nbad = 0;
+    const uint32_t zero32 = (uint32_t)(n_rows_sz >> 63);                  // 0, unknown to the compiler
 
     // One tile through all S stages.  FULL: all 16 rows exist (no per-row predicates); the one partial tile of a launch
     // takes the predicated copy of the same code.
+    //
+    // Schedule of stage i (row i needs k_0 .. k_i, the newest one, k_i, has just come out of tensor memory):
+    //   critical path   y_i = y0 + (prefix_i + k_i c_ii)  ->  split  ->  planes  ->  fence, bar.sync, 48 MMAs + commit
+    //   MMA window      everything that does not depend on the product in flight: the prefix of the NEXT row's sum
+    //                   (sum over j <= i of k_j c_{i+1,j}: ascending j, so the newest term is always added last and the
+    //                   value is bitwise the one a single ascending loop produces), the running sums, y1's bookkeeping
+    //   then            wait for the accumulators, drain them: k_{i+1}
+    // Registers: k_0 .. k_{KEEP-1} are kept; once they are all known the remaining rows (and the error estimate) become
+    // running sums that each later k_j is folded into as it arrives, so at most four state-sized arrays are live.
+    constexpr int KEEP = S < 4 ? S : 4;
+    constexpr int NACC = S - KEEP;
+    auto row_mask = [](int i) -> unsigned { return (unsigned)((RM >> (8 * i)) & 0xffull); };
     auto do_tile = [&](auto full_tag, const int t) {
         constexpr bool FULL = decltype(full_tag)::value;
         const int row0 = t * AT_ROWS;
         const int rows_here = FULL ? AT_ROWS : n_rows - row0;
         const size_t base = (size_t)row0 * LD + f;
-        float K[S][AT_ROWS];
+        float K[KEEP][AT_ROWS];
+        float A[NACC > 0 ? NACC : 1][AT_ROWS];                             // A[q - KEEP]: running sum of row q
+        float AE[AT_ROWS], PRE[AT_ROWS], KN[AT_ROWS], Y1[AT_ROWS];
         {
             float Y0[AT_ROWS];
 #pragma unroll
             for (int r = 0; r < AT_ROWS; ++r) {
                 Y0[r] = 0.f;
-                K[0][r] = 0.f;
+                KN[r] = 0.f;
                 if (FULL || r < rows_here) {
                     Y0[r] = __ldcs(y0 + base + (size_t)r * LD);
-                    K[0][r] = __ldcs(k0 + base + (size_t)r * LD);
+                    KN[r] = __ldcs(k0 + base + (size_t)r * LD);
                 }
             }
 #pragma unroll
             for (int r = 0; r < AT_ROWS; ++r) sts_f32(sy0 + r * LD * 4, Y0[r]);   // only this thread reads it back: no barrier
         }
-        float EP[AT_ROWS], TOL[AT_ROWS];                                   // error-sum prefix, tolerance (last row)
 #pragma unroll
         for (int i = 0; i < S; ++i) {
-            const unsigned mask = (unsigned)((RM >> (8 * i)) & 0xffull);
+            const unsigned mask = row_mask(i);
             const bool last = i == S - 1;
-            float cr[S], ce[S];
+            const bool has_prefix = (mask & ((1u << i) - 1u)) != 0u, has_new = ((mask >> i) & 1u) != 0u;
+            const float c_new = has_new ? s_cr[i * 8 + popc_below(mask, i)] : 0.f;
+            if (i < KEEP) {
 #pragma unroll
-            for (int j = 0; j < S; ++j) {
-                cr[j] = ((mask >> j) & 1u) ? s_cr[i * 8 + popc_below(mask, j)] : 0.f;
-                ce[j] = (last && ((EM >> j) & 1u)) ? s_ce[popc_below(EM, j)] : 0.f;
+                for (int r = 0; r < AT_ROWS; ++r) K[i < KEEP ? i : 0][r] = KN[r];
             }
-            // ---- y_i = y0 + sum_j k_j coef_ij (ascending j over the non-zero terms, rounded separately), split, planes ----
+            // ---- critical path: y_i, split, planes ----
 #pragma unroll
-            for (int r = 0; r < AT_ROWS; r += 2) {
-                float yv[2];
+            for (int r8 = 0; r8 < AT_ROWS; r8 += 8) {
+                uint32_t H[4], M[4], L[4];
 #pragma unroll
-                for (int q = 0; q < 2; ++q) {
-                    float ar = 0.f, ae = 0.f;
-                    bool fr = true, fe = true;
+                for (int r = r8; r < r8 + 8; r += 2) {
+                    float yv[2];
 #pragma unroll
-                    for (int j = 0; j <= i; ++j) {
-                        if ((mask >> j) & 1u) {
-                            const float p = K[j][r + q] * cr[j];
-                            ar = fr ? p : ar + p;
-                            fr = false;
-                        }
-                        if (last && ((EM >> j) & 1u)) {
-                            const float p = K[j][r + q] * ce[j];
-                            ae = fe ? p : ae + p;
-                            fe = false;
-                        }
+                    for (int q = 0; q < 2; ++q) {
+                        const float pre = i < KEEP ? PRE[r + q] : A[i >= KEEP ? i - KEEP : 0][r + q];
+                        float sum;
+                        if (has_prefix && has_new) sum = pre + KN[r + q] * c_new;
+                        else if (has_prefix) sum = pre;
+                        else sum = KN[r + q] * c_new;
+                        yv[q] = lds_f32(sy0 + (r + q) * LD * 4) + sum;
+                        if (last) Y1[r + q] = yv[q];
                     }
-                    const float y0v = lds_f32(sy0 + (r + q) * LD * 4);
-                    yv[q] = y0v + ar;
-                    if (last) {
-                        EP[r + q] = ae;
-                        // tol = atol + rtol * max(|y0|, |y1|) (misc.py:81), as k_norm forms it
-                        TOL[r + q] = Ar<float>::add(atolT, Ar<float>::mul(rtolT, Ar<float>::max_nan(fabsf(y0v), fabsf(yv[q]))));
-                        if (FULL || r + q < rows_here) {
-                            if (!isfinite(yv[q])) nbad += 1;
-                            const size_t o = base + (size_t)(r + q) * LD;
-                            if (ycand) ycand[o] = yv[q];
-                            if (store) {
-                                out.y1[o] = yv[q];
-                                out.err[o] = ae;
-                            }
-                        }
-                    }
+                    split2(yv[0], yv[1], H[(r - r8) >> 1], M[(r - r8) >> 1], L[(r - r8) >> 1]);
                 }
-                uint32_t h, m, l;
-                split2(yv[0], yv[1], h, m, l);
-                const uint32_t o0 = f_off + (uint32_t)r * 128 + ((f_chunk ^ (uint32_t)(r & 7)) << 4);
-                const uint32_t o1 = f_off + (uint32_t)(r + 1) * 128 + ((f_chunk ^ (uint32_t)((r + 1) & 7)) << 4);
-                sts_bf16x2(stage_u32 + o0, stage_u32 + o1, h);
-                sts_bf16x2(stage_u32 + AT_PLANE + o0, stage_u32 + AT_PLANE + o1, m);
-                sts_bf16x2(stage_u32 + 2 * AT_PLANE + o0, stage_u32 + 2 * AT_PLANE + o1, l);
+                sts_v4(st_f + (r8 >> 3) * AT_SBO, H[0], H[1], H[2], H[3]);
+                sts_v4(st_f + AT_PLANE + (r8 >> 3) * AT_SBO, M[0], M[1], M[2], M[3]);
+                sts_v4(st_f + 2 * AT_PLANE + (r8 >> 3) * AT_SBO, L[0], L[1], L[2], L[3]);
             }
             // ---- k_{i+1} = y_i W^T ----
             fence_async_smem();
             fence_before();
             asm volatile("bar.sync %0, 128;" :: "r"(g + 1) : "memory");
-            if (e == g && elect_one()) {                              // group g issues from sub-partition g
+            if (e == g % 4 && elect_one()) {                          // group g issues from sub-partition g mod 4
                 fence_after();
                 // weights plane PW (tensor memory) x stage plane PY (shared memory): the five cross terms >= 2^-16 in
                 // ascending magnitude into the small accumulator, hi.hi into the big one (tdq_linear.cu)
@@ -273,47 +283,145 @@ k_linear_attempt(const TdqCtrl *__restrict__ c, const float *y0, const float *k0
                     const uint32_t dcol = p == NPROD - 1 ? acc_big : acc_small;
 #pragma unroll
                     for (int ks = 0; ks < 8; ++ks) {
-                        const uint32_t koff = (ks >> 2) * AT_ATOM + (ks & 3) * 32;
-                        mma_ts(dcol, tmem + AT_COL_W + PW[p] * 64 + ks * 8, make_desc(stage_u32 + PY[p] * AT_PLANE + koff), IDESC16,
+                        mma_ts(dcol, tmem + AT_COL_W + PW[p] * 64 + ks * 8, make_desc_mn(stage_u32 + PY[p] * AT_PLANE + ks * 2 * AT_LBO), IDESC16,
                                (p == 0 || p == NPROD - 1) && ks == 0 ? 0u : 1u);
                     }
                 }
                 mma_commit(bar);
             }
             __syncwarp();
-            mbar_wait(bar, phase);
+            // ---- MMA window ----
+            uint32_t dep = 0;
+            if (i + 1 < KEEP && i + 1 < S) {
+                // prefix of the next row's sum over the slots known so far
+                const unsigned mn = row_mask(i + 1);
+                bool first = true;
+#pragma unroll
+                for (int j = 0; j <= i; ++j) {
+                    if ((mn >> j) & 1u) {
+                        const float cj = s_cr[(i + 1) * 8 + popc_below(mn, j)];
+#pragma unroll
+                        for (int r = 0; r < AT_ROWS; ++r) {
+                            const float p = K[j < KEEP ? j : 0][r] * cj;
+                            PRE[r] = first ? p : PRE[r] + p;
+                        }
+                        first = false;
+                    }
+                }
+                if (!first) dep |= dep16(PRE, zero32);
+            }
+            if (i == KEEP - 1) {
+                // every kept slot is known: the remaining rows and the error estimate become running sums (row by row of
+                // the tile, so that the kept slots die as the sums are born)
+#pragma unroll
+                for (int r = 0; r < AT_ROWS; ++r) {
+#pragma unroll
+                    for (int qrow = KEEP; qrow < S; ++qrow) {
+                        const unsigned mq = row_mask(qrow);
+                        float a_ = 0.f;
+                        bool first = true;
+#pragma unroll
+                        for (int j = 0; j <= i; ++j) {
+                            if ((mq >> j) & 1u) {
+                                const float p = K[j < KEEP ? j : 0][r] * s_cr[qrow * 8 + popc_below(mq, j)];
+                                a_ = first ? p : a_ + p;
+                                first = false;
+                            }
+                        }
+                        A[qrow - KEEP][r] = a_;
+                    }
+                    float e_ = 0.f;
+                    bool first = true;
+#pragma unroll
+                    for (int j = 0; j <= i; ++j) {
+                        if ((EM >> j) & 1u) {
+                            const float p = K[j < KEEP ? j : 0][r] * s_ce[popc_below(EM, j)];
+                            e_ = first ? p : e_ + p;
+                            first = false;
+                        }
+                    }
+                    AE[r] = e_;
+                }
+#pragma unroll
+                for (int qrow = KEEP; qrow < S; ++qrow) dep |= dep16(A[qrow - KEEP], zero32);
+                dep |= dep16(AE, zero32);
+            }
+            if (i >= KEEP) {
+                // fold k_i into the running sums of the later rows and of the error estimate
+#pragma unroll
+                for (int qrow = i + 1; qrow < S; ++qrow) {
+                    const unsigned mq = row_mask(qrow);
+                    if ((mq >> i) & 1u) {
+                        const float cj = s_cr[qrow * 8 + popc_below(mq, i)];
+                        const bool started = (mq & ((1u << i) - 1u)) != 0u;
+#pragma unroll
+                        for (int r = 0; r < AT_ROWS; ++r) {
+                            const float p = KN[r] * cj;
+                            A[qrow - KEEP][r] = started ? A[qrow - KEEP][r] + p : p;
+                        }
+                    }
+                }
+                if ((EM >> i) & 1u) {
+                    const float cj = s_ce[popc_below(EM, i)];
+                    const bool started = (EM & ((1u << i) - 1u)) != 0u;
+#pragma unroll
+                    for (int r = 0; r < AT_ROWS; ++r) {
+                        const float p = KN[r] * cj;
+                        AE[r] = started ? AE[r] + p : p;
+                    }
+                }
+#pragma unroll
+                for (int qrow = i + 1; qrow < S; ++qrow) dep |= dep16(A[qrow - KEEP], zero32);
+                dep |= dep16(AE, zero32);
+            }
+            if (last) {
+                // y1: non-finite count, candidate commit, (optional) y1 and the error prefix; tol = atol + rtol * max(|y0|, |y1|)
+                // (misc.py:81) replaces y1 in its registers
+#pragma unroll
+                for (int r = 0; r < AT_ROWS; ++r) {
+                    const float y1v = Y1[r];
+                    if (FULL || r < rows_here) {
+                        if (!isfinite(y1v)) nbad += 1;
+                        const size_t o = base + (size_t)r * LD;
+                        if (ycand) ycand[o] = y1v;
+                        if (store) {
+                            out.y1[o] = y1v;
+                            out.err[o] = AE[r];
+                        }
+                    }
+                    Y1[r] = Ar<float>::add(atolT, Ar<float>::mul(rtolT, Ar<float>::max_nan(fabsf(lds_f32(sy0 + r * LD * 4)), fabsf(y1v))));
+                }
+                dep |= dep16(Y1, zero32);
+            }
+            mbar_wait(bar + dep, phase);
             phase ^= 1u;
             fence_after();
             // drain: the small accumulator first, then the big one on top of it (16 registers of staging, not 32)
-            uint32_t tq[16];
-            float KN[AT_ROWS];
-            tmem_ld16(lane_base + (uint32_t)(g * 32 + 16), tq);
-            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            {
+                uint32_t tq[16];
+                tmem_ld16(lane_base + (uint32_t)(g * 32 + 16), tq);
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
-            for (int r = 0; r < AT_ROWS; ++r) KN[r] = __uint_as_float(tq[r]);
-            tmem_ld16(lane_base + (uint32_t)(g * 32), tq);
-            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                for (int r = 0; r < AT_ROWS; ++r) KN[r] = __uint_as_float(tq[r]);
+                tmem_ld16(lane_base + (uint32_t)(g * 32), tq);
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
-            for (int r = 0; r < AT_ROWS; ++r) KN[r] = KN[r] + __uint_as_float(tq[r]);
-            if (!last) {
+                for (int r = 0; r < AT_ROWS; ++r) KN[r] = KN[r] + __uint_as_float(tq[r]);
+            }
+            if (store) {
 #pragma unroll
-                for (int r = 0; r < AT_ROWS; ++r) K[(i + 1) < S ? (i + 1) : 0][r] = KN[r];
-                if (store) {
-#pragma unroll
-                    for (int r = 0; r < AT_ROWS; ++r)
-                        if (FULL || r < rows_here) out.k[i + 1][base + (size_t)r * LD] = KN[r];
-                }
-            } else {
+                for (int r = 0; r < AT_ROWS; ++r)
+                    if (FULL || r < rows_here) out.k[i + 1][base + (size_t)r * LD] = KN[r];
+            }
+            if (last) {
                 // ---- k_S: candidate commit, error ratio (misc.py:80-82 up to the mean) ----
 #pragma unroll
                 for (int r = 0; r < AT_ROWS; ++r) {
                     if (FULL || r < rows_here) {
-                        const size_t o = base + (size_t)r * LD;
-                        if (kcand) kcand[o] = KN[r];
-                        if (store) out.k[S][o] = KN[r];
+                        if (kcand) kcand[base + (size_t)r * LD] = KN[r];
                         if (fold) {
-                            const float num = Ar<float>::add(EP[r], Ar<float>::mul(KN[r], ecS));
-                            const float q = Ar<float>::div(num, TOL[r]);
+                            const float num = Ar<float>::add(AE[r], Ar<float>::mul(KN[r], ecS));
+                            const float q = Ar<float>::div(num, Y1[r]);
                             acc += (double)Ar<float>::mul(q, q);
                         }
                     }
@@ -333,7 +441,7 @@ k_linear_attempt(const TdqCtrl *__restrict__ c, const float *y0, const float *k0
         const double wa = warp_sum(acc), wb = warp_sum(bad);
         if (lane == 0) {
             s_red[warp] = wa;
-            s_red[12 + warp] = wb;
+            s_red[20 + warp] = wb;
         }
     }
     fence_before();
@@ -350,7 +458,7 @@ k_linear_attempt(const TdqCtrl *__restrict__ c, const float *y0, const float *k0
         double a = 0.0, b = 0.0;
         for (int w = 0; w < AT_THREADS / 32; ++w) {
             a += s_red[w];
-            b += s_red[12 + w];
+            b += s_red[20 + w];
         }
         p_sum[blockIdx.x] = a;
         p_bad[blockIdx.x] = b;
@@ -375,6 +483,11 @@ k_linear_attempt(const TdqCtrl *__restrict__ c, const float *y0, const float *k0
             *ticket = 0;                                                  // self-reset for the next launch
         }
     }
+    if (CTRL) {
+        __threadfence();
+        __syncthreads();
+        tdq_ctrl_dev::controller_block<float, G * 128>(c, norm_out, seg_counts, 1, nullptr);
+    }
 }
 
 // the sparsity of the supported FSAL tableaus (row masks 8 bits per row, error-prefix mask); tsit5 as the reference
@@ -382,18 +495,31 @@ k_linear_attempt(const TdqCtrl *__restrict__ c, const float *y0, const float *k0
 constexpr unsigned long long RM_DOPRI5 = 0x01ull | (0x03ull << 8) | (0x07ull << 16) | (0x0full << 24) | (0x1full << 32) | (0x3dull << 40);
 constexpr unsigned long long RM_BOSH3 = 0x01ull | (0x02ull << 8) | (0x07ull << 16);
 
-template <int S, unsigned long long RM, unsigned EM>
-int launch_attempt(const TdqCtrl *c, const float *y0, const float *k0, const AttOut &out, const uint32_t *wt, double *partials,
-                   double *norm_out, int store_always, size_t n_rows, cudaStream_t st) {
-    auto kern = k_linear_attempt<S, RM, EM>;
+template <int S, unsigned long long RM, unsigned EM, int G, bool CTRL>
+int launch_attempt_g(TdqCtrl *c, const float *y0, const float *k0, const AttOut &out, const uint32_t *wt, double *partials,
+                     double *norm_out, const int64_t *seg_counts, int store_always, size_t n_rows, cudaStream_t st) {
+    auto kern = k_linear_attempt<S, RM, EM, G, CTRL>;
+    constexpr int AT_SMEM = at_smem(G);
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM) != cudaSuccess) return -2;
     const size_t tiles = (n_rows + AT_ROWS - 1) / AT_ROWS;
-    size_t grid = (tiles + AT_GROUPS - 1) / AT_GROUPS;
+    size_t grid = (tiles + G - 1) / G;
     const size_t cap = (size_t)tdq_sm_count();
     if (grid > cap) grid = cap;
     if (grid == 0) grid = 1;
-    kern<<<(unsigned)grid, AT_THREADS, AT_SMEM, st>>>(c, y0, k0, out, wt, partials, norm_out, store_always, n_rows);
+    kern<<<(unsigned)grid, G * 128, AT_SMEM, st>>>(c, y0, k0, out, wt, partials, norm_out, seg_counts, store_always, n_rows);
     return 0;
+}
+
+template <int S, unsigned long long RM, unsigned EM>
+int launch_attempt(TdqCtrl *c, const float *y0, const float *k0, const AttOut &out, const uint32_t *wt, double *partials,
+                   double *norm_out, const int64_t *seg_counts, int store_always, size_t n_rows, cudaStream_t st) {
+    const char *v = getenv("TDQ_ATTEMPT_GROUPS");                         // experiment switch
+#define TDQ_GO(G_) (seg_counts ? launch_attempt_g<S, RM, EM, G_, true>(c, y0, k0, out, wt, partials, norm_out, seg_counts, store_always, n_rows, st) \
+                               : launch_attempt_g<S, RM, EM, G_, false>(c, y0, k0, out, wt, partials, norm_out, seg_counts, store_always, n_rows, st))
+    if (v && v[0] == '3') return TDQ_GO(3);
+    if (v && v[0] == '5') return TDQ_GO(5);
+    return TDQ_GO(4);
+#undef TDQ_GO
 }
 
 // row / error masks of a tableau, or false if it is not FSAL with 2..AT_MAX_S stages and an error weight on k_S
@@ -436,11 +562,12 @@ int tdq_linear_attempt_supported(const tdq_tableau *tab, int32_t dtype, int32_t 
 
 int tdq_linear_attempt(void *ctrl_dev, const tdq_tableau *tab, int32_t dtype, void *const *k_out, void *y1_out, void *err_out,
                        const void *y0, const void *k0, const void *planes, int32_t width, size_t n, double *partials,
-                       double *norm_out, int32_t store_always, void *stream) {
+                       double *norm_out, const int64_t *seg_counts_dev, int32_t store_always, void *stream) {
     TDQ_REQUIRE(ctrl_dev && tab && k_out && y1_out && err_out && planes, "null argument");
     TDQ_REQUIRE(dtype == TDQ_F32 && width == LD, "the fused linear field is float32, width 128");
     TDQ_REQUIRE(n % (size_t)width == 0, "state size is not a multiple of the field width");
     TDQ_REQUIRE((partials == nullptr) == (norm_out == nullptr), "partials and norm_out go together");
+    TDQ_REQUIRE(seg_counts_dev == nullptr || partials != nullptr, "the controller step needs the folded error norm");
     const size_t n_rows = n / (size_t)width;
     TDQ_REQUIRE(n_rows < ((size_t)1 << 31) - 64, "too many rows");
     TdqHostShape hs;
@@ -458,14 +585,14 @@ int tdq_linear_attempt(void *ctrl_dev, const tdq_tableau *tab, int32_t dtype, vo
     out.y1 = (float *)y1_out;
     out.err = (float *)err_out;
     if (n_rows == 0) return TDQ_OK;
-    const TdqCtrl *c = (const TdqCtrl *)ctrl_dev;
+    TdqCtrl *c = (TdqCtrl *)ctrl_dev;
     const uint32_t *wt = (const uint32_t *)planes;
     cudaStream_t st = (cudaStream_t)stream;
     int rc = -1;
     if (S == 6 && rm == RM_DOPRI5 && em == 0x3du)
-        rc = launch_attempt<6, RM_DOPRI5, 0x3du>(c, (const float *)y0, (const float *)k0, out, wt, partials, norm_out, store_always, n_rows, st);
+        rc = launch_attempt<6, RM_DOPRI5, 0x3du>(c, (const float *)y0, (const float *)k0, out, wt, partials, norm_out, seg_counts_dev, store_always, n_rows, st);
     else if (S == 3 && rm == RM_BOSH3 && em == 0x07u)
-        rc = launch_attempt<3, RM_BOSH3, 0x07u>(c, (const float *)y0, (const float *)k0, out, wt, partials, norm_out, store_always, n_rows, st);
+        rc = launch_attempt<3, RM_BOSH3, 0x07u>(c, (const float *)y0, (const float *)k0, out, wt, partials, norm_out, seg_counts_dev, store_always, n_rows, st);
     TDQ_REQUIRE(rc != -1, "no whole-attempt kernel for this tableau (tdq_linear_attempt_supported)");
     TDQ_REQUIRE(rc == 0, "launch configuration failed");
     TDQ_CHECK_CUDA(cudaGetLastError());
