@@ -341,6 +341,8 @@ def run_ours(args):
     y0 = y0_host.to(dev)
     t_dev = t.to(dev)
     opts = {"graph": True, "run_ahead": 2, "device_loop": not args.no_device_loop}
+    if args.no_fused_controller:
+        opts["fused_controller"] = False
     if pg:
         opts["process_group"] = pg
     stats = {}
@@ -554,6 +556,9 @@ def main():
                     help="N > 1: weak = 65536 trajectories per rank (configs[4]); strong = 65536 split over the ranks")
     ap.add_argument("--generic", action="store_true",
                     help="func as an opaque torch module (k_combine + cuBLAS SGEMM per stage) instead of LinearField")
+    ap.add_argument("--no-fused-controller", action="store_true",
+                    help="keep the controller step a launch of its own instead of running it in the last block of the "
+                         "whole-attempt kernel (needed under ncu: a kernel with a device-runtime call is not profiled)")
     ap.add_argument("--no-device-loop", action="store_true",
                     help="replay the step graph from the host instead of the device-side while loop (needed under ncu: "
                          "kernels inside a conditional graph node are not visible to its kernel-level profiling)")

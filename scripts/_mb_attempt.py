@@ -56,7 +56,7 @@ def timeit(name, fn, reps=15):
 attempt_stages(0)
 torch.cuda.synchronize()
 ref = [k.clone() for k in ks] + [y1.clone(), er.clone(), eng.norm_out.clone()]
-for grp in ("3", "4", "5"):
+for grp in ("3", "4", "5", "31", "41"):
     os.environ["TDQ_ATTEMPT_GROUPS"] = grp
     for k in ks:
         k.zero_()

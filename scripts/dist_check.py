@@ -29,7 +29,9 @@ def main():
     log("process group up")
     per = int(os.environ.get("DIST_CHECK_ROWS_PER_RANK", "0")) or (4096 // world)
     B, D = per * world, 128
-    f = P.BatchedLinear(D, torch.float32).to(dev)
+    f_generic = P.BatchedLinear(D, torch.float32).to(dev)
+    # the same field as a LinearField: the whole attempt (stages, norm, controller, peer exchange) is one tcgen05 launch
+    f_linear = tdq.LinearField(P.skew_matrix(D, torch.float32).to(dev))
     y0 = torch.randn(B, D, generator=torch.Generator().manual_seed(1)).to(dev)      # ONE seeded batch, sharded by rows
     t = torch.linspace(0., 3., 5).to(dev)
     rows = slice(rank * per, (rank + 1) * per)
@@ -38,9 +40,10 @@ def main():
              {"graph": False, "run_ahead": 0, "exchange": "nccl"}, {"graph": True, "run_ahead": 2, "exchange": "nccl"})
     if per > 8192:          # the big configuration (65,536 rows per rank): the two production modes only
         modes = ({"graph": True, "run_ahead": 2}, {"graph": True, "run_ahead": 2, "exchange": "nccl"})
-    for mode in modes:
+    fields = [("generic", f_generic)] + ([("linear", f_linear)] if os.environ.get("DIST_CHECK_LINEAR", "1") == "1" else [])
+    for fname, f, mode in [(n_, f_, m_) for n_, f_ in fields for m_ in modes]:
         st = {}
-        log("mode", mode, "sharded solve ...")
+        log("field", fname, "mode", mode, "sharded solve ...")
         with torch.no_grad():
             y = tdq.odeint(f, y0[rows].contiguous(), t, method="dopri5", rtol=1e-5, atol=1e-7,
                            options=dict(mode, process_group=True), _stats=st)
@@ -55,8 +58,8 @@ def main():
                                   options={k: v for k, v in mode.items() if k != "exchange"}, _stats=st1)
             err = (full - want).abs().max().item()
             same_steps = (st["n_accept"], st["n_reject"]) == (st1["n_accept"], st1["n_reject"])
-            print("mode", mode, "max|sharded - unsharded| =", err, "steps", (st["n_accept"], st["n_reject"]),
-                  (st1["n_accept"], st1["n_reject"]), flush=True)
+            print("field", fname, "fused_attempt", st.get("fused_attempt"), "mode", mode, "max|sharded - unsharded| =", err, "steps",
+                  (st["n_accept"], st["n_reject"]), (st1["n_accept"], st1["n_reject"]), flush=True)
             ok = ok and err < 1e-5 and same_steps
     if os.environ.get("DIST_CHECK_ADJOINT", "1") == "1":
         ok = adjoint_check(rank, world, dev) and ok

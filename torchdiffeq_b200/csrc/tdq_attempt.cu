@@ -30,7 +30,6 @@
 #include "tdq_tc.cuh"
 #include "tdq_ctrl_dev.cuh"
 
-#include <cstdlib>
 #include <type_traits>
 
 namespace {
@@ -41,7 +40,7 @@ constexpr int LD = 128;                        // state width = output features 
 constexpr int AT_ROWS = 16;                    // state rows per tile = MMA N
 constexpr int AT_PLANE = AT_ROWS * LD * 2;      // one bfloat16 plane of a tile: 16 rows x 128 features
 constexpr int AT_STAGE = 3 * AT_PLANE;         // hi, mid, lo
-constexpr int AT_AUX = 1024;                   // barriers, tensor-memory slot, coefficient tables, reduction scratch
+constexpr int AT_AUX = 2048;                   // barriers, tensor-memory slot, coefficient tables, reduction scratch
 constexpr int AT_Y0 = AT_ROWS * LD * 4;         // a tile's y0 (float32) stays in shared memory: read once per stage
 // G: tile pipelines (groups of 4 warps) per CTA
 constexpr int at_smem(int G) { return G * (AT_STAGE + AT_Y0) + AT_AUX + 1024; }
@@ -69,12 +68,21 @@ __device__ __forceinline__ void sts_v4(uint32_t addr, uint32_t a, uint32_t b, ui
 // A value that is zero at run time but depends on every element of `a`: added to the address of the mbarrier the group is
 // about to wait on, it forces the arithmetic of the MMA window to be issued BEFORE the wait (ptxas otherwise sinks part of it
 // below the wait, onto the critical path).  `zero` is a run-time zero the compiler cannot fold.  8 LOP3 per array.
-__device__ __forceinline__ uint32_t dep16(const float (&a)[16], uint32_t zero) {
+template <int N>
+__device__ __forceinline__ uint32_t dep16(const float (&a)[N], uint32_t zero) {
     uint32_t x = 0;
 #pragma unroll
-    for (int r = 0; r < 16; ++r) x ^= __float_as_uint(a[r]);
+    for (int r = 0; r < N; ++r) x ^= __float_as_uint(a[r]);
     return x & zero;
 }
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t (&r)[8]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+                 : "r"(taddr) : "memory");
+}
+template <int N> __device__ __forceinline__ void tmem_ldn(uint32_t taddr, uint32_t (&r)[N]);
+template <> __device__ __forceinline__ void tmem_ldn<16>(uint32_t taddr, uint32_t (&r)[16]) { tmem_ld16(taddr, r); }
+template <> __device__ __forceinline__ void tmem_ldn<8>(uint32_t taddr, uint32_t (&r)[8]) { tmem_ld8(taddr, r); }
 // one lane of a converged warp (the compiler keeps the operands of what follows in uniform registers)
 __device__ __forceinline__ bool elect_one() {
     uint32_t pred = 0;
@@ -104,21 +112,24 @@ __host__ __device__ constexpr int popc_below(unsigned mask, int j) {
 // CTRL: the last block to finish also runs the controller step (tdq_ctrl_dev.cuh: accept / reject, next step size, the next
 // attempt's tables, the device-side loop's condition) -- one launch per attempt instead of two.  That instantiation carries a
 // device-runtime call (cudaGraphSetConditional), which kernel-level profilers refuse; the CTRL = false one is what ncu sees.
-template <int S, unsigned long long RM, unsigned EM, int G, bool CTRL>
-__global__ void __launch_bounds__(G * 128, 1)
+// RT: rows of a tile per thread.  16: one warpgroup (4 warps) per tile; 8: two warpgroups per tile, each thread half the rows
+// (warps w and w + 4 own the same tensor-memory lanes and drain columns [0, 8) / [8, 16)): half the registers and half the
+// dependent work per thread, twice the warps to hide latencies with.
+template <int S, unsigned long long RM, unsigned EM, int G, int RT, bool CTRL>
+__global__ void __launch_bounds__(G * 128 * (16 / RT), 1)
 k_linear_attempt(TdqCtrl *c, const float *y0, const float *k0, AttOut out, const uint32_t *__restrict__ wt,
                  double *partials, double *norm_out, const int64_t *seg_counts, int store_always, size_t n_rows_sz) {
     if (c->halt) return;
     extern __shared__ uint8_t smem_raw[];
     uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-    constexpr int AT_GROUPS = G, AT_THREADS = G * 128;
+    constexpr int AT_GROUPS = G, HN = AT_ROWS / RT, WPG = 4 * HN, AT_THREADS = G * 128 * HN;
     uint8_t *aux = smem + G * (AT_STAGE + AT_Y0);
     uint64_t *bars = reinterpret_cast<uint64_t *>(aux);                    // one "accumulators complete" barrier per group
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(aux + 32);
     int *s_flag = reinterpret_cast<int *>(aux + 40);
     float *s_cr = reinterpret_cast<float *>(aux + 64);                    // [S][8]: coef[i][m] as float32
     float *s_ce = s_cr + AT_MAX_S * 8;                                    // [8]:    ecoef[m]
-    double *s_red = reinterpret_cast<double *>(aux + 512);                // [2][20]
+    double *s_red = reinterpret_cast<double *>(aux + 512);                // [2][32]
     const int tid = threadIdx.x, lane = tid & 31;
     const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);                  // warp-uniform for the compiler as well
     const int n_rows = (int)n_rows_sz;
@@ -143,19 +154,21 @@ k_linear_attempt(TdqCtrl *c, const float *y0, const float *k0, AttOut out, const
     fence_after();
     const uint32_t tmem = __shfl_sync(0xffffffffu, *tmem_slot, 0);
 
-    const int g = warp >> 2, e = warp & 3, f = e * 32 + lane;             // this thread's tensor-memory lane = feature
+    // group g = one tile pipeline; e = tensor-memory lane quarter (= warp index mod 4); h = which RT rows of the tile
+    const int g = warp / WPG, wl = warp % WPG, e = wl & 3, h = wl >> 2, f = e * 32 + lane;   // f: this thread's lane = feature
     const uint32_t lane_base = tmem + ((uint32_t)(e * 32) << 16);
-    if (g < 3) {   // weights -> tensor memory, once: group g stores plane g (hi, mid, lo)
+    {   // weights -> tensor memory, once: six chunks (plane, half of K) shared out over the warpgroups
 #pragma unroll 1
-        for (int c0 = 0; c0 < 64; c0 += 32) {
+        for (int ch = warp >> 2; ch < 6; ch += AT_THREADS / 128) {
+            const int pl = ch >> 1, c0 = (ch & 1) * 32;
             uint32_t r[32];
-            const uint4 *src = reinterpret_cast<const uint4 *>(wt + ((size_t)g * LD + f) * 64 + c0);
+            const uint4 *src = reinterpret_cast<const uint4 *>(wt + ((size_t)pl * LD + f) * 64 + c0);
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
                 const uint4 v = src[j];
                 r[4 * j] = v.x; r[4 * j + 1] = v.y; r[4 * j + 2] = v.z; r[4 * j + 3] = v.w;
             }
-            tmem_st32(lane_base + AT_COL_W + g * 64 + c0, r);
+            tmem_st32(lane_base + AT_COL_W + pl * 64 + c0, r);
         }
         asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
     }
@@ -186,12 +199,12 @@ k_linear_attempt(TdqCtrl *c, const float *y0, const float *k0, AttOut out, const
     const float ecS = s_ce[EK];
 
     uint8_t *stage = smem + g * AT_STAGE;
-    const uint32_t sy0 = smem_u32(smem + AT_GROUPS * AT_STAGE + g * AT_Y0) + (uint32_t)f * 4;   // [row][feature], this thread's column
+    const uint32_t sy0 = smem_u32(smem + AT_GROUPS * AT_STAGE + g * AT_Y0) + (uint32_t)(h * RT * LD + f) * 4;   // [row][feature]: this thread's rows, its column
     const uint32_t stage_u32 = smem_u32(stage);
     const uint32_t bar = bar0 + 8 * g;
     const uint32_t acc_big = tmem + g * 32, acc_small = tmem + g * 32 + 16;
     uint32_t phase = 0;
-    const uint32_t st_f = stage_u32 + (uint32_t)f * 16;                    // this thread's 16-byte slot of a core-matrix row
+    const uint32_t st_f = stage_u32 + (uint32_t)f * 16 + (uint32_t)(h * (RT / 8)) * AT_SBO;   // this thread's 16-byte slot of its first core-matrix row group
 
     const int tiles = (n_rows + AT_ROWS - 1) / AT_ROWS;
     const int workers = (int)gridDim.x * AT_GROUPS;
@@ -216,15 +229,15 @@ k_linear_attempt(TdqCtrl *c, const float *y0, const float *k0, AttOut out, const
     auto do_tile = [&](auto full_tag, const int t) {
         constexpr bool FULL = decltype(full_tag)::value;
         const int row0 = t * AT_ROWS;
-        const int rows_here = FULL ? AT_ROWS : n_rows - row0;
-        const size_t base = (size_t)row0 * LD + f;
-        float K[KEEP][AT_ROWS];
-        float A[NACC > 0 ? NACC : 1][AT_ROWS];                             // A[q - KEEP]: running sum of row q
-        float AE[AT_ROWS], PRE[AT_ROWS], KN[AT_ROWS], Y1[AT_ROWS];
+        const int rows_here = FULL ? RT : n_rows - row0 - h * RT;      // of this thread's RT rows
+        const size_t base = (size_t)(row0 + h * RT) * LD + f;
+        float K[KEEP][RT];
+        float A[NACC > 0 ? NACC : 1][RT];                             // A[q - KEEP]: running sum of row q
+        float AE[RT], PRE[RT], KN[RT], Y1[RT];
         {
-            float Y0[AT_ROWS];
+            float Y0[RT];
 #pragma unroll
-            for (int r = 0; r < AT_ROWS; ++r) {
+            for (int r = 0; r < RT; ++r) {
                 Y0[r] = 0.f;
                 KN[r] = 0.f;
                 if (FULL || r < rows_here) {
@@ -233,7 +246,7 @@ k_linear_attempt(TdqCtrl *c, const float *y0, const float *k0, AttOut out, const
                 }
             }
 #pragma unroll
-            for (int r = 0; r < AT_ROWS; ++r) sts_f32(sy0 + r * LD * 4, Y0[r]);   // only this thread reads it back: no barrier
+            for (int r = 0; r < RT; ++r) sts_f32(sy0 + r * LD * 4, Y0[r]);   // only this thread reads it back: no barrier
         }
 #pragma unroll
         for (int i = 0; i < S; ++i) {
@@ -243,11 +256,11 @@ k_linear_attempt(TdqCtrl *c, const float *y0, const float *k0, AttOut out, const
             const float c_new = has_new ? s_cr[i * 8 + popc_below(mask, i)] : 0.f;
             if (i < KEEP) {
 #pragma unroll
-                for (int r = 0; r < AT_ROWS; ++r) K[i < KEEP ? i : 0][r] = KN[r];
+                for (int r = 0; r < RT; ++r) K[i < KEEP ? i : 0][r] = KN[r];
             }
             // ---- critical path: y_i, split, planes ----
 #pragma unroll
-            for (int r8 = 0; r8 < AT_ROWS; r8 += 8) {
+            for (int r8 = 0; r8 < RT; r8 += 8) {
                 uint32_t H[4], M[4], L[4];
 #pragma unroll
                 for (int r = r8; r < r8 + 8; r += 2) {
@@ -271,8 +284,8 @@ k_linear_attempt(TdqCtrl *c, const float *y0, const float *k0, AttOut out, const
             // ---- k_{i+1} = y_i W^T ----
             fence_async_smem();
             fence_before();
-            asm volatile("bar.sync %0, 128;" :: "r"(g + 1) : "memory");
-            if (e == g % 4 && elect_one()) {                          // group g issues from sub-partition g mod 4
+            asm volatile("bar.sync %0, %1;" :: "r"(g + 1), "n"(WPG * 32) : "memory");
+            if (wl == g % 4 && elect_one()) {                         // group g issues from sub-partition g mod 4
                 fence_after();
                 // weights plane PW (tensor memory) x stage plane PY (shared memory): the five cross terms >= 2^-16 in
                 // ascending magnitude into the small accumulator, hi.hi into the big one (tdq_linear.cu)
@@ -301,7 +314,7 @@ k_linear_attempt(TdqCtrl *c, const float *y0, const float *k0, AttOut out, const
                     if ((mn >> j) & 1u) {
                         const float cj = s_cr[(i + 1) * 8 + popc_below(mn, j)];
 #pragma unroll
-                        for (int r = 0; r < AT_ROWS; ++r) {
+                        for (int r = 0; r < RT; ++r) {
                             const float p = K[j < KEEP ? j : 0][r] * cj;
                             PRE[r] = first ? p : PRE[r] + p;
                         }
@@ -314,7 +327,7 @@ k_linear_attempt(TdqCtrl *c, const float *y0, const float *k0, AttOut out, const
                 // every kept slot is known: the remaining rows and the error estimate become running sums (row by row of
                 // the tile, so that the kept slots die as the sums are born)
 #pragma unroll
-                for (int r = 0; r < AT_ROWS; ++r) {
+                for (int r = 0; r < RT; ++r) {
 #pragma unroll
                     for (int qrow = KEEP; qrow < S; ++qrow) {
                         const unsigned mq = row_mask(qrow);
@@ -355,7 +368,7 @@ k_linear_attempt(TdqCtrl *c, const float *y0, const float *k0, AttOut out, const
                         const float cj = s_cr[qrow * 8 + popc_below(mq, i)];
                         const bool started = (mq & ((1u << i) - 1u)) != 0u;
 #pragma unroll
-                        for (int r = 0; r < AT_ROWS; ++r) {
+                        for (int r = 0; r < RT; ++r) {
                             const float p = KN[r] * cj;
                             A[qrow - KEEP][r] = started ? A[qrow - KEEP][r] + p : p;
                         }
@@ -365,7 +378,7 @@ k_linear_attempt(TdqCtrl *c, const float *y0, const float *k0, AttOut out, const
                     const float cj = s_ce[popc_below(EM, i)];
                     const bool started = (EM & ((1u << i) - 1u)) != 0u;
 #pragma unroll
-                    for (int r = 0; r < AT_ROWS; ++r) {
+                    for (int r = 0; r < RT; ++r) {
                         const float p = KN[r] * cj;
                         AE[r] = started ? AE[r] + p : p;
                     }
@@ -378,7 +391,7 @@ k_linear_attempt(TdqCtrl *c, const float *y0, const float *k0, AttOut out, const
                 // y1: non-finite count, candidate commit, (optional) y1 and the error prefix; tol = atol + rtol * max(|y0|, |y1|)
                 // (misc.py:81) replaces y1 in its registers
 #pragma unroll
-                for (int r = 0; r < AT_ROWS; ++r) {
+                for (int r = 0; r < RT; ++r) {
                     const float y1v = Y1[r];
                     if (FULL || r < rows_here) {
                         if (!isfinite(y1v)) nbad += 1;
@@ -398,25 +411,25 @@ k_linear_attempt(TdqCtrl *c, const float *y0, const float *k0, AttOut out, const
             fence_after();
             // drain: the small accumulator first, then the big one on top of it (16 registers of staging, not 32)
             {
-                uint32_t tq[16];
-                tmem_ld16(lane_base + (uint32_t)(g * 32 + 16), tq);
+                uint32_t tq[RT];
+                tmem_ldn<RT>(lane_base + (uint32_t)(g * 32 + 16 + h * RT), tq);
                 asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
-                for (int r = 0; r < AT_ROWS; ++r) KN[r] = __uint_as_float(tq[r]);
-                tmem_ld16(lane_base + (uint32_t)(g * 32), tq);
+                for (int r = 0; r < RT; ++r) KN[r] = __uint_as_float(tq[r]);
+                tmem_ldn<RT>(lane_base + (uint32_t)(g * 32 + h * RT), tq);
                 asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
-                for (int r = 0; r < AT_ROWS; ++r) KN[r] = KN[r] + __uint_as_float(tq[r]);
+                for (int r = 0; r < RT; ++r) KN[r] = KN[r] + __uint_as_float(tq[r]);
             }
             if (store) {
 #pragma unroll
-                for (int r = 0; r < AT_ROWS; ++r)
+                for (int r = 0; r < RT; ++r)
                     if (FULL || r < rows_here) out.k[i + 1][base + (size_t)r * LD] = KN[r];
             }
             if (last) {
                 // ---- k_S: candidate commit, error ratio (misc.py:80-82 up to the mean) ----
 #pragma unroll
-                for (int r = 0; r < AT_ROWS; ++r) {
+                for (int r = 0; r < RT; ++r) {
                     if (FULL || r < rows_here) {
                         if (kcand) kcand[base + (size_t)r * LD] = KN[r];
                         if (fold) {
@@ -431,7 +444,15 @@ k_linear_attempt(TdqCtrl *c, const float *y0, const float *k0, AttOut out, const
     };
 #pragma unroll 1
     for (int t = g * (int)gridDim.x + (int)blockIdx.x; t < tiles; t += workers) {
-        if (n_rows - t * AT_ROWS >= AT_ROWS) do_tile(std::true_type{}, t);
+        {   // the next tile's y0 / k_0 rows of this warp (128 bytes each) towards L2: lanes 0..RT-1 -> y0, 16..16+RT-1 -> k_0
+            const int tn = t + workers, pr = lane & 15;
+            const long long prow = (long long)tn * AT_ROWS + h * RT + pr;
+            if (tn < tiles && pr < RT && prow < (long long)n_rows) {
+                const float *pp = (lane < 16 ? y0 : k0) + (size_t)prow * LD + e * 32;
+                asm volatile("prefetch.global.L2 [%0];" :: "l"(pp));
+            }
+        }
+        if (n_rows - t * AT_ROWS >= AT_ROWS) do_tile(std::true_type{}, t);          // (a partial tile: rows_here may be <= 0 for h = 1)
         else do_tile(std::false_type{}, t);
     }
     const double bad = (double)nbad;
@@ -441,7 +462,7 @@ k_linear_attempt(TdqCtrl *c, const float *y0, const float *k0, AttOut out, const
         const double wa = warp_sum(acc), wb = warp_sum(bad);
         if (lane == 0) {
             s_red[warp] = wa;
-            s_red[20 + warp] = wb;
+            s_red[32 + warp] = wb;
         }
     }
     fence_before();
@@ -458,7 +479,7 @@ k_linear_attempt(TdqCtrl *c, const float *y0, const float *k0, AttOut out, const
         double a = 0.0, b = 0.0;
         for (int w = 0; w < AT_THREADS / 32; ++w) {
             a += s_red[w];
-            b += s_red[20 + w];
+            b += s_red[32 + w];
         }
         p_sum[blockIdx.x] = a;
         p_bad[blockIdx.x] = b;
@@ -486,7 +507,7 @@ k_linear_attempt(TdqCtrl *c, const float *y0, const float *k0, AttOut out, const
     if (CTRL) {
         __threadfence();
         __syncthreads();
-        tdq_ctrl_dev::controller_block<float, G * 128>(c, norm_out, seg_counts, 1, nullptr);
+        tdq_ctrl_dev::controller_block<float, AT_THREADS>(c, norm_out, seg_counts, 1, nullptr);
     }
 }
 
@@ -495,10 +516,10 @@ k_linear_attempt(TdqCtrl *c, const float *y0, const float *k0, AttOut out, const
 constexpr unsigned long long RM_DOPRI5 = 0x01ull | (0x03ull << 8) | (0x07ull << 16) | (0x0full << 24) | (0x1full << 32) | (0x3dull << 40);
 constexpr unsigned long long RM_BOSH3 = 0x01ull | (0x02ull << 8) | (0x07ull << 16);
 
-template <int S, unsigned long long RM, unsigned EM, int G, bool CTRL>
+template <int S, unsigned long long RM, unsigned EM, int G, int RT, bool CTRL>
 int launch_attempt_g(TdqCtrl *c, const float *y0, const float *k0, const AttOut &out, const uint32_t *wt, double *partials,
                      double *norm_out, const int64_t *seg_counts, int store_always, size_t n_rows, cudaStream_t st) {
-    auto kern = k_linear_attempt<S, RM, EM, G, CTRL>;
+    auto kern = k_linear_attempt<S, RM, EM, G, RT, CTRL>;
     constexpr int AT_SMEM = at_smem(G);
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM) != cudaSuccess) return -2;
     const size_t tiles = (n_rows + AT_ROWS - 1) / AT_ROWS;
@@ -506,19 +527,19 @@ int launch_attempt_g(TdqCtrl *c, const float *y0, const float *k0, const AttOut 
     const size_t cap = (size_t)tdq_sm_count();
     if (grid > cap) grid = cap;
     if (grid == 0) grid = 1;
-    kern<<<(unsigned)grid, G * 128, AT_SMEM, st>>>(c, y0, k0, out, wt, partials, norm_out, seg_counts, store_always, n_rows);
+    kern<<<(unsigned)grid, G * 128 * (AT_ROWS / RT), AT_SMEM, st>>>(c, y0, k0, out, wt, partials, norm_out, seg_counts, store_always, n_rows);
     return 0;
 }
 
 template <int S, unsigned long long RM, unsigned EM>
 int launch_attempt(TdqCtrl *c, const float *y0, const float *k0, const AttOut &out, const uint32_t *wt, double *partials,
                    double *norm_out, const int64_t *seg_counts, int store_always, size_t n_rows, cudaStream_t st) {
-    const char *v = getenv("TDQ_ATTEMPT_GROUPS");                         // experiment switch
-#define TDQ_GO(G_) (seg_counts ? launch_attempt_g<S, RM, EM, G_, true>(c, y0, k0, out, wt, partials, norm_out, seg_counts, store_always, n_rows, st) \
-                               : launch_attempt_g<S, RM, EM, G_, false>(c, y0, k0, out, wt, partials, norm_out, seg_counts, store_always, n_rows, st))
-    if (v && v[0] == '3') return TDQ_GO(3);
-    if (v && v[0] == '5') return TDQ_GO(5);
-    return TDQ_GO(4);
+    // Four tile pipelines of one warpgroup each, 16 rows per thread (128 registers).  Measured alternatives at 65,536 x 128,
+    // dopri5 (profiles/README.md): 3 pipelines 106.6 us, 4: 96.1, 5 (96 registers, spills): 103.4; two warpgroups per tile
+    // (8 rows per thread) 3 x 2: 102.2, 4 x 2: 102.0.
+#define TDQ_GO(G_, RT_) (seg_counts ? launch_attempt_g<S, RM, EM, G_, RT_, true>(c, y0, k0, out, wt, partials, norm_out, seg_counts, store_always, n_rows, st) \
+                                    : launch_attempt_g<S, RM, EM, G_, RT_, false>(c, y0, k0, out, wt, partials, norm_out, seg_counts, store_always, n_rows, st))
+    return TDQ_GO(4, 16);
 #undef TDQ_GO
 }
 

@@ -745,4 +745,5 @@ def odeint(func, y0, t, *, rtol=1e-7, atol=1e-9, method=None, options=None, even
         _stats["launches"] = _stats.get("launches", 0) + getattr(eng, "launches", 0)
         _stats["attempts"] = getattr(eng, "n_attempts", None)
         _stats["n_accept"], _stats["n_reject"] = getattr(eng, "n_accept", None), getattr(eng, "n_reject", None)
+        _stats["fused_linear"], _stats["fused_attempt"] = _LAST_STATS["fused_linear"], _LAST_STATS["fused_attempt"]
     return _unflatten(p, sol)
