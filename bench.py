@@ -125,7 +125,9 @@ TRAFFIC_FUSED = {"bytes": 946.1e6, "source": "static: dram__bytes_read+write of 
                                                "(profiles/r2_ncu_full_fused_rows_summary.csv: reads 873 MB = the algorithmic reads, writes 73 MB -- most "
                                                "of the 268 MB written is still in L2 when a kernel ends); not measured by this run"}
 # the whole-attempt launch (k_linear_attempt): from the ncu --set full capture under profiles/
-TRAFFIC_ATTEMPT = {"bytes": None, "source": "see profiles/README.md (ncu --set full of k_linear_attempt)"}
+TRAFFIC_ATTEMPT = {"bytes": 82.8e6, "source": "static: dram__bytes_read.sum 67.4 MB (= y0 + k_0, the algorithmic reads) + dram__bytes_write.sum "
+                                                  "15.4 MB of one k_linear_attempt launch, ncu --set full (profiles/r2_ncu_full_k_linear_attempt_raw.csv): "
+                                                  "most of the 67 MB of candidates it writes is still in L2 when the launch ends; not measured by this run"}
 FULL_ATTEMPTS = 74         # step attempts of the full workload (reference, oracle and CUDA path agree)
 CPU_SAMPLE_T_END = 1.0     # the CPU sample integrates the FULL batch over t in [0, 1] (9 of the 74 attempts, + the start-up work)
 REF_DIR = os.path.join(ROOT, "baseline", "_ref")      # the unmodified reference, `pip install --target`

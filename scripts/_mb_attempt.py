@@ -56,17 +56,23 @@ def timeit(name, fn, reps=15):
 attempt_stages(0)
 torch.cuda.synchronize()
 ref = [k.clone() for k in ks] + [y1.clone(), er.clone(), eng.norm_out.clone()]
-for grp in ("3", "4", "5", "31", "41"):
-    os.environ["TDQ_ATTEMPT_GROUPS"] = grp
+for accs in ("", "1"):
+    if accs:
+        os.environ["TDQ_ATTEMPT_ACCS2"] = "1"
+    else:
+        os.environ.pop("TDQ_ATTEMPT_ACCS2", None)
     for k in ks:
         k.zero_()
     attempt_whole(0, 1, True)
     torch.cuda.synchronize()
     got = [k.clone() for k in ks] + [y1.clone(), er.clone(), eng.norm_out.clone()]
     ok = all(torch.equal(a_, b_) for a_, b_ in zip(got[:-1], ref[:-1]))
-    print("groups", grp, "bitwise", ok, "norm rel diff", float((got[-1][0] - ref[-1][0]).abs() / ref[-1][0]))
-    timeit("%s whole attempt [%s groups], norm folded, stages not stored" % (method, grp), lambda i: attempt_whole(i, 0, True))
-os.environ["TDQ_ATTEMPT_GROUPS"] = os.environ.get("MB_GROUPS", "4")
+    rel = max(float((a_ - b_).abs().max() / b_.abs().max()) for a_, b_ in zip(got[:-1], ref[:-1]))
+    print("split accumulators" if accs else "one accumulator pair", "bitwise", ok, "max rel diff", rel, "norm rel diff",
+          float((got[-1][0] - ref[-1][0]).abs() / ref[-1][0]))
+    timeit("%s whole attempt [%s], norm folded, stages not stored" % (method, "2 x (big, small)" if accs else "big, small"),
+           lambda i: attempt_whole(i, 0, True))
+os.environ.pop("TDQ_ATTEMPT_ACCS2", None)
 a = timeit("%s whole attempt, norm folded, stages not stored" % method, lambda i: attempt_whole(i, 0, True))
 b = timeit("%s whole attempt, norm folded, stages stored" % method, lambda i: attempt_whole(i, 1, True))
 c = timeit("%s whole attempt, no norm, stages stored" % method, lambda i: attempt_whole(i, 1, False))

@@ -16,6 +16,11 @@ def pytest_configure(config):
 def pytest_collection_modifyitems(config, items):
     import torch
     if torch.cuda.is_available():
+        # a hung kernel or a lost mailbox tick must cost minutes, not the default of forever
+        if config.pluginmanager.hasplugin("timeout"):
+            for item in items:
+                if "gpu" in item.keywords and item.get_closest_marker("timeout") is None:
+                    item.add_marker(pytest.mark.timeout(240))
         return
     skip = pytest.mark.skip(reason="no CUDA device")
     for item in items:

@@ -512,6 +512,10 @@ class AdaptiveEngine:
             spins += 1
             if spins > 2000:
                 time.sleep(0)            # let other Python threads run; the GPU work is independent
+                if spins % 20000 == 0 and torch.cuda.current_stream().query() and mb.seq < target:
+                    # everything that was queued has run and the attempt never reported: fail instead of spinning forever
+                    raise _lib.TdqError("the device finished the queued attempts without reporting attempt %d (mailbox at %d)"
+                                        % (target, mb.seq))
         return mb
 
     def _raise_if_failed(self, mb):

@@ -30,6 +30,7 @@
 #include "tdq_tc.cuh"
 #include "tdq_ctrl_dev.cuh"
 
+#include <cstdlib>
 #include <type_traits>
 
 namespace {
@@ -115,11 +116,18 @@ __host__ __device__ constexpr int popc_below(unsigned mask, int j) {
 // RT: rows of a tile per thread.  16: one warpgroup (4 warps) per tile; 8: two warpgroups per tile, each thread half the rows
 // (warps w and w + 4 own the same tensor-memory lanes and drain columns [0, 8) / [8, 16)): half the registers and half the
 // dependent work per thread, twice the warps to hide latencies with.
-template <int S, unsigned long long RM, unsigned EM, int G, int RT, bool CTRL>
+// ACCS: accumulators per partial product group (1: one small + one big; 2: the K steps alternate between two of each --
+// consecutive MMAs then never accumulate into the same tensor-memory tile).
+template <int S, unsigned long long RM, unsigned EM, int G, int RT, bool CTRL, int ACCS>
 __global__ void __launch_bounds__(G * 128 * (16 / RT), 1)
 k_linear_attempt(TdqCtrl *c, const float *y0, const float *k0, AttOut out, const uint32_t *__restrict__ wt,
                  double *partials, double *norm_out, const int64_t *seg_counts, int store_always, size_t n_rows_sz) {
-    if (c->halt) return;
+    if (c->halt) {
+        // An attempt issued after the end of the solve is a no-op -- but its controller step still has to tick the mailbox:
+        // a host that runs ahead (eager run_ahead, graph replay) accounts for every attempt it queued (tdq_ctrl_dev.cuh).
+        if (CTRL && blockIdx.x == 0) tdq_ctrl_dev::controller_block<float, G * 128 * (16 / RT)>(c, norm_out, seg_counts, 1, nullptr);
+        return;
+    }
     extern __shared__ uint8_t smem_raw[];
     uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     constexpr int AT_GROUPS = G, HN = AT_ROWS / RT, WPG = 4 * HN, AT_THREADS = G * 128 * HN;
@@ -202,7 +210,8 @@ k_linear_attempt(TdqCtrl *c, const float *y0, const float *k0, AttOut out, const
     const uint32_t sy0 = smem_u32(smem + AT_GROUPS * AT_STAGE + g * AT_Y0) + (uint32_t)(h * RT * LD + f) * 4;   // [row][feature]: this thread's rows, its column
     const uint32_t stage_u32 = smem_u32(stage);
     const uint32_t bar = bar0 + 8 * g;
-    const uint32_t acc_big = tmem + g * 32, acc_small = tmem + g * 32 + 16;
+    constexpr int ACOLS = 32 * ACCS;                                       // accumulator columns per group: ACCS x (big, small)
+    const uint32_t acc0 = tmem + g * ACOLS;                                // [big_0, small_0, (big_1, small_1)] x 16 columns
     uint32_t phase = 0;
     const uint32_t st_f = stage_u32 + (uint32_t)f * 16 + (uint32_t)(h * (RT / 8)) * AT_SBO;   // this thread's 16-byte slot of its first core-matrix row group
 
@@ -293,11 +302,11 @@ k_linear_attempt(TdqCtrl *c, const float *y0, const float *k0, AttOut out, const
                 constexpr int PW[NPROD] = {1, 2, 0, 1, 0, 0}, PY[NPROD] = {1, 0, 2, 0, 1, 0};
 #pragma unroll
                 for (int p = 0; p < NPROD; ++p) {
-                    const uint32_t dcol = p == NPROD - 1 ? acc_big : acc_small;
 #pragma unroll
                     for (int ks = 0; ks < 8; ++ks) {
+                        const uint32_t dcol = acc0 + (ks % ACCS) * 32 + (p == NPROD - 1 ? 0 : 16);
                         mma_ts(dcol, tmem + AT_COL_W + PW[p] * 64 + ks * 8, make_desc_mn(stage_u32 + PY[p] * AT_PLANE + ks * 2 * AT_LBO), IDESC16,
-                               (p == 0 || p == NPROD - 1) && ks == 0 ? 0u : 1u);
+                               (p == 0 || p == NPROD - 1) && ks < ACCS ? 0u : 1u);
                     }
                 }
                 mma_commit(bar);
@@ -412,14 +421,15 @@ k_linear_attempt(TdqCtrl *c, const float *y0, const float *k0, AttOut out, const
             // drain: the small accumulator first, then the big one on top of it (16 registers of staging, not 32)
             {
                 uint32_t tq[RT];
-                tmem_ldn<RT>(lane_base + (uint32_t)(g * 32 + 16 + h * RT), tq);
-                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
-                for (int r = 0; r < RT; ++r) KN[r] = __uint_as_float(tq[r]);
-                tmem_ldn<RT>(lane_base + (uint32_t)(g * 32 + h * RT), tq);
-                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                for (int a_ = 0; a_ < 2 * ACCS; ++a_) {
+                    // small_0, (small_1,) big_0 (, big_1): ascending magnitude
+                    const int col = (a_ < ACCS ? a_ * 32 + 16 : (a_ - ACCS) * 32) + h * RT;
+                    tmem_ldn<RT>(lane_base + (uint32_t)(g * ACOLS + col), tq);
+                    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
-                for (int r = 0; r < RT; ++r) KN[r] = KN[r] + __uint_as_float(tq[r]);
+                    for (int r = 0; r < RT; ++r) KN[r] = a_ == 0 ? __uint_as_float(tq[r]) : KN[r] + __uint_as_float(tq[r]);
+                }
             }
             if (store) {
 #pragma unroll
@@ -516,10 +526,10 @@ k_linear_attempt(TdqCtrl *c, const float *y0, const float *k0, AttOut out, const
 constexpr unsigned long long RM_DOPRI5 = 0x01ull | (0x03ull << 8) | (0x07ull << 16) | (0x0full << 24) | (0x1full << 32) | (0x3dull << 40);
 constexpr unsigned long long RM_BOSH3 = 0x01ull | (0x02ull << 8) | (0x07ull << 16);
 
-template <int S, unsigned long long RM, unsigned EM, int G, int RT, bool CTRL>
+template <int S, unsigned long long RM, unsigned EM, int G, int RT, bool CTRL, int ACCS>
 int launch_attempt_g(TdqCtrl *c, const float *y0, const float *k0, const AttOut &out, const uint32_t *wt, double *partials,
                      double *norm_out, const int64_t *seg_counts, int store_always, size_t n_rows, cudaStream_t st) {
-    auto kern = k_linear_attempt<S, RM, EM, G, RT, CTRL>;
+    auto kern = k_linear_attempt<S, RM, EM, G, RT, CTRL, ACCS>;
     constexpr int AT_SMEM = at_smem(G);
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM) != cudaSuccess) return -2;
     const size_t tiles = (n_rows + AT_ROWS - 1) / AT_ROWS;
@@ -537,9 +547,10 @@ int launch_attempt(TdqCtrl *c, const float *y0, const float *k0, const AttOut &o
     // Four tile pipelines of one warpgroup each, 16 rows per thread (128 registers).  Measured alternatives at 65,536 x 128,
     // dopri5 (profiles/README.md): 3 pipelines 106.6 us, 4: 96.1, 5 (96 registers, spills): 103.4; two warpgroups per tile
     // (8 rows per thread) 3 x 2: 102.2, 4 x 2: 102.0.
-#define TDQ_GO(G_, RT_) (seg_counts ? launch_attempt_g<S, RM, EM, G_, RT_, true>(c, y0, k0, out, wt, partials, norm_out, seg_counts, store_always, n_rows, st) \
-                                    : launch_attempt_g<S, RM, EM, G_, RT_, false>(c, y0, k0, out, wt, partials, norm_out, seg_counts, store_always, n_rows, st))
-    return TDQ_GO(4, 16);
+#define TDQ_GO(G_, RT_, A_) (seg_counts ? launch_attempt_g<S, RM, EM, G_, RT_, true, A_>(c, y0, k0, out, wt, partials, norm_out, seg_counts, store_always, n_rows, st) \
+                                        : launch_attempt_g<S, RM, EM, G_, RT_, false, A_>(c, y0, k0, out, wt, partials, norm_out, seg_counts, store_always, n_rows, st))
+    if (getenv("TDQ_ATTEMPT_ACCS2")) return TDQ_GO(4, 16, 2);            // experiment
+    return TDQ_GO(4, 16, 1);
 #undef TDQ_GO
 }
 
