@@ -30,7 +30,6 @@
 #include "tdq_tc.cuh"
 #include "tdq_ctrl_dev.cuh"
 
-#include <cstdlib>
 #include <type_traits>
 
 namespace {
@@ -546,10 +545,10 @@ int launch_attempt(TdqCtrl *c, const float *y0, const float *k0, const AttOut &o
                    double *norm_out, const int64_t *seg_counts, int store_always, size_t n_rows, cudaStream_t st) {
     // Four tile pipelines of one warpgroup each, 16 rows per thread (128 registers).  Measured alternatives at 65,536 x 128,
     // dopri5 (profiles/README.md): 3 pipelines 106.6 us, 4: 96.1, 5 (96 registers, spills): 103.4; two warpgroups per tile
-    // (8 rows per thread) 3 x 2: 102.2, 4 x 2: 102.0.
+    // (8 rows per thread) 3 x 2: 102.2, 4 x 2: 102.0.  Two accumulator pairs per tile (ACCS = 2: consecutive MMAs never
+    // accumulate into the same tensor-memory tile): 97.4 against 92.3 -- the MMA chain is not what paces a stage.
 #define TDQ_GO(G_, RT_, A_) (seg_counts ? launch_attempt_g<S, RM, EM, G_, RT_, true, A_>(c, y0, k0, out, wt, partials, norm_out, seg_counts, store_always, n_rows, st) \
                                         : launch_attempt_g<S, RM, EM, G_, RT_, false, A_>(c, y0, k0, out, wt, partials, norm_out, seg_counts, store_always, n_rows, st))
-    if (getenv("TDQ_ATTEMPT_ACCS2")) return TDQ_GO(4, 16, 2);            // experiment
     return TDQ_GO(4, 16, 1);
 #undef TDQ_GO
 }

@@ -130,7 +130,9 @@ template <typename T, int NK>
 int launch_fit(const TdqCtrl *c, const void *y1, const void *kS, const KPtrs &kmid, void *const *coeff, void *solution,
                size_t n, bool vec, cudaStream_t st) {
     size_t blocks = ((vec ? n / Vec<T>::N : n) + kThreads - 1) / kThreads;
-    const size_t cap = (size_t)tdq_sm_count() * 8;          // persistent: the usual no-op launch stays cheap
+    // persistent, two blocks per SM: 64 KB of loads in flight per SM saturate HBM when the fit runs, and the usual no-op
+    // launch (73 of 74 attempts of configs[1]) costs a few hundred blocks' worth of scheduling less
+    const size_t cap = (size_t)tdq_sm_count() * 2;
     if (blocks > cap) blocks = cap;
     if (blocks == 0) blocks = 1;
     T *co[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
