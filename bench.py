@@ -519,6 +519,12 @@ def run_ours(args):
                     "hbm": {"algorithmic_bytes_per_attempt": att_bytes, "achieved_gbs": att_bytes / (ams * 1e-3) / 1e9,
                             "frac_of_hbm_peak": att_bytes / (ams * 1e-3) / 1e9 / peak,
                             "note": "2 reads + 2 writes per element: the six launches it replaces moved 34 + 6 per element"},
+                    # SURVEY.md 8(d)'s algorithmic bytes of the stage combinations + error norm (40*N*s per attempt, what any
+                    # formulation that passes the stage values through memory must move) over this launch's time: above the
+                    # HBM peak, because the launch does not move them
+                    "vs_unfused_hbm_roofline": {"survey_algorithmic_bytes_per_attempt": comb_bytes + norm_bytes,
+                                                "effective_gbs": (comb_bytes + norm_bytes) / (ams * 1e-3) / 1e9,
+                                                "x_of_hbm_peak": (comb_bytes + norm_bytes) / (ams * 1e-3) / 1e9 / peak},
                     "replaces": {"launches": 7, "ms": fgms, "speedup": fgms / ams},
                     "stage_kernels": stage_roof, "generic_path_kernel": k_combine_roof}
             else:
