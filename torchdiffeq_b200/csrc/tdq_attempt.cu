@@ -3,8 +3,8 @@
 //
 // Why this is possible: for a linear field an attempt is ROW-LOCAL.  k_i = (y0 + sum_j coef_ij k_j) W^T needs nothing from
 // other state rows, so a tile of rows can be taken through all S stages without leaving the SM: y0 and the k_j stay in
-// registers, the stage value goes to shared memory as the B operand of tcgen05.mma (three bfloat16 planes, as in
-// tdq_linear.cu), the product comes back from tensor memory.  HBM sees 2 reads (y0, k_0) and 2 writes (the candidate pair
+// registers / shared memory, the stage value goes to shared memory as the B operand of tcgen05.mma (three bfloat16 planes,
+// as in tdq_linear.cu), the product comes back from tensor memory.  HBM sees 2 reads (y0, k_0) and 2 writes (the candidate pair
 // y1, k_S) per element and attempt instead of the 34 + 6 of six fused stage launches plus the norm launch (tdq_linear.cu,
 // tdq_norm.cu), and one launch instead of seven; the attempt becomes tensor bound (S x 6 bf16 products per element).
 // What rk_common.py:43-90 (_runge_kutta_step), misc.py:80-82 (_compute_error_ratio up to the mean) and the assignment
@@ -15,14 +15,17 @@
 // same accumulation order -- k_i, y1 and the error-sum prefix are BITWISE what tdq_linear_stage writes, (err/tol)^2 per
 // element bitwise what k_norm computes; only the order of the float64 sum over elements differs (tests/test_gpu_linear.py).
 //
-// Layout: 384 threads = 3 independent tile pipelines ("groups") of 4 warps, one CTA per SM.  A tile is 16 state rows x 128
+// Layout: 512 threads = 4 independent tile pipelines ("groups") of 4 warps, one CTA per SM.  A tile is 16 state rows x 128
 // features.  The accumulator is D^T (lane = output feature, column = state row; M = 128, N = 16), so thread (warp e, lane l)
-// of a group owns feature f = 32 e + l of all 16 rows: k_0..k_{S-1}[16] are 96 registers (dopri5; y0 sits in shared memory), a warp's
-// access to one row is 128 contiguous bytes of global memory, and the bf16 planes are written with 2-byte stores (32 lanes
-// = 64 contiguous bytes of a 128-byte swizzle row: conflict free).  Per stage a group does: combine + split + st.shared,
-// fence.proxy.async, bar.sync (its 128 threads), one thread issues 48 MMAs (weights stationary in tensor memory, 192
-// columns, shared by the groups) and a commit, everybody waits on the group's mbarrier and drains 2 x 16 columns.  The
-// chain of a tile is serial by nature (stage i+1 needs k_i); the three groups interleave, one hiding the other's latency.
+// of a group owns feature f = 32 e + l of all 16 rows: a warp's access to one row is 128 contiguous bytes of global memory, and
+// its 8 consecutive rows of one feature are one 16-byte vector of an MN-major core matrix of the B operand (6 st.shared.v4 per
+// stage).  State per thread: k_0..k_3 in registers (64), y0 in shared memory; once k_0..k_3 are known the remaining rows and the
+// error estimate are running sums that each later k_j is folded into.  Per stage a group does: newest term + split + st.shared,
+// fence.proxy.async, bar.sync (its 128 threads), one elected thread issues 48 MMAs (weights stationary in tensor memory, 192
+// columns, shared by the groups) and a commit; while they run, the prefix of the next row's sum; then everybody waits on the
+// group's mbarrier and drains 2 x 16 columns.  The chain of a tile is serial by nature (stage i+1 needs k_i); the four groups
+// interleave, one hiding the other's latency.  The last block to finish adds the per-block partials of the squared error norm
+// and runs the controller step (tdq_ctrl_dev.cuh).  Measurements and the variants tried: DESIGN.md section 3c.
 //
 // Stage derivatives, y1 and the error prefix are written to HBM only for attempts that can contain an output time (the
 // lazy interpolant fit needs them, tdq_interp.cu) or when the caller keeps every step (dense output, events).
@@ -45,7 +48,7 @@ constexpr int AT_Y0 = AT_ROWS * LD * 4;         // a tile's y0 (float32) stays i
 // G: tile pipelines (groups of 4 warps) per CTA
 constexpr int at_smem(int G) { return G * (AT_STAGE + AT_Y0) + AT_AUX + 1024; }
 constexpr int AT_TMEM_COLS = 512;
-constexpr int AT_COL_W = 256;                  // weights: 3 planes x 64 columns; accumulators of group g: [32 g, 32 g + 32)
+constexpr int AT_COL_W = 256;                  // weights: 3 planes x 64 columns; accumulators of group g: 32 ACCS columns from 32 ACCS g
 constexpr int AT_MAX_S = 7;
 constexpr uint32_t IDESC16 = tc_idesc(AT_ROWS) | (1u << 16);   // B (the stage planes) is MN-major: bit 16
 
@@ -63,8 +66,6 @@ __device__ __forceinline__ void sts_v4(uint32_t addr, uint32_t a, uint32_t b, ui
     asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" :: "r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
 }
 
-// explicit shared-space accesses with 32-bit addresses (a pointer derived from the aligned dynamic shared memory base is
-// generic to the compiler: 64-bit address registers and generic ST/LD otherwise)
 // A value that is zero at run time but depends on every element of `a`: added to the address of the mbarrier the group is
 // about to wait on, it forces the arithmetic of the MMA window to be issued BEFORE the wait (ptxas otherwise sinks part of it
 // below the wait, onto the critical path).  `zero` is a run-time zero the compiler cannot fold.  8 LOP3 per array.
@@ -89,6 +90,8 @@ __device__ __forceinline__ bool elect_one() {
     asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\t@p mov.s32 %0, 1;\n\t}\n" : "+r"(pred));
     return pred != 0;
 }
+// explicit shared-space accesses with 32-bit addresses (a pointer derived from the aligned dynamic shared memory base is
+// generic to the compiler: 64-bit address registers and generic ST/LD otherwise)
 __device__ __forceinline__ void sts_f32(uint32_t addr, float v) { asm volatile("st.shared.f32 [%0], %1;" :: "r"(addr), "f"(v) : "memory"); }
 __device__ __forceinline__ float lds_f32(uint32_t addr) {
     float v;
