@@ -22,3 +22,13 @@ python scripts/timeline.py > $OUT/timeline.txt
 python scripts/detest_sweep.py > $OUT/detest_sweep.jsonl
 nvcc -gencode arch=compute_100a,code=sm_100a -O3 --fmad=false -o $OUT/exp_combine scripts/exp_combine.cu && $OUT/exp_combine > $OUT/tma_sweep.txt
 # 4. multi-GPU (N = 2, 4, 8):  torchrun --nproc-per-node N scripts/dist_check.py ;  bench.py --gpus N [--scaling strong]
+
+# 5. the whole-attempt kernel (csrc/tdq_attempt.cu; profiles/r2_*attempt*).  Under ncu the controller step must be a launch of its
+#    own (--no-fused-controller): a kernel that carries a device-runtime call is skipped by kernel-level profiling.
+#   python bench.py --steps 10 --warmup 3                                  > r2_bench_n1_attempt.json
+#   python scripts/_mb_attempt.py                                          > r2_mb_attempt_variants.txt   (stand-alone launches, bitwise check first)
+#   B2="python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-device-loop --no-fused-controller"
+#   ncu --metrics gpu__time_duration.sum --clock-control none -c 3000 --csv --log-file r2_launches_bench_attempt.csv $B2
+#   ncu --set full --clock-control none --import-source on -k regex:k_linear_attempt --launch-skip 100 -c 1 -o k_linear_attempt -f $B2
+#   torchrun --nproc-per-node 2 bench.py --gpus 2 --steps 5 --warmup 3 --no-cpu-baseline                      > r2_bench_n2_attempt.json
+#   DIST_CHECK_ADJOINT=0 DIST_CHECK_ROWS_PER_RANK=2048 torchrun --nproc-per-node 2 scripts/dist_check.py      > r2_dist_check_n2_attempt.log

@@ -59,3 +59,34 @@ def test_no_cpu_fallback():
     y0 = torch.ones(3)
     with pytest.raises(tdq.TdqError):
         tdq.odeint(lambda t, y: -y, y0, torch.tensor([0., 1.]))
+
+
+def test_linear_attempt_host_side_contract():
+    """tdq_linear_attempt_supported is a pure host function of (tableau, dtype, width); tdq_linear_attempt validates its
+    arguments before it touches the device (csrc/tdq_attempt.cu)."""
+    import ctypes as C
+    from torchdiffeq_b200 import _lib
+    lib = _lib.load()
+    want = {"dopri5": 1, "bosh3": 1, "tsit5": 0, "dopri8": 0, "fehlberg2": 0, "adaptive_heun": 0}
+    for m, w in want.items():
+        tab = _lib.tableau(m)
+        assert lib.tdq_linear_attempt_supported(C.byref(tab), 0, 128) == w, m
+        assert lib.tdq_linear_attempt_supported(C.byref(tab), 1, 128) == 0          # float64
+        assert lib.tdq_linear_attempt_supported(C.byref(tab), 0, 64) == 0           # another width
+    assert lib.tdq_linear_attempt_supported(None, 0, 128) == 0
+    tab = _lib.tableau("dopri5")
+    bad = C.c_void_p(16)                                                             # never dereferenced: the checks come first
+    kp = _lib.ptr_array([None] + [16] * 6)
+    # null control block / float64 / state not a whole number of rows / norm outputs that do not go together /
+    # the controller step without the folded norm
+    assert lib.tdq_linear_attempt(None, C.byref(tab), 0, kp, bad, bad, None, None, bad, 128, 1280, None, None, None, 1, None) != 0
+    assert lib.tdq_linear_attempt(bad, C.byref(tab), 1, kp, bad, bad, None, None, bad, 128, 1280, None, None, None, 1, None) != 0
+    assert lib.tdq_linear_attempt(bad, C.byref(tab), 0, kp, bad, bad, None, None, bad, 128, 1281, None, None, None, 1, None) != 0
+    assert lib.tdq_linear_attempt(bad, C.byref(tab), 0, kp, bad, bad, None, None, bad, 128, 1280, bad, None, None, 1, None) != 0
+    assert lib.tdq_linear_attempt(bad, C.byref(tab), 0, kp, bad, bad, None, None, bad, 128, 1280, None, None, bad, 1, None) != 0
+    # a tableau the kernel does not take is refused as well
+    t8 = _lib.tableau("dopri8")
+    k8 = _lib.ptr_array([None] + [16] * 13)
+    assert lib.tdq_linear_attempt(bad, C.byref(t8), 0, k8, bad, bad, None, None, bad, 128, 1280, None, None, None, 1, None) != 0
+    # an empty state is a no-op that succeeds without a launch
+    assert lib.tdq_linear_attempt(bad, C.byref(tab), 0, kp, bad, bad, None, None, bad, 128, 0, None, None, None, 1, None) == 0
