@@ -183,3 +183,37 @@ def test_plugin_registration_and_seam_identification():
             plugin.unregister(rep)
             assert not isinstance(odeint_mod.SOLVERS["dopri5"], plugin._Dispatch)
             break
+
+
+def test_fused_linear_options_and_eligibility():
+    """The switches of the fused linear paths are options of this package (no 'Unexpected arguments' warning, misc.py:13-15),
+    and `fusable` (fields.py) only accepts an unmodified LinearField on a float32 [..., 128] state."""
+    import warnings
+    import torch
+    import torchdiffeq_b200 as tdq
+    from torchdiffeq_b200 import _lib
+    import importlib
+    O_ = importlib.import_module("torchdiffeq_b200.odeint")
+    from torchdiffeq_b200.fields import fusable
+
+    with warnings.catch_warnings(record=True) as w:
+        warnings.simplefilter("always")
+        O_._warn_unused("dopri5", {"fused_linear": False, "fused_attempt": False, "fused_controller": False, "run_ahead": 0}, set())
+        assert not w
+        O_._warn_unused("dopri5", {"not_an_option": 1}, set())
+        assert len(w) == 1 and "not_an_option" in str(w[0].message)
+
+    lib = _lib.load()
+    cpu = torch.device("cpu")
+    f = tdq.LinearField(torch.eye(128))
+    assert fusable(f, (7, 128), torch.float32, cpu, lib) is f.weight
+    assert fusable(f, (7, 128), torch.float64, cpu, lib) is None              # state dtype
+    assert fusable(f, (7, 64), torch.float32, cpu, lib) is None               # width
+    assert fusable(tdq.LinearField(torch.eye(64)), (7, 64), torch.float32, cpu, lib) is None   # no kernel for that width
+    assert fusable(lambda t, y: y, (7, 128), torch.float32, cpu, lib) is None
+
+    class Sub(tdq.LinearField):
+        def forward(self, t, y):
+            return super().forward(t, y) * 2.0
+
+    assert fusable(Sub(torch.eye(128)), (7, 128), torch.float32, cpu, lib) is None   # an overridden forward is never fused
