@@ -4,7 +4,10 @@ Kernel level, through the C ABI: the product against float64 (a float32-grade bo
 same inputs); the fused row against the unfused pair -- the stage value is formed with the same roundings, so
 tdq_linear_stage == tdq_linear_apply(tdq_stage_combine(...)) BITWISE, and the FSAL row's y1 / error prefix == tdq_stage_combine_final
 bitwise.  Solve level: the fused solve against the generic one (func as a torch call), against the oracle, and against the golden
-vectors of the unmodified reference for the configs[1]-shaped problem (rtol 1e-4 / atol 1e-6, the tolerance north_star states)."""
+vectors of the unmodified reference for the configs[1]-shaped problem (rtol 1e-4 / atol 1e-6, the tolerance north_star states).
+The whole-attempt kernel (csrc/tdq_attempt.cu, the default for dopri5 / bosh3, so every solve-level test above runs through it):
+tdq_linear_attempt == S x tdq_linear_stage + tdq_error_norm_commit (+ tdq_controller) BITWISE at the kernel level, and the solves
+it drives against the per-stage path in every execution mode."""
 import ctypes as C
 import os
 
